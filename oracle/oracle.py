@@ -1,0 +1,254 @@
+"""numpy/ctypes front end of the CPU ORACLE (oracle/libsei_oracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product
+package (scale-equivariant-imaging_b200/) never does and fails loudly without its CUDA
+library instead of falling back to anything here.
+
+Every function takes and returns C-contiguous numpy arrays; dtype float32 selects the
+fp32 instantiation of the C restatement (mimics the reference run in fp32), float64 the
+fp64 one.  The reference file:line each function follows is cited in
+oracle/sei_oracle_impl.h next to its C body.
+
+Parity pin: tests/test_oracle_golden.py compares every function with the fixtures in
+tests/golden/, which were produced by running the reference itself
+(tests/golden/make_golden.py).  The pieces of the path that live in the reference's
+un-vendored dependency deepinv v0.2.0 (GaussianNoise, EILoss, SupLoss, mse) are restated
+from its published behaviour and are pinned only through the reference's own call sites
+(losses, physics factory) as executed with tests/golden/deepinv_shim: parity for those
+is "unpinned" against upstream deepinv.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsei_oracle.so")
+_lib = None
+
+PAD_MODES = {"valid": 0, "circular": 1, "replicate": 2, "reflect": 3, "zero": 4}
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("sei_oracle.c", "sei_oracle_impl.h")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-B", "libsei_oracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        for sfx in ("f32", "f64"):
+            getattr(_lib, f"orc_sure_loss_{sfx}").restype = C.c_double
+            getattr(_lib, f"orc_mse_{sfx}").restype = C.c_double
+    return _lib
+
+
+def _sfx(a):
+    if a.dtype == np.float32:
+        return "f32", C.c_float
+    if a.dtype == np.float64:
+        return "f64", C.c_double
+    raise TypeError(f"oracle supports float32/float64, got {a.dtype}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype=None):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def named_kernel(name):
+    """physics/kernels.py get_kernel -> (k, k) float64."""
+    buf = np.zeros(64 * 64, dtype=np.float64)
+    k = lib().orc_named_kernel(name.encode(), _p(buf))
+    if k < 0:
+        raise ValueError(f"Unsupported kernel: {name}")
+    return buf[: k * k].reshape(k, k).copy()
+
+
+def blur_circular(x, kernel, adjoint=False):
+    """BlurV2.A / Blur(circular).A (adjoint=False) or their transpose (adjoint=True). x: (B,C,H,W)."""
+    x = _c(x)
+    sfx, _ = _sfx(x)
+    h = _c(kernel, x.dtype).reshape(kernel.shape[-2], kernel.shape[-1])
+    B, Cc, H, W = x.shape
+    if H < h.shape[0] or W < h.shape[1]:
+        raise ValueError("image smaller than the blur kernel")
+    y = np.empty_like(x)
+    getattr(lib(), f"orc_blur_circular_{sfx}")(_p(x), _p(y), C.c_long(B * Cc), H, W, _p(h), h.shape[0], h.shape[1], int(adjoint))
+    return y
+
+
+def conv_v1(x, filt, padding):
+    x = _c(x)
+    sfx, _ = _sfx(x)
+    f = _c(filt, x.dtype).reshape(filt.shape[-2], filt.shape[-1])
+    B, Cc, H, W = x.shape
+    ho, wo = C.c_int(), C.c_int()
+    mode = PAD_MODES[padding]
+    getattr(lib(), f"orc_conv_v1_out_size_{sfx}")(H, W, f.shape[0], f.shape[1], mode, C.byref(ho), C.byref(wo))
+    y = np.empty((B, Cc, ho.value, wo.value), dtype=x.dtype)
+    getattr(lib(), f"orc_conv_v1_{sfx}")(_p(x), _p(y), C.c_long(B * Cc), H, W, _p(f), f.shape[0], f.shape[1], mode)
+    return y
+
+
+def conv_transpose_v1(y, filt, padding):
+    y = _c(y)
+    sfx, _ = _sfx(y)
+    f = _c(filt, y.dtype).reshape(filt.shape[-2], filt.shape[-1])
+    B, Cc, H, W = y.shape
+    ho, wo = C.c_int(), C.c_int()
+    mode = PAD_MODES[padding]
+    getattr(lib(), f"orc_conv_transpose_v1_out_size_{sfx}")(H, W, f.shape[0], f.shape[1], mode, C.byref(ho), C.byref(wo))
+    x = np.empty((B, Cc, ho.value, wo.value), dtype=y.dtype)
+    getattr(lib(), f"orc_conv_transpose_v1_{sfx}")(_p(y), _p(x), C.c_long(B * Cc), H, W, _p(f), f.shape[0], f.shape[1], mode)
+    return x
+
+
+def down_aa(x, rate):
+    """Downsampling.A: antialiased bicubic decimation by `rate`."""
+    x = _c(x)
+    sfx, _ = _sfx(x)
+    B, Cc, H, W = x.shape
+    fn = getattr(lib(), f"orc_down_out_size_{sfx}")
+    y = np.empty((B, Cc, fn(H, rate), fn(W, rate)), dtype=x.dtype)
+    getattr(lib(), f"orc_down_aa_{sfx}")(_p(x), _p(y), C.c_long(B * Cc), H, W, rate)
+    return y
+
+
+def down_aa_vjp(gy, rate, in_hw):
+    """Transpose of down_aa (autograd backward of A / true adjoint). in_hw = (H, W) of x."""
+    gy = _c(gy)
+    sfx, _ = _sfx(gy)
+    B, Cc = gy.shape[:2]
+    H, W = in_hw
+    gx = np.empty((B, Cc, H, W), dtype=gy.dtype)
+    getattr(lib(), f"orc_down_aa_vjp_{sfx}")(_p(gy), _p(gx), C.c_long(B * Cc), H, W, rate)
+    return gx
+
+
+def up_bicubic(y, rate):
+    """Downsampling.A_adjoint with true_adjoint=False: plain bicubic upsample."""
+    y = _c(y)
+    sfx, _ = _sfx(y)
+    B, Cc, h, w = y.shape
+    x = np.empty((B, Cc, h * rate, w * rate), dtype=y.dtype)
+    getattr(lib(), f"orc_up_bicubic_{sfx}")(_p(y), _p(x), C.c_long(B * Cc), h, w, rate)
+    return x
+
+
+def scale_grid(B, S, rate, center, dtype):
+    rate = _c(rate, dtype).reshape(B)
+    center = _c(center, dtype).reshape(B, 2)
+    grid = np.empty((B, S, S, 2), dtype=dtype)
+    sfx, _ = _sfx(grid)
+    getattr(lib(), f"orc_scale_grid_{sfx}")(_p(grid), B, S, _p(rate), _p(center))
+    return grid
+
+
+def scale_transform(x, rate, center):
+    """padded_downsampling_transform(x, rate, center, 'bicubic', 'reflection', antialiased=False)."""
+    x = _c(x)
+    sfx, _ = _sfx(x)
+    B, Cc, S, S2 = x.shape
+    if S != S2:
+        raise ValueError("the scale transform is defined for square images only")
+    rate = _c(rate, x.dtype).reshape(B)
+    center = _c(center, x.dtype).reshape(B, 2)
+    out = np.empty_like(x)
+    getattr(lib(), f"orc_scale_transform_{sfx}")(_p(x), _p(out), B, Cc, S, _p(rate), _p(center))
+    return out
+
+
+def sample_params_from_uniforms(u_rate, u_center, rates=(0.75, 0.5)):
+    """sample_from + sample_downsampling_parameters (src/transforms.py:5-24) given the two
+    uniform draws (shape (B,) then (B, 2)) the reference takes from torch.rand, in order."""
+    dt = u_rate.dtype
+    values = np.asarray(rates, dtype=dt)
+    idx = np.floor(dt.type(len(rates)) * u_rate).astype(np.int32)
+    rate = values[idx]
+    center = (dt.type(2) * u_center - dt.type(1)).reshape(-1, 1, 1, 2)
+    return rate, center
+
+
+def add_noise(y, n, sigma):
+    y = _c(y)
+    sfx, ct = _sfx(y)
+    n = _c(n, y.dtype)
+    out = np.empty_like(y)
+    getattr(lib(), f"orc_add_noise_{sfx}")(_p(y), _p(n), _p(out), C.c_long(y.size), ct(sigma))
+    return out
+
+
+def sure_loss(y1, y2, y, b, margin_mse, margin_div, tau, sigma2, averaged_cst):
+    y1 = _c(y1)
+    sfx, _ = _sfx(y1)
+    y2, y, b = _c(y2, y1.dtype), _c(y, y1.dtype), _c(b, y1.dtype)
+    B, Cc, H, W = y1.shape
+    mse, div = C.c_double(), C.c_double()
+    loss = getattr(lib(), f"orc_sure_loss_{sfx}")(
+        _p(y1), _p(y2), _p(y), _p(b), B, Cc, H, W, int(margin_mse), int(margin_div),
+        C.c_double(tau), C.c_double(sigma2), int(bool(averaged_cst)), C.byref(mse), C.byref(div))
+    return loss, mse.value, div.value
+
+
+def mse(a, b):
+    a = _c(a)
+    sfx, _ = _sfx(a)
+    b = _c(b, a.dtype)
+    return getattr(lib(), f"orc_mse_{sfx}")(_p(a), _p(b), C.c_long(a.size))
+
+
+# ---------------------------------------------------------------------------------------
+# Loss assembly (src/losses/__init__.py:67-142, src/losses/sure.py, deepinv EILoss) with the
+# network supplied as a callable and every random tensor supplied by the caller.
+# ---------------------------------------------------------------------------------------
+class OraclePhysics:
+    """A (and its transpose) of either task, in the oracle."""
+
+    def __init__(self, task, kernel=None, rate=None, sigma=5 / 255):
+        self.task, self.kernel, self.rate, self.sigma = task, kernel, rate, sigma
+
+    def A(self, x):
+        if self.task == "deblurring":
+            return blur_circular(x, self.kernel)
+        return down_aa(x, self.rate)
+
+    def A_vjp(self, gy, in_hw=None):
+        if self.task == "deblurring":
+            return blur_circular(gy, self.kernel, adjoint=True)
+        return down_aa_vjp(gy, self.rate, in_hw)
+
+
+def proposed_loss(physics, model, y, draws, margin, cropped_div=True, averaged_cst=None,
+                  alpha=1.0, tau=1e-2, sure_sigma=5 / 255):
+    """ProposedLoss.forward for transforms="Scaling_Transforms", stop_gradient=True.
+    draws = dict(b=..., u_rate=..., u_center=..., noise=...) in the reference's draw order
+    (SURVEY.md section 3.1).  Returns the loss and the intermediates the tests compare."""
+    # SureGaussianLoss gets sigma = noise_level/255 as a Python float (src/losses/__init__.py:104),
+    # while the noise model holds it as a float32 Parameter (deepinv GaussianNoise)
+    sigma2 = sure_sigma ** 2
+    x_net = model(y)
+    y1 = physics.A(x_net)
+    b = draws["b"]
+    x_net2 = model(y + b * y.dtype.type(tau))
+    y2 = physics.A(x_net2)
+    margin_div = margin if cropped_div else 0
+    l_sure, mse_v, div_v = sure_loss(y1, y2, y, b, margin, margin_div, tau, sigma2, averaged_cst)
+    rate, center = sample_params_from_uniforms(draws["u_rate"], draws["u_center"])
+    x2 = scale_transform(x_net, rate, center)
+    y_ei = add_noise(physics.A(x2), draws["noise"], physics.sigma)
+    x3 = model(y_ei)
+    l_ei = alpha * mse(x3, x2)
+    return dict(loss=l_sure + l_ei, loss_sure=l_sure, loss_ei=l_ei, mse=mse_v, div=div_v,
+                x_net=x_net, x_net2=x_net2, x2=x2, y_ei=y_ei, x3=x3, y1=y1, y2=y2)
