@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- SEI training imgs/sec @256x256 on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch: the reference's `proposed` training step
+(demo/train.py:258-268: zero_grad, loss(x, y, model) with SURE + equivariant terms, backward,
+optimizer step) on the workload BASELINE.json's configs[1] names: deblurring Gaussian_R2,
+synthetic 256x256 RGB crops, batch 32 per GPU.  Physics, scale transform and loss reductions run
+in the libsei_b200 kernels behind the reference's own Python API (physics.get_physics,
+losses.get_loss).  See `config.network` in the output for the network the step drives.
+
+Prints ONE JSON line (rank 0).  --impl reference times the CPU restatement of the same step
+(oracle/, the reference is pure Python and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "scale-equivariant-imaging_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH, SIZE, CH = 32, 256, 3
+KERNEL, NOISE_LEVEL, MARGIN = "Gaussian_R2", 5, 6
+WORKLOAD = f"deblurring {KERNEL} method=proposed, synthetic {SIZE}x{SIZE} RGB crops, batch {BATCH} per GPU (BASELINE configs[1])"
+
+
+def loss_args():
+    from argparse import Namespace
+    return Namespace(task="deblurring", noise_level=NOISE_LEVEL, physics_v2=True, kernel=KERNEL, sr_factor=None,
+                     physics_true_adjoint=False, partial_sure=True, sure_margin=None, partial_sure_sr=False,
+                     Loss__crop_training_pairs=False, Loss__crop_size=48, ProposedLoss__stop_gradient=True,
+                     ProposedLoss__sure_alternative=None, ProposedLoss__alpha_tradeoff=1.0,
+                     ProposedLoss__transforms="Scaling_Transforms", ScalingTransform__kind="padded",
+                     ScalingTransform__antialias=False, method="proposed", sure_cropped_div=True,
+                     sure_averaged_cst=None)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    import losses
+    import physics
+    import sei_b200
+    from sei_b200 import ops
+    from toy_model import ToyModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sei_b200 hot path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    torch.manual_seed(0 + rank)
+    largs = loss_args()
+    phys = physics.get_physics(largs, device=dev)
+    loss_fn = losses.get_loss(largs, phys)
+    model = ToyModel(rate=1).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=True)
+    params = [p for p in model.parameters()]
+
+    # synthetic data: NBUF resident batches (x ~ U[0,1), y = A x + sigma n) -> 2*NBUF*25 MB > L2 (126 MB)
+    NBUF = 8
+    xs = [torch.rand(BATCH, CH, SIZE, SIZE, device=dev) for _ in range(NBUF)]
+    ys = [phys(x) for x in xs]
+    host_x = [x.cpu().pin_memory() for x in xs[:2]]
+    host_y = [y.cpu().pin_memory() for y in ys[:2]]
+    x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    loss_static = torch.zeros((), device=dev)
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def fwd_bwd():
+        opt.zero_grad(set_to_none=False)
+        loss = loss_fn(x=x_static, y=y_static, model=model)
+        loss.backward()
+        loss_static.copy_(loss.detach())
+
+    def allreduce_grads():
+        if world > 1:
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat_grad)
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat_grad[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    # capture forward+backward and the optimizer step as CUDA graphs (the step is ~40 small launches)
+    use_graph = not args.no_graph
+    g_fb = g_opt = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        x_static.copy_(xs[0]); y_static.copy_(ys[0])
+        for _ in range(3):
+            fwd_bwd(); allreduce_grads(); opt.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb, stream=side):
+                fwd_bwd()
+            with torch.cuda.graph(g_opt, stream=side):
+                opt.step()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            g_fb = g_opt = None
+            torch.cuda.synchronize()
+
+    n_before = sei_b200.launch_count()
+    fwd_bwd()
+    launches_per_step = sei_b200.launch_count() - n_before
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        x_static.copy_(xs[i % NBUF]); y_static.copy_(ys[i % NBUF])
+        if g_fb is not None:
+            g_fb.replay(); allreduce_grads(); g_opt.replay()
+        else:
+            fwd_bwd(); allreduce_grads(); opt.step()
+
+    def step_e2e(i):
+        x_static.copy_(host_x[i % 2], non_blocking=True); y_static.copy_(host_y[i % 2], non_blocking=True)
+        if g_fb is not None:
+            g_fb.replay(); allreduce_grads(); g_opt.replay()
+        else:
+            fwd_bwd(); allreduce_grads(); opt.step()
+        return float(loss_static.item())       # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_step = timed(step_resident, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    clock_summary = clocks.stop() if rank == 0 else None
+    final_loss = float(loss_static.item())
+    assert np.isfinite(final_loss), "loss diverged"
+
+    # roofline of the dominant kernel (blur_band_kernel: 5 of the step's operator launches): timed back to
+    # back over a rotating set of inputs larger than L2, CUDA events on the launching stream
+    roofline = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        khost = phys._kernel_host
+        big = [torch.rand(BATCH * 4, CH, SIZE, SIZE, device=dev) for _ in range(3)]   # 3 x 100 MB in, +100 MB out
+        for b_ in big:
+            ops.blur_circular(b_, khost)
+        torch.cuda.synchronize()
+        reps = 30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            ops.blur_circular(big[i % 3], khost)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        alg_bytes = 8.0 * big[0].numel()
+        achieved = alg_bytes / (us * 1e-6) / 1e9
+        roofline = {"kernel": "blur_band_kernel<13> (circular Gaussian_R2 blur, A / A^T)", "bound": "hbm",
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "us_per_launch": round(us, 2),
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "how": f"{reps} back-to-back launches on {BATCH * 4}x{CH}x{SIZE}x{SIZE} fp32, 3 rotating inputs (400 MB > L2)"}
+        del big
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_reference_sample(seconds_budget=20.0)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    imgs = BATCH * world
+    out = {
+        "metric": "SEI training imgs/sec @256x256 (proposed step)", "value": round(imgs / (ms_step * 1e-3), 2),
+        "unit": "imgs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "network": "4-parameter pointwise stand-in (tests/toy_model.py): this line measures the "
+                              "operator + loss-assembly path (3 A, 2 A^T, fused T->A->noise, SURE/MSE reductions, Adam); "
+                              "the restoration CNN is not in this line",
+                   "global_batch": imgs, "parallelism": f"dp{world}", "cuda_graph": g_fb is not None,
+                   "l2": f"inputs rotate over {NBUF} resident batches ({2 * NBUF * 25} MB > 126 MB L2)",
+                   "final_loss": final_loss},
+        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "imgs/s", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": int(2 * xs[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "how": "losses.get_loss(...)(x, y, model) + backward + Adam from pinned host x,y; loss.item() each step"},
+        "gpu_launches": int(launches_per_step * args.steps * 2),
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------- CPU restatement arm
+def reference_step_factory(batch):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    kern = orc.named_kernel(KERNEL)
+    phys = orc.OraclePhysics("deblurring", kernel=kern, sigma=float(np.float32(NOISE_LEVEL / 255)))
+    x = rng.random((batch, CH, SIZE, SIZE), dtype=np.float32)
+    y = orc.add_noise(phys.A(x), rng.standard_normal(x.shape).astype(np.float32), phys.sigma)
+    w, c = np.array([0.8, 0.15, 0.05], np.float32), np.float32(0.01)
+
+    def step():
+        b = np.zeros_like(y)
+        b[:, :, MARGIN:-MARGIN, MARGIN:-MARGIN] = rng.standard_normal((batch, CH, SIZE - 2 * MARGIN, SIZE - 2 * MARGIN)).astype(np.float32)
+        draws = dict(b=b, u_rate=rng.random(batch, dtype=np.float32), u_center=rng.random((batch, 2), dtype=np.float32),
+                     noise=rng.standard_normal(y.shape).astype(np.float32))
+        out = orc.proposed_step(phys, w, c, y, draws, MARGIN)
+        return out["loss"]
+
+    return step
+
+
+def run_reference_sample(seconds_budget=20.0, batch=None, steps=None, warmup=1):
+    """Time the CPU restatement of the step (oracle/, OpenMP over all host cores) on a bounded sample."""
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    batch = batch or 8
+    step = reference_step_factory(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    n = steps or max(1, min(10, int(seconds_budget / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return {"value": round(batch / dt, 3), "unit": "imgs/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of the same proposed step on a batch of {batch} {SIZE}x{SIZE} RGB crops "
+                      f"(oracle/ C restatement, OpenMP {cores} threads), {dt * 1e3:.1f} ms/step",
+            "ms_per_step": round(dt * 1e3, 2), "batch": batch}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    base = run_reference_sample(batch=8, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    out = {"impl": "reference", "metric": "SEI training imgs/sec @256x256 (proposed step)", "value": base["value"],
+           "unit": "imgs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "network": "4-parameter pointwise stand-in (same as the B200 arm)",
+                      "global_batch": base["batch"], "parallelism": "cpu"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+/*
+ * sei_b200.h -- C ABI of libsei_b200.so: the B200 (sm_100a) implementation of the
+ * Scale-Equivariant-Imaging per-step hot path (degradation physics forward/adjoint,
+ * random scale transform, loss reductions).
+ *
+ * The reference (jscanvic/Scale-Equivariant-Imaging, pure Python/PyTorch) has no FFI; its
+ * boundary for this path is the Python object protocol of src/physics, src/transforms.py
+ * and src/losses.  Each entry point below replaces the torch
+ * library call(s) cited next to it, and is what the reference-side binding in
+ * INTEGRATION.md (a ctypes stub inside the reference's own classes) would bind.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  All image tensors are float32,
+ *    NCHW, contiguous; `planes` = B*C independent H x W planes.
+ *  - the caller owns every buffer (inputs, outputs, workspaces).  The library never
+ *    allocates or frees device memory and keeps no pointer after a call returns.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ *    the legacy default stream) and is CUDA-graph capturable.
+ *  - return value: 0 on success; SEI_EINVAL for an unsupported argument; otherwise a
+ *    positive cudaError_t.  sei_last_error() gives a thread-local message.  There is no
+ *    CPU fallback: without a CUDA device every compute call fails.
+ *  - pointers named *_host are read on the host during the call; all others are
+ *    device pointers.
+ */
+#ifndef SEI_B200_H
+#define SEI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEI_ABI_VERSION 1
+#define SEI_EINVAL (-22)
+
+/* path selectors for the operators that have a tiled (TMA row-band) and a direct kernel */
+#define SEI_PATH_AUTO 0
+#define SEI_PATH_DIRECT 1
+#define SEI_PATH_TILED 2
+
+int sei_abi_version(void);
+const char* sei_last_error(void);
+/* name of the kernel variant the last call on this thread launched ("" if none) */
+const char* sei_last_kernel(void);
+/* number of kernels this library has launched from this process (all threads) */
+long long sei_launch_count(void);
+/* 0 if a CUDA device with compute capability 10.x is current; fills the out-params */
+int sei_device_info(int* sm_count, int* smem_per_block_optin, int* cc_major, int* cc_minor);
+
+/* ---- degradation physics -------------------------------------------------------------
+ * Circular blur: BlurV2.A (reference src/physics/blur/__init__.py:205-223, the rfft2 /
+ * multiply / irfft2 sequence) and Blur(padding="circular").A (:34-74, the per-(b,c)
+ * F.conv2d loop):           y[n] = sum_i h[i] x[(n - i + k//2) mod N]  on both axes.
+ * adjoint != 0: the transpose, i.e. autograd backward of A, BlurV2.A_adjoint (:225-227)
+ * and conv_transpose(.., "circular") (:77-134).
+ * kernel_host: kh x kw taps, row-major, double (the reference keeps the kernel in
+ * float64 and casts to the image dtype per call).  If noise != NULL the deepinv
+ * GaussianNoise step attached at src/physics/__init__.py:53 is fused:
+ * y += sigma * noise (noise: device, same shape as y, standard normal draws).
+ * Requires H >= kh and W >= kw (the reference fails otherwise as well). */
+int sei_blur_circular_f32(const float* x, float* y, long long planes, int H, int W,
+                          const double* kernel_host, int kh, int kw, int adjoint,
+                          const float* noise, float sigma, int path, void* stream);
+
+/* v1 operator with the non-default paddings (src/physics/blur/__init__.py:34-161).
+ * mode: 0 valid, 1 circular, 2 replicate, 3 reflect, 4 zero (transpose only).
+ * transpose == 0: conv(x, filter, padding);  != 0: conv_transpose(y, filter, padding).
+ * H, W are the INPUT plane sizes; the output plane size is written to Ho/Wo
+ * (call with out == NULL to query the size only). */
+int sei_blur_padded_f32(const float* in, float* out, long long planes, int H, int W,
+                        const double* filter_host, int fh, int fw, int mode, int transpose,
+                        int* Ho, int* Wo, void* stream);
+
+/* SR forward: Downsampling.A (src/physics/downsampling/__init__.py:16-19) =
+ * F.interpolate(x, scale_factor=1/rate, mode="bicubic", antialias=True).
+ * x: planes x H x W  ->  y: planes x floor(H/rate) x floor(W/rate).  Optional fused noise. */
+int sei_down_aa_f32(const float* x, float* y, long long planes, int H, int W, int rate,
+                    const float* noise, float sigma, int path, void* stream);
+/* transpose of the above (autograd backward of A; true_adjoint=True, :21-31).
+ * gy: planes x floor(H/rate) x floor(W/rate)  ->  gx: planes x H x W. */
+int sei_down_aa_transpose_f32(const float* gy, float* gx, long long planes, int H, int W,
+                              int rate, int path, void* stream);
+/* Downsampling.A_adjoint with true_adjoint=False (:32-35): plain bicubic upsample,
+ * F.interpolate(y, scale_factor=rate, mode="bicubic").  y: planes x h x w -> planes x h*rate x w*rate */
+int sei_up_bicubic_f32(const float* y, float* x, long long planes, int h, int w, int rate,
+                       void* stream);
+
+/* ---- scale transform -----------------------------------------------------------------
+ * padded_downsampling_transform (src/transforms.py:60-83) with mode="bicubic",
+ * padding_mode="reflection", antialiased=False: builds the grid of
+ * get_downsampling_grid (:27-43) analytically and applies
+ * F.grid_sample(align_corners=True).  x, out: B x C x S x S (square only, like the
+ * reference).  rate: B floats, center: B x 2 floats (cx, cy), both DEVICE pointers
+ * (they are drawn on the device; no host sync). */
+int sei_scale_transform_f32(const float* x, float* out, int B, int C, int S,
+                            const float* rate, const float* center, int path, void* stream);
+/* sample_from + sample_downsampling_parameters (src/transforms.py:5-24) given the two
+ * uniform draws u_rate (B) and u_center (B x 2):
+ *   rate_b = rates[floor(n_rates * u_rate_b)],  center_b = 2 * u_center_b - 1. */
+int sei_scale_params_f32(const float* u_rate, const float* u_center, int B,
+                         const float* rates_host, int n_rates, float* rate, float* center,
+                         void* stream);
+
+/* Fused EI re-measurement (deepinv EILoss.forward as built at
+ * src/losses/__init__.py:117-122, steps x2 = T(x_net); y = physics(x2)):
+ *   x2 = scale_transform(x_net),  y_out = A(x2) + sigma * noise
+ * in one kernel, so x2 is written once and never re-read from HBM.
+ * Deblurring: rate_sr = 1 and kernel_host != NULL (circular blur).
+ * SR: rate_sr in {2,3,4} and kernel_host == NULL (antialiased bicubic decimation).
+ * x_net, x2: B x C x S x S;  y_out, noise: B x C x S/rate_sr x S/rate_sr. */
+int sei_ei_remeasure_f32(const float* x_net, float* x2, float* y_out, int B, int C, int S,
+                         const float* rate, const float* center,
+                         const double* kernel_host, int kh, int kw, int rate_sr,
+                         const float* noise, float sigma, void* stream);
+
+/* ---- loss reductions -----------------------------------------------------------------
+ * All reductions are deterministic (fixed-order two-stage tree, double accumulation of
+ * the per-block partials).  `workspace` must hold sei_reduce_workspace_bytes() bytes. */
+long long sei_reduce_workspace_bytes(void);
+
+/* nn.MSELoss (deepinv metric.mse; EILoss / SupLoss):  out[0] = mean((a-b)^2) */
+int sei_mse_f32(const float* a, const float* b, long long n, float* out, void* workspace,
+                void* stream);
+/* backward: ga = gscale[0] * 2/n * (a-b);  gb = -ga if gb != NULL.  gscale: device scalar */
+int sei_mse_backward_f32(const float* a, const float* b, long long n, const float* gscale,
+                         float* ga, float* gb, void* stream);
+
+/* SureGaussianLoss.forward + mc_div (src/losses/sure.py:7-76) given y1 = A(x_net),
+ * y2 = A(model(y + tau*b)):
+ *   mse = mean_{interior(margin_mse)} (y1-y)^2
+ *   div = mean_{interior(margin_div)} b*(y2-y1)/tau
+ *   out[0] = mse + 2*sigma2*div - (averaged_cst ? sigma2 : sigma2/B); out[1] = mse; out[2] = div */
+int sei_sure_loss_f32(const float* y1, const float* y2, const float* y, const float* b,
+                      int B, int C, int H, int W, int margin_mse, int margin_div,
+                      float tau, float sigma2, int averaged_cst, float* out, void* workspace,
+                      void* stream);
+/* backward: g1 = d loss / d y1, g2 = d loss / d y2 (scaled by gscale[0]) */
+int sei_sure_loss_backward_f32(const float* y1, const float* y, const float* b,
+                               int B, int C, int H, int W, int margin_mse, int margin_div,
+                               float tau, float sigma2, const float* gscale,
+                               float* g1, float* g2, void* stream);
+
+/* mc_div's probe (sure.py:8-24): out = y + tau * b, where b is `draw` placed in the
+ * interior (margin wide border of zeros) -- draw: B x C x (H-2m) x (W-2m) (or y-shaped if
+ * margin == 0).  b_out (optional) receives the zero-bordered b. */
+int sei_sure_perturb_f32(const float* y, const float* draw, int B, int C, int H, int W,
+                         int margin, float tau, float* out, float* b_out, void* stream);
+
+/* deepinv GaussianNoise.forward: out = y + sigma * noise */
+int sei_add_noise_f32(const float* y, const float* noise, long long n, float sigma, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEI_B200_H */

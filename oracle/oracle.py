@@ -252,3 +252,50 @@ def proposed_loss(physics, model, y, draws, margin, cropped_div=True, averaged_c
     l_ei = alpha * mse(x3, x2)
     return dict(loss=l_sure + l_ei, loss_sure=l_sure, loss_ei=l_ei, mse=mse_v, div=div_v,
                 x_net=x_net, x_net2=x_net2, x2=x2, y_ei=y_ei, x3=x3, y1=y1, y2=y2)
+
+
+def pointwise_model(w, c, rate=1):
+    """The 4-parameter stand-in network of tests/toy_model.py in numpy, plus its parameter gradient."""
+
+    def up(v):
+        return np.repeat(np.repeat(v, rate, axis=-2), rate, axis=-1) if rate != 1 else v
+
+    def fwd(v):
+        u = up(v)
+        dt = u.dtype.type
+        return dt(w[0]) * u + dt(w[1]) * np.roll(u, (1, 2), (-2, -1)) + dt(w[2]) * u * u + dt(c)
+
+    def param_grad(v, g):
+        u = up(v).astype(np.float64)
+        g = g.astype(np.float64)
+        return np.array([(g * u).sum(), (g * np.roll(u, (1, 2), (-2, -1))).sum(), (g * u * u).sum()]), g.sum()
+
+    return fwd, param_grad
+
+
+def proposed_step(physics, w, c, y, draws, margin, rate=1, alpha=1.0, tau=1e-2, sure_sigma=5 / 255):
+    """One 'proposed' training step of the reference (loss forward AND backward to the network
+    parameters; demo/train.py:258-266 with src/losses) for the stand-in network: the CPU
+    restatement that bench.py times as cpu_baseline / --impl reference."""
+    fwd, pgrad = pointwise_model(w, c, rate)
+    out = proposed_loss(physics, fwd, y, draws, margin, alpha=alpha, tau=tau, sure_sigma=sure_sigma)
+    dt = y.dtype.type
+    B, C, H, W = y.shape
+    n_int = B * C * (H - 2 * margin) * (W - 2 * margin)
+    mask = np.zeros_like(y)
+    mask[:, :, margin:H - margin, margin:W - margin] = 1
+    k = dt(2.0 * sure_sigma ** 2 / (tau * n_int))
+    g_y2 = k * draws["b"] * mask
+    g_y1 = dt(2.0 / n_int) * (out["y1"] - y) * mask - g_y2
+    in_hw = out["x_net"].shape[-2:]
+    g_xnet = physics.A_vjp(g_y1, in_hw)
+    g_xnet2 = physics.A_vjp(g_y2, in_hw)
+    g_x3 = dt(2.0 * alpha / out["x3"].size) * (out["x3"] - out["x2"])
+    gw = np.zeros(3)
+    gc = 0.0
+    for v, g in ((y, g_xnet), (y + draws["b"] * dt(tau), g_xnet2), (out["y_ei"], g_x3)):
+        a, b_ = pgrad(v, g)
+        gw += a
+        gc += b_
+    out.update(grad_w=gw, grad_c=gc, g_xnet=g_xnet, g_xnet2=g_xnet2, g_x3=g_x3)
+    return out

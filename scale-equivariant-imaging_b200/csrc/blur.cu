@@ -1,0 +1,222 @@
+// blur.cu -- circular blur A / A^T (reference: src/physics/blur/__init__.py BlurV2.A :205-223,
+// Blur(padding="circular") :34-74/:164-194, adjoints :77-134/:225-227).
+//
+// Tiled kernel (blur_band_kernel): one CTA owns a full-width band of TH output rows of one
+// plane.  The TH+2P input rows (circular in y) are contiguous runs of global memory, so they are
+// staged into shared memory by 1..3 bulk async copies on the TMA engine (UBLKCP) completing on
+// an mbarrier; the horizontal wrap-around is free because whole rows are resident.  The kernel is
+// separable: a vertical pass (register-blocked, 8 output rows x 4 columns per thread, taps as
+// constant-bank operands) writes an intermediate band to shared memory, a horizontal pass
+// (4 outputs per thread from 128-bit shared loads) produces the result, adds the optional
+// sigma * noise epilogue and stores with 128-bit writes.  HBM traffic = 4 B read + 4 B written
+// per element (halo rows are re-read from L2, not DRAM).
+//
+// Direct kernel (blur_direct_kernel): any shape / any (also non-separable, even-sized) kernel,
+// one thread per output element, taps in the constant bank.
+#include "tile_ops.cuh"
+#include <algorithm>
+#include <stdlib.h>
+
+namespace sei {
+
+constexpr int kBandThreads = 256;
+
+struct BlurBandParams {
+    const float* x;
+    float* y;
+    const float* noise;
+    float sigma;
+    int H, W, TH, nbands;
+    float cv[kMaxK];   // correlation-form taps: y[n] = sum_t c[t] x[n + t - P]
+    float ch[kMaxK];
+};
+
+template <int K, bool NOISE>
+__global__ void __launch_bounds__(kBandThreads, 2) blur_band_kernel(const __grid_constant__ BlurBandParams p)
+{
+    constexpr int P = K / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+
+    const int H = p.H, W = p.W;
+    const int band = blockIdx.x % p.nbands;
+    const long long plane = blockIdx.x / p.nbands;
+    const int r0 = band * p.TH;
+    const int th = min(p.TH, H - r0);
+    const int rin = th + 2 * P;
+
+    float* sIn = reinterpret_cast<float*>(smem_raw);      // [TH + 2P][W]
+    float* sMid = sIn + (size_t)(p.TH + 2 * P) * W;       // [TH][W]
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t row_bytes = (uint32_t)W * 4u;
+        mbar_arrive_expect_tx(&bar, (uint32_t)rin * row_bytes);
+        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sIn),
+                                reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * H * W), H, row_bytes,
+                                r0 - P, rin, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    blur_vpass<K, kBandThreads>(sIn, sMid, W, th, p.cv);
+    __syncthreads();
+    const size_t row0 = ((size_t)plane * H + r0) * W;
+    blur_hpass<K, kBandThreads, NOISE>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
+}
+
+struct BlurDirectParams {
+    const float* x;
+    float* y;
+    const float* noise;
+    float sigma;
+    int H, W, kh, kw, adjoint;
+    long long total;
+    float k2[kMaxK * kMaxK];
+};
+
+__global__ void __launch_bounds__(256) blur_direct_kernel(const __grid_constant__ BlurDirectParams p)
+{
+    const int H = p.H, W = p.W, ch = p.kh / 2, cw = p.kw / 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int n2 = (int)(idx % W);
+        const long long t = idx / W;
+        const int n1 = (int)(t % H);
+        const float* xp = p.x + (t / H) * (long long)H * W;
+        float acc = 0.f;
+        for (int i1 = 0; i1 < p.kh; ++i1) {
+            int r = p.adjoint ? n1 + i1 - ch : n1 - i1 + ch;
+            if (r < 0) r += H;
+            if (r >= H) r -= H;
+            const float* xrow = xp + (size_t)r * W;
+            for (int i2 = 0; i2 < p.kw; ++i2) {
+                int c = p.adjoint ? n2 + i2 - cw : n2 - i2 + cw;
+                if (c < 0) c += W;
+                if (c >= W) c -= W;
+                acc = fmaf(p.k2[i1 * p.kw + i2], __ldg(xrow + c), acc);
+            }
+        }
+        if (p.noise) acc = fmaf(p.sigma, p.noise[idx], acc);
+        p.y[idx] = acc;
+    }
+}
+
+// kernel = outer(v, h) within rounding?  (both named families are exactly separable)
+static bool factor_separable(const double* k, int kh, int kw, double* v, double* h)
+{
+    double total = 0, maxabs = 0;
+    for (int i = 0; i < kh * kw; ++i) { total += k[i]; maxabs = std::max(maxabs, fabs(k[i])); }
+    if (total == 0 || maxabs == 0) return false;
+    for (int i = 0; i < kh; ++i) { v[i] = 0; for (int j = 0; j < kw; ++j) v[i] += k[i * kw + j]; }
+    for (int j = 0; j < kw; ++j) { h[j] = 0; for (int i = 0; i < kh; ++i) h[j] += k[i * kw + j]; h[j] /= total; }
+    double err = 0;
+    for (int i = 0; i < kh; ++i)
+        for (int j = 0; j < kw; ++j) err = std::max(err, fabs(v[i] * h[j] - k[i * kw + j]));
+    return err <= 1e-9 * maxabs;
+}
+
+bool factor_separable_public(const double* k, int kh, int kw, double* v, double* h)
+{
+    return factor_separable(k, kh, kw, v, h);
+}
+
+template <int K>
+static int launch_band(const BlurBandParams& p, long long planes, size_t smem, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)(planes * p.nbands);
+    if (p.noise) {
+        SEI_CUDA(allow_smem(blur_band_kernel<K, true>, smem));
+        blur_band_kernel<K, true><<<grid, kBandThreads, smem, st>>>(p);
+        return finish_launch("blur_band_kernel<noise>");
+    }
+    SEI_CUDA(allow_smem(blur_band_kernel<K, false>, smem));
+    blur_band_kernel<K, false><<<grid, kBandThreads, smem, st>>>(p);
+    return finish_launch("blur_band_kernel");
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+// pick the band height: largest multiple of 8 (<= 64) such that two CTAs fit per SM
+int blur_pick_band_rows(int H, int W, int P, int smem_optin)
+{
+    const int forced = env_int("SEI_BLUR_TH", 0);
+    const size_t budget = std::min((size_t)smem_optin, (size_t)110 * 1024);
+    int best = 0;
+    for (int th = 8; th <= 64; th += 8) {
+        const size_t need = (size_t)(2 * th + 2 * P) * W * 4;
+        if (need <= budget) best = th;
+    }
+    if (best == 0 && (size_t)(16 + 2 * P) * W * 4 <= (size_t)smem_optin) best = 8;   // one CTA per SM
+    if (forced > 0 && forced % 8 == 0 && (size_t)(2 * forced + 2 * P) * W * 4 <= (size_t)smem_optin) best = forced;
+    if (best == 0) return 0;
+    const int hceil = ((H + 7) / 8) * 8;
+    return std::min(best, hceil);
+}
+
+}  // namespace sei
+
+using namespace sei;
+
+extern "C" int sei_blur_circular_f32(const float* x, float* y, long long planes, int H, int W,
+                                     const double* kernel_host, int kh, int kw, int adjoint,
+                                     const float* noise, float sigma, int path, void* stream)
+{
+    SEI_REQUIRE(x && y && kernel_host, "null pointer argument");
+    SEI_REQUIRE(planes >= 0 && H > 0 && W > 0, "bad shape planes=%lld H=%d W=%d", planes, H, W);
+    SEI_REQUIRE(kh >= 1 && kw >= 1 && kh <= kMaxK && kw <= kMaxK, "kernel size %dx%d unsupported (max %d)", kh, kw, kMaxK);
+    SEI_REQUIRE(H >= kh && W >= kw, "image %dx%d smaller than the %dx%d blur kernel", H, W, kh, kw);
+    SEI_REQUIRE(path >= SEI_PATH_AUTO && path <= SEI_PATH_TILED, "bad path %d", path);
+    SEI_REQUIRE(planes * (long long)H * W < (1ll << 40), "tensor too large");
+    if (planes == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+
+    double v[kMaxK], h[kMaxK];
+    const bool sep = kh == kw && (kh % 2 == 1) && factor_separable(kernel_host, kh, kw, v, h);
+    const bool ksupported = kh == 5 || kh == 7 || kh == 9 || kh == 13 || kh == 19;
+    const int P = kh / 2;
+    const int TH = sep && ksupported && (W % 4 == 0) && W >= 4 * ((P + 3) / 4) ? blur_pick_band_rows(H, W, P, dp.smem_optin) : 0;
+    const bool aligned = aligned16(x) && aligned16(y) && (!noise || aligned16(noise));
+    const bool tiled_ok = TH > 0 && aligned && planes * ((H + TH - 1) / TH) < (1ll << 31);
+    SEI_REQUIRE(path != SEI_PATH_TILED || tiled_ok,
+                "tiled blur path not available (separable=%d k=%d W=%d aligned=%d)", (int)sep, kh, W, (int)aligned);
+
+    if (tiled_ok && path != SEI_PATH_DIRECT) {
+        BlurBandParams p;
+        p.x = x; p.y = y; p.noise = noise; p.sigma = sigma;
+        p.H = H; p.W = W; p.TH = TH; p.nbands = (H + TH - 1) / TH;
+        for (int t = 0; t < kh; ++t) {
+            // forward (convolution): c[t] = h[K-1-t]; transpose (correlation): c[t] = h[t]
+            p.cv[t] = (float)(adjoint ? v[t] : v[kh - 1 - t]);
+            p.ch[t] = (float)(adjoint ? h[t] : h[kh - 1 - t]);
+        }
+        const size_t smem = (size_t)(2 * TH + 2 * P) * W * 4;
+        switch (kh) {
+        case 5: return launch_band<5>(p, planes, smem, st);
+        case 7: return launch_band<7>(p, planes, smem, st);
+        case 9: return launch_band<9>(p, planes, smem, st);
+        case 13: return launch_band<13>(p, planes, smem, st);
+        default: return launch_band<19>(p, planes, smem, st);
+        }
+    }
+
+    BlurDirectParams p;
+    p.x = x; p.y = y; p.noise = noise; p.sigma = sigma;
+    p.H = H; p.W = W; p.kh = kh; p.kw = kw; p.adjoint = adjoint ? 1 : 0;
+    p.total = planes * (long long)H * W;
+    for (int i = 0; i < kh * kw; ++i) p.k2[i] = (float)kernel_host[i];
+    const long long blocks = (p.total + 255) / 256;
+    const unsigned grid = (unsigned)std::min<long long>(blocks, (long long)dp.sm_count * 32);
+    blur_direct_kernel<<<grid, 256, 0, st>>>(p);
+    return finish_launch("blur_direct_kernel");
+}

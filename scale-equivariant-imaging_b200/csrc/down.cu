@@ -1,0 +1,547 @@
+// down.cu -- SR physics: antialiased bicubic decimation A and its transpose A^T
+// (reference: src/physics/downsampling/__init__.py:16-19 F.interpolate(bicubic, antialias=True);
+//  autograd backward / true adjoint :21-31; plain bicubic upsample :32-35).
+//
+// A is separable: per axis, output i reads the 4*rate inputs [rate*i - OFF, rate*i - OFF + 4*rate)
+// with fixed polyphase weights; the first/last two outputs of an axis have truncated,
+// renormalised windows (ATen semantics, see sei::aa_axis_weights).
+//
+// Forward tiled kernel (down_band_kernel): one CTA = TH output rows x full width of one plane.
+// The rate*TH + 3*rate input rows are streamed through a double-buffered shared-memory stage by
+// bulk async copies (TMA engine, mbarrier completion) in chunks of CH rows; each chunk is
+// filtered horizontally (decimating by rate) into a resident intermediate of width W/rate, and
+// a final vertical pass produces the band.  Input is read from HBM once (+ 3*rate halo rows per
+// band from L2).  Transpose tiled kernel (down_t_band_kernel): one CTA = TH input-resolution
+// rows; the ~TH/rate + 4 gradient rows it depends on are staged by one bulk copy; vertical then
+// horizontal 4-tap polyphase passes.  Direct kernels cover every other shape.
+#include "sei_common.cuh"
+#include <algorithm>
+
+namespace sei {
+
+constexpr int kDownThreads = 256;
+
+// interior window start: xmin(i) = rate*i - aa_off(rate), aa_off = ceil(1.5*rate - 0.5) = 3, 4, 6 for rate 2, 3, 4
+__host__ __device__ constexpr int aa_off(int rate) { return (3 * rate) / 2; }
+
+struct DownParams {
+    const float* x;      // fwd: input planes H x W ; transpose: gy planes Ho x Wo
+    float* y;            // fwd: output planes Ho x Wo ; transpose: gx planes H x W
+    const float* noise;
+    float sigma;
+    int H, W, Ho, Wo;
+    int TH, nbands, CH;
+    float wint[kAaMaxTaps];   // interior weights
+};
+
+struct BorderTab {      // weights of the 4 border outputs of one axis: indices 0, 1, n-2, n-1
+    float w[4][kAaMaxTaps];
+    int xmin[4];
+    int xsize[4];
+};
+
+__device__ __forceinline__ int border_slot(int i, int n) { return i < 2 ? i : (i >= n - 2 ? i - (n - 4) : -1); }
+
+template <int R>
+__global__ void __launch_bounds__(kDownThreads, 2) down_band_kernel(const __grid_constant__ DownParams p)
+{
+    constexpr int T = 4 * R, OFF = aa_off(R);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar[2];
+    __shared__ BorderTab colTab, rowTab;
+
+    const int H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo, CW = Wo >> 2;
+    const int band = blockIdx.x % p.nbands;
+    const long long plane = blockIdx.x / p.nbands;
+    const int i0 = band * p.TH;
+    const int th = min(p.TH, Ho - i0);
+    const int in_lo = max(0, R * i0 - OFF);
+    const int in_hi = min(H, R * (i0 + th - 1) - OFF + T);
+    const int nin = in_hi - in_lo;
+    const int CH = p.CH;
+    const int nchunks = (nin + CH - 1) / CH;
+
+    float* sTmp = reinterpret_cast<float*>(smem_raw);                  // [R*TH + 3R][Wo]
+    float* sStage = sTmp + (size_t)(R * p.TH + 3 * R) * Wo;             // [2][CH][W]
+    const unsigned char* xplane = reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * H * W);
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        const int k = threadIdx.x - 32;
+        const int j = k < 2 ? k : Wo - 4 + k;
+        aa_axis_weights(j, W, R, colTab.w[k], colTab.xmin[k], colTab.xsize[k]);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 68) {
+        const int k = threadIdx.x - 64;
+        const int i = k < 2 ? k : Ho - 4 + k;
+        aa_axis_weights(i, H, R, rowTab.w[k], rowTab.xmin[k], rowTab.xsize[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = min(CH, nin);
+        mbar_arrive_expect_tx(&bar[0], (uint32_t)n * row_bytes);
+        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sStage), xplane, H, row_bytes, in_lo, n, &bar[0]);
+    }
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        // prefetch the next chunk into the other buffer (its previous contents were consumed
+        // before the __syncthreads that ended iteration c-1)
+        if (threadIdx.x == 0 && c + 1 < nchunks) {
+            const int n = min(CH, nin - (c + 1) * CH);
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar[buf ^ 1], (uint32_t)n * row_bytes);
+            bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sStage + (size_t)(buf ^ 1) * CH * W), xplane, H,
+                                    row_bytes, in_lo + (c + 1) * CH, n, &bar[buf ^ 1]);
+        }
+        mbar_wait(&bar[buf], (c >> 1) & 1);
+        const int nrows = min(CH, nin - c * CH);
+        const float* stage = sStage + (size_t)buf * CH * W;
+        // ---- horizontal pass over this chunk: sTmp[row][j] = sum_t w[t] * in[row][R*j - OFF + t]
+        for (int item = threadIdx.x; item < nrows * CW; item += kDownThreads) {
+            const int r = item / CW, j4 = item - r * CW;
+            const float* row = stage + (size_t)r * W;
+            float out[4];
+            if (j4 > 0 && j4 < CW - 1) {
+                constexpr int SKIP = 4 * ((OFF + 3) / 4) - OFF;
+                constexpr int NV = (SKIP + 7 * R + 3) / 4;
+                const float* src = row + 4 * R * j4 - (OFF + SKIP);
+                float v[4 * NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], v[SKIP + R * o + t], a);
+                    out[o] = a;
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int j = 4 * j4 + o;
+                    const int k = border_slot(j, Wo);
+                    float a = 0.f;
+                    if (k >= 0) {
+                        const float* src = row + colTab.xmin[k];
+                        for (int t = 0; t < colTab.xsize[k]; ++t) a = fmaf(colTab.w[k][t], src[t], a);
+                    } else {
+                        const float* src = row + R * j - OFF;
+#pragma unroll
+                        for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], src[t], a);
+                    }
+                    out[o] = a;
+                }
+            }
+            *reinterpret_cast<float4*>(sTmp + (size_t)(c * CH + r) * Wo + 4 * j4) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+        __syncthreads();
+    }
+
+    // ---- vertical pass: y[i][j] = sum_t w[t] * sTmp[R*i - OFF + t - in_lo][j]
+    float* yplane = p.y + (size_t)plane * Ho * Wo;
+    const float* nplane = p.noise ? p.noise + (size_t)plane * Ho * Wo : nullptr;
+    for (int item = threadIdx.x; item < th * CW; item += kDownThreads) {
+        const int r = item / CW, j4 = item - r * CW;
+        const int i = i0 + r;
+        const int k = border_slot(i, Ho);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < 0) {
+            const float* src = sTmp + (size_t)(R * i - OFF - in_lo) * Wo + 4 * j4;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * Wo);
+                const float w = p.wint[t];
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+        } else {
+            const float* src = sTmp + (size_t)(rowTab.xmin[k] - in_lo) * Wo + 4 * j4;
+            for (int t = 0; t < rowTab.xsize[k]; ++t) {
+                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * Wo);
+                const float w = rowTab.w[k][t];
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+        }
+        const size_t g = (size_t)i * Wo + 4 * j4;
+        if (nplane) {
+            const float4 n = ld_stream4(nplane + g);
+            acc.x = fmaf(p.sigma, n.x, acc.x); acc.y = fmaf(p.sigma, n.y, acc.y);
+            acc.z = fmaf(p.sigma, n.z, acc.z); acc.w = fmaf(p.sigma, n.w, acc.w);
+        }
+        st_stream4(yplane + g, acc);
+    }
+}
+
+// ------------------------------------------------------------------ transpose, tiled
+// contributors of input-resolution index m along one axis: up to NQ (output index, weight) pairs
+constexpr int kNQ = 6;
+struct Contrib {
+    int idx[kNQ];
+    float w[kNQ];
+};
+
+__device__ __forceinline__ void aa_contributors(int m, int in_size, int out_size, int rate, Contrib& c)
+{
+    const int off = aa_off(rate);
+    const int ic = (m + off) / rate;
+    int n = 0;
+#pragma unroll 1
+    for (int i = ic - 4; i <= ic + 1; ++i) {
+        int idx = 0;
+        float wv = 0.f;
+        if (i >= 0 && i < out_size) {
+            float w[kAaMaxTaps];
+            int xmin, xsize;
+            aa_axis_weights(i, in_size, rate, w, xmin, xsize);
+            const int t = m - xmin;
+            if (t >= 0 && t < xsize) {
+                float sel = 0.f;
+#pragma unroll
+                for (int q = 0; q < kAaMaxTaps; ++q) sel = (q == t) ? w[q] : sel;
+                idx = i;
+                wv = sel;
+            }
+        }
+        c.idx[n] = idx;
+        c.w[n] = wv;
+        ++n;
+    }
+}
+
+constexpr int kBorderCols = 32;   // per side, >= 5*rate - off + slack
+
+template <int R>
+__global__ void __launch_bounds__(kDownThreads, 2) down_t_band_kernel(const __grid_constant__ DownParams p)
+{
+    constexpr int OFF = aa_off(R);
+    constexpr bool kStaticPhase = (4 % R) == 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ Contrib colL[kBorderCols], colR[kBorderCols];
+
+    const int H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo, CWo = Wo >> 2, CW = W >> 2;
+    const int band = blockIdx.x % p.nbands;
+    const long long plane = blockIdx.x / p.nbands;
+    const int m0 = band * p.TH;
+    const int th = min(p.TH, H - m0);
+    // gradient rows that can contribute to rows [m0, m0+th)
+    const int g_lo = max(0, (m0 + OFF) / R - 4);
+    const int g_hi = min(Ho, (m0 + th - 1 + OFF) / R + 2);
+    const int ng = g_hi - g_lo;
+    const int GR = p.TH / R + 8;                     // allocated gradient rows
+
+    float* sG = reinterpret_cast<float*>(smem_raw);             // [GR][Wo]
+    float* sTmp = sG + (size_t)GR * Wo;                          // [TH][Wo]
+    Contrib* rowC = reinterpret_cast<Contrib*>(sTmp + (size_t)p.TH * Wo);   // [TH]
+
+    const int NL = min(W, 5 * R - OFF);                          // columns [0, NL) are border
+    const int NR0 = max(NL, R * (Wo - 2) - OFF);                 // columns [NR0, W) are border
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ng > 0) {
+        const uint32_t row_bytes = (uint32_t)Wo * 4u;
+        mbar_arrive_expect_tx(&bar, (uint32_t)ng * row_bytes);
+        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sG),
+                                reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * Ho * Wo), Ho, row_bytes,
+                                g_lo, ng, &bar);
+    }
+    // contributor tables (overlaps the copy)
+    for (int t = threadIdx.x; t < th; t += kDownThreads) aa_contributors(m0 + t, H, Ho, R, rowC[t]);
+    for (int t = threadIdx.x; t < NL; t += kDownThreads) aa_contributors(t, W, Wo, R, colL[t]);
+    for (int t = threadIdx.x; t < W - NR0; t += kDownThreads) aa_contributors(NR0 + t, W, Wo, R, colR[t]);
+    __syncthreads();
+    if (ng > 0) mbar_wait(&bar, 0);
+
+    // ---- vertical pass: sTmp[m][j] = sum_q w_q * gy[i_q][j]
+    for (int item = threadIdx.x; item < th * CWo; item += kDownThreads) {
+        const int r = item / CWo, j4 = item - r * CWo;
+        const Contrib& c = rowC[r];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q) {
+            const float w = c.w[q];
+            if (w != 0.f) {
+                const float4 v = *reinterpret_cast<const float4*>(sG + (size_t)(c.idx[q] - g_lo) * Wo + 4 * j4);
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(sTmp + (size_t)r * Wo + 4 * j4) = acc;
+    }
+    __syncthreads();
+
+    // ---- horizontal pass: gx[m][n] = sum_q w_q * sTmp[m][j_q]
+    float* gplane = p.y + (size_t)plane * H * W;
+    for (int item = threadIdx.x; item < th * CW; item += kDownThreads) {
+        const int r = item / CW, n4 = item - r * CW;
+        const float* row = sTmp + (size_t)r * Wo;
+        float out[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int n = 4 * n4 + o;
+            float a = 0.f;
+            if (n >= NL && n < NR0) {
+                // interior: outputs j = (n+OFF)/R - q, tap (n+OFF)%R + R*q, q = 0..3
+                const int ph = kStaticPhase ? (o + OFF) % R : (n + OFF) % R;
+                const int jb = kStaticPhase ? (4 / R) * n4 + (o + OFF) / R : (n + OFF) / R;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a = fmaf(p.wint[ph + R * q], row[jb - q], a);
+            } else {
+                const Contrib& c = n < NL ? colL[n] : colR[n - NR0];
+#pragma unroll
+                for (int q = 0; q < kNQ; ++q)
+                    if (c.w[q] != 0.f) a = fmaf(c.w[q], row[c.idx[q]], a);
+            }
+            out[o] = a;
+        }
+        st_stream4(gplane + (size_t)(m0 + r) * W + 4 * n4, make_float4(out[0], out[1], out[2], out[3]));
+    }
+}
+
+// ------------------------------------------------------------------ direct kernels (any shape)
+struct DownDirectParams {
+    const float* x;
+    float* y;
+    const float* noise;
+    float sigma;
+    int H, W, Ho, Wo, rate;
+    long long total;
+};
+
+__global__ void __launch_bounds__(128) down_direct_kernel(const __grid_constant__ DownDirectParams p)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % p.Wo);
+        const long long t = idx / p.Wo;
+        const int i = (int)(t % p.Ho);
+        const float* xp = p.x + (t / p.Ho) * (long long)p.H * p.W;
+        float wy[kAaMaxTaps], wx[kAaMaxTaps];
+        int ymin, ysize, xmin, xsize;
+        aa_axis_weights(i, p.H, p.rate, wy, ymin, ysize);
+        aa_axis_weights(j, p.W, p.rate, wx, xmin, xsize);
+        float acc = 0.f;
+#pragma unroll 1
+        for (int a = 0; a < ysize; ++a) {
+            const float* row = xp + (size_t)(ymin + a) * p.W + xmin;
+            float h = 0.f;
+#pragma unroll
+            for (int b = 0; b < kAaMaxTaps; ++b)
+                if (b < xsize) h = fmaf(wx[b], __ldg(row + b), h);
+            float wsel = 0.f;
+#pragma unroll
+            for (int q = 0; q < kAaMaxTaps; ++q) wsel = (q == a) ? wy[q] : wsel;
+            acc = fmaf(wsel, h, acc);
+        }
+        if (p.noise) acc = fmaf(p.sigma, p.noise[idx], acc);
+        p.y[idx] = acc;
+    }
+}
+
+// transpose: x = gy planes (Ho x Wo), y = gx planes (H x W)
+__global__ void __launch_bounds__(128) down_t_direct_kernel(const __grid_constant__ DownDirectParams p)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % p.W);
+        const long long t = idx / p.W;
+        const int m = (int)(t % p.H);
+        const float* gp = p.x + (t / p.H) * (long long)p.Ho * p.Wo;
+        Contrib cy, cx;
+        aa_contributors(m, p.H, p.Ho, p.rate, cy);
+        aa_contributors(n, p.W, p.Wo, p.rate, cx);
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < kNQ; ++a) {
+            if (cy.w[a] != 0.f) {
+                const float* row = gp + (size_t)cy.idx[a] * p.Wo;
+                float h = 0.f;
+#pragma unroll
+                for (int b = 0; b < kNQ; ++b)
+                    if (cx.w[b] != 0.f) h = fmaf(cx.w[b], __ldg(row + cx.idx[b]), h);
+                acc = fmaf(cy.w[a], h, acc);
+            }
+        }
+        p.y[idx] = acc;
+    }
+}
+
+// plain bicubic upsample (A = -0.75, align_corners=False, clamped taps)
+struct UpParams {
+    const float* y;
+    float* x;
+    int h, w, rate;
+    long long total;
+};
+
+__global__ void __launch_bounds__(256) up_bicubic_kernel(const __grid_constant__ UpParams p)
+{
+    const int H = p.h * p.rate, W = p.w * p.rate;
+    const float s = 1.0f / (float)p.rate;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % W);
+        const long long t = idx / W;
+        const int i = (int)(t % H);
+        const float* yp = p.y + (t / H) * (long long)p.h * p.w;
+        const float ry = s * ((float)i + 0.5f) - 0.5f, rx = s * ((float)j + 0.5f) - 0.5f;
+        const float fy = floorf(ry), fx = floorf(rx);
+        float cy[4], cx[4];
+        keys_coeffs(ry - fy, cy);
+        keys_coeffs(rx - fx, cx);
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int r = min(max((int)fy - 1 + a, 0), p.h - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = min(max((int)fx - 1 + b, 0), p.w - 1);
+                row = fmaf(__ldg(yp + (size_t)r * p.w + c), cx[b], row);
+            }
+            acc = fmaf(row, cy[a], acc);
+        }
+        p.x[idx] = acc;
+    }
+}
+
+static void interior_weights(int rate, float* wint)
+{
+    // any interior output index has the same weights; take one far from both borders
+    float w[kAaMaxTaps];
+    int xmin, xsize;
+    aa_axis_weights(8, 64 * rate, rate, w, xmin, xsize);
+    for (int t = 0; t < kAaMaxTaps; ++t) wint[t] = w[t];
+}
+
+template <int R>
+static int launch_down(const DownParams& p, long long planes, size_t smem, cudaStream_t st, bool transpose)
+{
+    const unsigned grid = (unsigned)(planes * p.nbands);
+    if (transpose) {
+        SEI_CUDA(allow_smem(down_t_band_kernel<R>, smem));
+        down_t_band_kernel<R><<<grid, kDownThreads, smem, st>>>(p);
+        return finish_launch("down_t_band_kernel");
+    }
+    SEI_CUDA(allow_smem(down_band_kernel<R>, smem));
+    down_band_kernel<R><<<grid, kDownThreads, smem, st>>>(p);
+    return finish_launch(p.noise ? "down_band_kernel<noise>" : "down_band_kernel");
+}
+
+static int down_common(const float* in, float* out, long long planes, int H, int W, int rate,
+                       const float* noise, float sigma, int path, void* stream, bool transpose)
+{
+    SEI_REQUIRE(in && out, "null pointer argument");
+    SEI_REQUIRE(rate >= 2 && rate <= 4, "rate %d unsupported (2..4)", rate);
+    SEI_REQUIRE(planes >= 0 && H >= rate && W >= rate, "bad shape planes=%lld H=%d W=%d rate=%d", planes, H, W, rate);
+    SEI_REQUIRE(path >= SEI_PATH_AUTO && path <= SEI_PATH_TILED, "bad path %d", path);
+    if (planes == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const int Ho = (int)floor((double)H * (1.0 / (double)rate)), Wo = (int)floor((double)W * (1.0 / (double)rate));
+
+    DownParams p;
+    p.x = in; p.y = out; p.noise = noise; p.sigma = sigma;
+    p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo;
+    interior_weights(rate, p.wint);
+
+    bool tiled_ok = (W % (4 * rate) == 0) && Wo >= 8 && Ho >= 4 && aligned16(in) && aligned16(out) &&
+                    (!noise || aligned16(noise));
+    size_t smem = 0;
+    if (tiled_ok) {
+        const size_t budget = std::min((size_t)dp.smem_optin, (size_t)110 * 1024);
+        if (!transpose) {
+            p.CH = std::max(1, (int)(16384 / ((size_t)W * 4)));
+            int best = 0;
+            for (int th = 4; th <= 32; th += 4) {
+                const size_t need = ((size_t)(rate * th + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
+                if (need <= budget) best = th;
+            }
+            p.TH = std::min(best, ((Ho + 3) / 4) * 4);
+            p.nbands = p.TH ? (Ho + p.TH - 1) / p.TH : 0;
+            smem = ((size_t)(rate * p.TH + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
+        } else {
+            int best = 0;
+            for (int th = 8; th <= 64; th += 8) {
+                const size_t need = ((size_t)(th / rate + 8) * Wo + (size_t)th * Wo) * 4 + (size_t)th * sizeof(Contrib);
+                if (need <= budget) best = th;
+            }
+            p.TH = std::min(best, ((H + 7) / 8) * 8);
+            p.CH = 0;
+            p.nbands = p.TH ? (H + p.TH - 1) / p.TH : 0;
+            smem = ((size_t)(p.TH / rate + 8) * Wo + (size_t)p.TH * Wo) * 4 + (size_t)p.TH * sizeof(Contrib);
+            // border-column tables hold kBorderCols entries per side
+            tiled_ok = tiled_ok && (5 * rate - aa_off(rate)) <= kBorderCols &&
+                       (W - std::max(5 * rate - aa_off(rate), rate * (Wo - 2) - aa_off(rate))) <= kBorderCols;
+        }
+        tiled_ok = tiled_ok && p.TH > 0 && planes * p.nbands < (1ll << 31);
+    }
+    SEI_REQUIRE(path != SEI_PATH_TILED || tiled_ok, "tiled SR path not available for H=%d W=%d rate=%d", H, W, rate);
+
+    if (tiled_ok && path != SEI_PATH_DIRECT) {
+        switch (rate) {
+        case 2: return launch_down<2>(p, planes, smem, st, transpose);
+        case 3: return launch_down<3>(p, planes, smem, st, transpose);
+        default: return launch_down<4>(p, planes, smem, st, transpose);
+        }
+    }
+    DownDirectParams d;
+    d.x = in; d.y = out; d.noise = noise; d.sigma = sigma;
+    d.H = H; d.W = W; d.Ho = Ho; d.Wo = Wo; d.rate = rate;
+    d.total = planes * (long long)(transpose ? (long long)H * W : (long long)Ho * Wo);
+    const unsigned grid = (unsigned)std::min<long long>((d.total + 127) / 128, (long long)dp.sm_count * 64);
+    if (transpose) {
+        down_t_direct_kernel<<<grid, 128, 0, st>>>(d);
+        return finish_launch("down_t_direct_kernel");
+    }
+    down_direct_kernel<<<grid, 128, 0, st>>>(d);
+    return finish_launch("down_direct_kernel");
+}
+
+}  // namespace sei
+
+using namespace sei;
+
+extern "C" int sei_down_aa_f32(const float* x, float* y, long long planes, int H, int W, int rate,
+                               const float* noise, float sigma, int path, void* stream)
+{
+    return down_common(x, y, planes, H, W, rate, noise, sigma, path, stream, false);
+}
+
+extern "C" int sei_down_aa_transpose_f32(const float* gy, float* gx, long long planes, int H, int W,
+                                         int rate, int path, void* stream)
+{
+    return down_common(gy, gx, planes, H, W, rate, nullptr, 0.f, path, stream, true);
+}
+
+extern "C" int sei_up_bicubic_f32(const float* y, float* x, long long planes, int h, int w, int rate, void* stream)
+{
+    SEI_REQUIRE(y && x, "null pointer argument");
+    SEI_REQUIRE(planes >= 0 && h > 0 && w > 0 && rate >= 1 && rate <= 8, "bad arguments");
+    if (planes == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    UpParams p;
+    p.y = y; p.x = x; p.h = h; p.w = w; p.rate = rate;
+    p.total = planes * (long long)h * rate * w * rate;
+    const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
+    up_bicubic_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return finish_launch("up_bicubic_kernel");
+}

@@ -1,0 +1,166 @@
+// tile_ops.cuh -- shared-memory tile passes reused by the stand-alone and the fused kernels.
+#pragma once
+#include "sei_common.cuh"
+
+namespace sei {
+
+constexpr int kMaxK = 31;
+constexpr int kRH = 8;   // output rows per vertical-pass work item
+
+// ---------------------------------------------------------------- separable circular blur passes
+// vertical: sMid[o][c] = sum_t cv[t] * sIn[o + t][c],  o in [0, th), rows of sIn in [0, rin = th + K - 1)
+// Register-blocked: each work item owns kRH output rows x 4 columns and streams kRH + K - 1 input
+// rows through a scatter-form accumulation, so every shared load feeds up to kRH * 4 FMAs and the
+// taps are compile-time-indexed constant-bank operands.
+template <int K, int NT>
+__device__ __forceinline__ void blur_vpass(const float* __restrict__ sIn, float* __restrict__ sMid, int W, int th,
+                                           const float* __restrict__ cv)
+{
+    const int CW = W >> 2, rin = th + K - 1;
+    const int ngroups = (th + kRH - 1) / kRH;
+    for (int item = threadIdx.x; item < ngroups * CW; item += NT) {
+        const int g = item / CW, c4 = item - g * CW;
+        const int o0 = g * kRH;
+        const float* base = sIn + (size_t)o0 * W + c4 * 4;
+        float4 acc[kRH];
+#pragma unroll
+        for (int o = 0; o < kRH; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o0 + kRH <= th) {
+#pragma unroll
+            for (int i = 0; i < kRH + K - 1; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * W);
+#pragma unroll
+                for (int o = 0; o < kRH; ++o) {
+                    const int t = i - o;
+                    if (t >= 0 && t < K) {
+                        const float c = cv[t];
+                        acc[o].x = fmaf(c, v.x, acc[o].x); acc[o].y = fmaf(c, v.y, acc[o].y);
+                        acc[o].z = fmaf(c, v.z, acc[o].z); acc[o].w = fmaf(c, v.w, acc[o].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kRH; ++o) *reinterpret_cast<float4*>(sMid + (size_t)(o0 + o) * W + c4 * 4) = acc[o];
+        } else {
+            const int nvalid = rin - o0;
+#pragma unroll
+            for (int i = 0; i < kRH + K - 1; ++i) {
+                if (i < nvalid) {
+                    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * W);
+#pragma unroll
+                    for (int o = 0; o < kRH; ++o) {
+                        const int t = i - o;
+                        if (t >= 0 && t < K) {
+                            const float c = cv[t];
+                            acc[o].x = fmaf(c, v.x, acc[o].x); acc[o].y = fmaf(c, v.y, acc[o].y);
+                            acc[o].z = fmaf(c, v.z, acc[o].z); acc[o].w = fmaf(c, v.w, acc[o].w);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kRH; ++o)
+                if (o0 + o < th) *reinterpret_cast<float4*>(sMid + (size_t)(o0 + o) * W + c4 * 4) = acc[o];
+        }
+    }
+}
+
+// horizontal (circular in x): y[r][n] = sum_t ch[t] * sMid[r][(n + t - P) mod W] (+ sigma * noise)
+// yrow0 / nrow0 point at the first output row of the band in global memory (row pitch W).
+template <int K, int NT, bool NOISE>
+__device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int W, int th, const float* __restrict__ ch,
+                                           float* __restrict__ yrow0, const float* __restrict__ nrow0, float sigma)
+{
+    constexpr int P = K / 2;
+    constexpr int LCH = (P + 3) / 4;         // float4 chunks to the left of the output chunk
+    constexpr int NCH = 2 * LCH + 1;
+    constexpr int LEFT = 4 * LCH;
+    const int CW = W >> 2;
+    for (int item = threadIdx.x; item < th * CW; item += NT) {
+        const int r = item / CW, c4 = item - r * CW;
+        const float* row = sMid + (size_t)r * W;
+        float v[4 * NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            int cc = c4 - LCH + q;
+            if (cc < 0) cc += CW;
+            if (cc >= CW) cc -= CW;
+            const float4 t = *reinterpret_cast<const float4*>(row + cc * 4);
+            v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const float c = ch[t];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) out[o] = fmaf(c, v[LEFT + o + t - P], out[o]);
+        }
+        const size_t g = (size_t)r * W + c4 * 4;
+        if (NOISE) {
+            const float4 n = ld_stream4(nrow0 + g);
+            out[0] = fmaf(sigma, n.x, out[0]); out[1] = fmaf(sigma, n.y, out[1]);
+            out[2] = fmaf(sigma, n.z, out[2]); out[3] = fmaf(sigma, n.w, out[3]);
+        }
+        st_stream4(yrow0 + g, make_float4(out[0], out[1], out[2], out[3]));
+    }
+}
+
+// ---------------------------------------------------------------- scale-transform taps
+// pixel coordinate of output index idx along one axis, rounding exactly like the reference:
+//   u = 2/S * idx - 1 ; g = 1/rate * (u - c) + c          (src/transforms.py:31-41, fp32 tensors)
+//   pix = ((g + 1) / 2) * (S - 1)                          (grid_sample unnormalize, align_corners=True)
+__device__ __forceinline__ float scale_src_coord(int idx, float two_over_S, float inv_rate, float c, float Sm1)
+{
+    const float u = __fsub_rn(__fmul_rn(two_over_S, (float)idx), 1.0f);
+    const float g = __fadd_rn(__fmul_rn(inv_rate, __fsub_rn(u, c)), c);
+    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), Sm1);
+}
+
+struct AxisTap {
+    float w[4];
+    int idx[4];
+};
+
+__device__ __forceinline__ void scale_axis_tap(int i, int S, float two_over_S, float inv_rate, float c, AxisTap& t)
+{
+    const float pix = scale_src_coord(i, two_over_S, inv_rate, c, (float)(S - 1));
+    const float fl = floorf(pix);
+    keys_coeffs(pix - fl, t.w);
+    // |pix| stays far below 2^31 for any sane rate; clamp defensively so the int cast is defined
+    const int base = (int)fminf(fmaxf(fl, -1.0e9f), 1.0e9f) - 1;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) t.idx[a] = reflect_clip(base + a, S);
+}
+
+// vertical 4-tap pass: dst[r][c] = sum_a w[r][a] * src[idx[r][a]][c]   (rows of `src` have pitch S;
+// idx already relative to src's first row)
+template <int NT>
+__device__ __forceinline__ void scale_vpass(const float* __restrict__ src, float* __restrict__ dst, int S, int nrows,
+                                            const AxisTap* __restrict__ rowT)
+{
+    const int CW = S >> 2;
+    for (int item = threadIdx.x; item < nrows * CW; item += NT) {
+        const int r = item / CW, c4 = item - r * CW;
+        const AxisTap t = rowT[r];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t.idx[a] * S + 4 * c4);
+            acc.x = fmaf(t.w[a], v.x, acc.x); acc.y = fmaf(t.w[a], v.y, acc.y);
+            acc.z = fmaf(t.w[a], v.z, acc.z); acc.w = fmaf(t.w[a], v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)r * S + 4 * c4) = acc;
+    }
+}
+
+// horizontal 4-tap gather for one (row, column): sum_b wx[b] * row[ix[b]]
+__device__ __forceinline__ float scale_hgather(const float* __restrict__ row, const AxisTap& t)
+{
+    float a = row[t.idx[0]] * t.w[0];
+    a = fmaf(row[t.idx[1]], t.w[1], a);
+    a = fmaf(row[t.idx[2]], t.w[2], a);
+    a = fmaf(row[t.idx[3]], t.w[3], a);
+    return a;
+}
+
+}  // namespace sei

@@ -1,0 +1,72 @@
+"""ctypes binding of libsei_b200.so (include/sei_b200.h).  No CPU fallback: if the library or
+a CUDA device is missing every operator raises."""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_ip = C.POINTER(C.c_int)
+
+SIGNATURES = {
+    "sei_abi_version": (C.c_int, []),
+    "sei_last_error": (C.c_char_p, []),
+    "sei_last_kernel": (C.c_char_p, []),
+    "sei_launch_count": (C.c_longlong, []),
+    "sei_device_info": (C.c_int, [_ip, _ip, _ip, _ip]),
+    "sei_blur_circular_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _vp, _i, _i, _i, _vp, _f, _i, _vp]),
+    "sei_blur_padded_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _vp, _i, _i, _i, _i, _ip, _ip, _vp]),
+    "sei_down_aa_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp, _f, _i, _vp]),
+    "sei_down_aa_transpose_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "sei_up_bicubic_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp]),
+    "sei_scale_transform_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sei_scale_params_f32": (C.c_int, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "sei_ei_remeasure_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp]),
+    "sei_reduce_workspace_bytes": (C.c_longlong, []),
+    "sei_mse_f32": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _vp]),
+    "sei_mse_backward_f32": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "sei_sure_loss_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
+    "sei_sure_loss_backward_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "sei_sure_perturb_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "sei_add_noise_f32": (C.c_int, [_vp, _vp, _ll, _f, _vp, _vp]),
+}
+
+
+class SeiError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeiError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+                "(run `python __graft_entry__.py build`). There is no CPU/PyTorch fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sei_abi_version() != 1:
+            raise SeiError("libsei_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().sei_last_error().decode(errors="replace")
+        raise SeiError(f"libsei_b200 call failed (code {rc}): {msg}")
+
+
+def last_kernel():
+    return load().sei_last_kernel().decode()
+
+
+def launch_count():
+    return int(load().sei_launch_count())

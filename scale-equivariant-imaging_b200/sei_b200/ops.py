@@ -1,0 +1,379 @@
+"""Tensor-level wrappers over the C ABI (include/sei_b200.h) and the autograd Functions whose
+backward passes call the hand-written transpose kernels.  torch is used for device memory and
+streams only; every arithmetic step below runs in libsei_b200.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SeiError, check
+
+PATH_AUTO, PATH_DIRECT, PATH_TILED = 0, 1, 2
+PAD_MODES = {"valid": 0, "circular": 1, "replicate": 2, "reflect": 3, "zero": 4}
+
+
+def _t(x, name):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not x.is_cuda:
+        raise SeiError(f"{name} is on {x.device}: the sei_b200 operators run on CUDA (sm_100a) only; "
+                       "there is no CPU fallback")
+    if x.dtype != torch.float32:
+        raise SeiError(f"{name} has dtype {x.dtype}: the sei_b200 operators compute in float32")
+    return x.contiguous()
+
+
+def _ptr(x):
+    return C.c_void_p(x.data_ptr()) if x is not None else None
+
+
+def _stream(x):
+    return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+
+
+def _host64(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return a, C.c_void_p(a.ctypes.data)
+
+
+def kernel_to_host(kernel):
+    """(1,1,kh,kw) / (kh,kw) torch or numpy kernel -> contiguous float64 numpy (kh, kw)."""
+    if isinstance(kernel, torch.Tensor):
+        kernel = kernel.detach().to("cpu", torch.float64).numpy()
+    k = np.asarray(kernel, dtype=np.float64)
+    k = k.reshape(k.shape[-2], k.shape[-1])
+    return np.ascontiguousarray(k)
+
+
+_workspaces = {}
+
+
+def _workspace(x):
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = int(_lib.load().sei_reduce_workspace_bytes())
+        ws = torch.zeros(n, dtype=torch.uint8, device=x.device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------ raw operators
+def blur_circular(x, kernel_host, adjoint=False, noise=None, sigma=0.0, path=PATH_AUTO):
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    n = _t(noise, "noise") if noise is not None else None
+    if n is not None and n.shape != x.shape:
+        raise SeiError("noise must have the shape of the measurement")
+    k, kp = _host64(kernel_host)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_blur_circular_f32(_ptr(x), _ptr(y), B * Cc, H, W, kp, k.shape[0], k.shape[1],
+                                                int(bool(adjoint)), _ptr(n), float(sigma), path, _stream(x)))
+    return y
+
+
+def blur_padded(x, filter_host, padding, transpose=False):
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    f, fp = _host64(filter_host)
+    mode = PAD_MODES[padding]
+    ho, wo = C.c_int(), C.c_int()
+    lib = _lib.load()
+    check(lib.sei_blur_padded_f32(None, None, B * Cc, H, W, fp, f.shape[0], f.shape[1], mode, int(transpose),
+                                  C.byref(ho), C.byref(wo), None))
+    out = torch.empty((B, Cc, ho.value, wo.value), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sei_blur_padded_f32(_ptr(x), _ptr(out), B * Cc, H, W, fp, f.shape[0], f.shape[1], mode,
+                                      int(transpose), C.byref(ho), C.byref(wo), _stream(x)))
+    return out
+
+
+def down_out_size(n, rate):
+    return int(np.floor(n * (1.0 / rate)))
+
+
+def down_aa(x, rate, noise=None, sigma=0.0, path=PATH_AUTO):
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, Cc, down_out_size(H, rate), down_out_size(W, rate)), dtype=x.dtype, device=x.device)
+    n = _t(noise, "noise") if noise is not None else None
+    if n is not None and n.shape != y.shape:
+        raise SeiError("noise must have the shape of the measurement")
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_down_aa_f32(_ptr(x), _ptr(y), B * Cc, H, W, int(rate), _ptr(n), float(sigma), path,
+                                          _stream(x)))
+    return y
+
+
+def down_aa_transpose(gy, rate, in_hw, path=PATH_AUTO):
+    gy = _t(gy, "gy")
+    B, Cc, Ho, Wo = gy.shape
+    H, W = in_hw
+    if (Ho, Wo) != (down_out_size(H, rate), down_out_size(W, rate)):
+        raise SeiError(f"gradient of shape {tuple(gy.shape)} does not match an input of {H}x{W} at rate {rate}")
+    gx = torch.empty((B, Cc, H, W), dtype=gy.dtype, device=gy.device)
+    with torch.cuda.device(gy.device):
+        check(_lib.load().sei_down_aa_transpose_f32(_ptr(gy), _ptr(gx), B * Cc, H, W, int(rate), path, _stream(gy)))
+    return gx
+
+
+def up_bicubic(y, rate):
+    y = _t(y, "y")
+    B, Cc, h, w = y.shape
+    x = torch.empty((B, Cc, h * rate, w * rate), dtype=y.dtype, device=y.device)
+    with torch.cuda.device(y.device):
+        check(_lib.load().sei_up_bicubic_f32(_ptr(y), _ptr(x), B * Cc, h, w, int(rate), _stream(y)))
+    return x
+
+
+def scale_params(u_rate, u_center, rates):
+    u_rate, u_center = _t(u_rate, "u_rate"), _t(u_center, "u_center")
+    B = u_rate.numel()
+    rate = torch.empty((B,), dtype=torch.float32, device=u_rate.device)
+    center = torch.empty((B, 1, 1, 2), dtype=torch.float32, device=u_rate.device)
+    r = np.ascontiguousarray(np.asarray(rates, dtype=np.float32))
+    with torch.cuda.device(u_rate.device):
+        check(_lib.load().sei_scale_params_f32(_ptr(u_rate), _ptr(u_center), B, C.c_void_p(r.ctypes.data), len(r),
+                                               _ptr(rate), _ptr(center), _stream(u_rate)))
+    return rate, center
+
+
+def scale_transform(x, rate, center, path=PATH_AUTO):
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    if H != W:
+        raise SeiError("the scale transform is defined for square images only (like the reference's grid)")
+    rate = _t(rate, "downsampling_rate").reshape(-1)
+    center = _t(center, "center").reshape(-1)
+    if rate.numel() != B or center.numel() != 2 * B:
+        raise SeiError("downsampling_rate must have B entries and center B x 2")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_scale_transform_f32(_ptr(x), _ptr(out), B, Cc, H, _ptr(rate), _ptr(center), path,
+                                                  _stream(x)))
+    return out
+
+
+def ei_remeasure(x_net, rate, center, kernel_host, rate_sr, noise, sigma):
+    x_net = _t(x_net, "x_net")
+    B, Cc, S, S2 = x_net.shape
+    if S != S2:
+        raise SeiError("the scale transform is defined for square images only")
+    rate = _t(rate, "downsampling_rate").reshape(-1)
+    center = _t(center, "center").reshape(-1)
+    x2 = torch.empty_like(x_net)
+    So = S if rate_sr == 1 else down_out_size(S, rate_sr)
+    y = torch.empty((B, Cc, So, So), dtype=x_net.dtype, device=x_net.device)
+    n = _t(noise, "noise") if noise is not None else None
+    if kernel_host is not None:
+        k, kp = _host64(kernel_host)
+        kh, kw = k.shape
+    else:
+        kp, kh, kw = None, 0, 0
+    with torch.cuda.device(x_net.device):
+        check(_lib.load().sei_ei_remeasure_f32(_ptr(x_net), _ptr(x2), _ptr(y), B, Cc, S, _ptr(rate), _ptr(center),
+                                               kp, kh, kw, int(rate_sr), _ptr(n), float(sigma), _stream(x_net)))
+    return x2, y
+
+
+def add_noise(y, noise, sigma):
+    y, noise = _t(y, "y"), _t(noise, "noise")
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        check(_lib.load().sei_add_noise_f32(_ptr(y), _ptr(noise), y.numel(), float(sigma), _ptr(out), _stream(y)))
+    return out
+
+
+def sure_perturb(y, draw, margin, tau):
+    y, draw = _t(y, "y"), _t(draw, "draw")
+    B, Cc, H, W = y.shape
+    out, b = torch.empty_like(y), torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        check(_lib.load().sei_sure_perturb_f32(_ptr(y), _ptr(draw), B, Cc, H, W, int(margin), float(tau), _ptr(out),
+                                               _ptr(b), _stream(y)))
+    return out, b
+
+
+# ------------------------------------------------------------------------------ autograd
+class _BlurCircular(torch.autograd.Function):
+    """y = A x (adjoint=False) or A^T x; backward applies the other one (hand-written transpose)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel_host, adjoint, path):
+        ctx.kernel_host, ctx.adjoint, ctx.path = kernel_host, adjoint, path
+        return blur_circular(x, kernel_host, adjoint=adjoint, path=path)
+
+    @staticmethod
+    def backward(ctx, g):
+        return blur_circular(g, ctx.kernel_host, adjoint=not ctx.adjoint, path=ctx.path), None, None, None
+
+
+class _BlurCircularNoise(torch.autograd.Function):
+    """y = A x + sigma * noise in one kernel (physics(x) of the EI branch)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel_host, noise, sigma):
+        ctx.kernel_host = kernel_host
+        return blur_circular(x, kernel_host, noise=noise, sigma=sigma)
+
+    @staticmethod
+    def backward(ctx, g):
+        return blur_circular(g, ctx.kernel_host, adjoint=True), None, None, None
+
+
+class _BlurPadded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, filter_host, padding, transpose):
+        ctx.filter_host, ctx.padding, ctx.transpose = filter_host, padding, transpose
+        return blur_padded(x, filter_host, padding, transpose)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.padding == "zero":
+            raise NotImplementedError("backward through conv_transpose(padding='zero') is not supported")
+        return blur_padded(g, ctx.filter_host, ctx.padding, not ctx.transpose), None, None, None
+
+
+class _DownAA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rate, noise, sigma, path):
+        ctx.rate, ctx.in_hw, ctx.path = rate, tuple(x.shape[-2:]), path
+        return down_aa(x, rate, noise=noise, sigma=sigma, path=path)
+
+    @staticmethod
+    def backward(ctx, g):
+        return down_aa_transpose(g, ctx.rate, ctx.in_hw, path=ctx.path), None, None, None, None
+
+
+class _DownAATranspose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gy, rate, in_hw, path):
+        ctx.rate, ctx.path = rate, path
+        return down_aa_transpose(gy, rate, in_hw, path=path)
+
+    @staticmethod
+    def backward(ctx, g):
+        return down_aa(g, ctx.rate, path=ctx.path), None, None, None
+
+
+class _AddNoise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, noise, sigma):
+        return add_noise(y, noise, sigma)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+class _ScaleTransform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rate, center, path):
+        return scale_transform(x, rate, center, path=path)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError(
+            "backward through the scale transform (--no-ProposedLoss__stop_gradient) is not implemented yet; "
+            "the reference default is stop_gradient=True (demo/train.py:47-49)")
+
+
+class _Mse(torch.autograd.Function):
+    """nn.MSELoss(): mean((a-b)^2); backward = one elementwise kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _t(a, "input"), _t(b, "target")
+        if a.shape != b.shape:
+            raise SeiError(f"mse: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            check(_lib.load().sei_mse_f32(_ptr(a), _ptr(b), a.numel(), _ptr(out), _ptr(_workspace(a)), _stream(a)))
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous().float()
+        ga = torch.empty_like(a)
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            check(_lib.load().sei_mse_backward_f32(_ptr(a), _ptr(b), a.numel(), _ptr(g), _ptr(ga), _ptr(gb), _stream(a)))
+        return ga, gb
+
+
+class _SureLoss(torch.autograd.Function):
+    """SureGaussianLoss given y1 = A(x_net), y2 = A(model(y + tau b)) -> scalar; see sei_sure_loss_f32."""
+
+    @staticmethod
+    def forward(ctx, y1, y2, y, b, margin_mse, margin_div, tau, sigma2, averaged_cst):
+        y1, y2, y, b = _t(y1, "y1"), _t(y2, "y2"), _t(y, "y"), _t(b, "b")
+        B, Cc, H, W = y.shape
+        out = torch.empty((3,), dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            check(_lib.load().sei_sure_loss_f32(_ptr(y1), _ptr(y2), _ptr(y), _ptr(b), B, Cc, H, W, int(margin_mse),
+                                                int(margin_div), float(tau), float(sigma2), int(bool(averaged_cst)),
+                                                _ptr(out), _ptr(_workspace(y)), _stream(y)))
+        ctx.save_for_backward(y1, y, b)
+        ctx.cfg = (int(margin_mse), int(margin_div), float(tau), float(sigma2))
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g, _g_aux):
+        y1, y, b = ctx.saved_tensors
+        B, Cc, H, W = y.shape
+        mm, md, tau, sigma2 = ctx.cfg
+        g = g.contiguous().float()
+        g1, g2 = torch.empty_like(y1), torch.empty_like(y1)
+        with torch.cuda.device(y.device):
+            check(_lib.load().sei_sure_loss_backward_f32(_ptr(y1), _ptr(y), _ptr(b), B, Cc, H, W, mm, md, tau, sigma2,
+                                                         _ptr(g), _ptr(g1), _ptr(g2), _stream(y)))
+        return g1, g2, None, None, None, None, None, None, None
+
+
+class _McDiv(torch.autograd.Function):
+    """mean over the interior of b*(y2-y1)/tau (sure.py mc_div), differentiable in y1 and y2.
+    Reuses the SURE kernels: the residual term vanishes when y := y1, and sigma2 = 1/2 turns the
+    2*sigma2 factor into 1."""
+
+    @staticmethod
+    def forward(ctx, y1, y2, b, margin, tau):
+        y1, y2, b = _t(y1, "y1"), _t(y2, "y2"), _t(b, "b")
+        B, Cc, H, W = y1.shape
+        out = torch.empty((3,), dtype=torch.float32, device=y1.device)
+        with torch.cuda.device(y1.device):
+            check(_lib.load().sei_sure_loss_f32(_ptr(y1), _ptr(y2), _ptr(y1), _ptr(b), B, Cc, H, W, int(margin),
+                                                int(margin), float(tau), 0.5, 1, _ptr(out), _ptr(_workspace(y1)),
+                                                _stream(y1)))
+        ctx.save_for_backward(y1, b)
+        ctx.cfg = (int(margin), float(tau))
+        return out[2].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        y1, b = ctx.saved_tensors
+        B, Cc, H, W = y1.shape
+        margin, tau = ctx.cfg
+        g = g.contiguous().float()
+        g1, g2 = torch.empty_like(y1), torch.empty_like(y1)
+        with torch.cuda.device(y1.device):
+            check(_lib.load().sei_sure_loss_backward_f32(_ptr(y1), _ptr(y1), _ptr(b), B, Cc, H, W, margin, margin, tau,
+                                                         0.5, _ptr(g), _ptr(g1), _ptr(g2), _stream(y1)))
+        return g1, g2, None, None, None
+
+
+def mc_div(y1, y2, b, margin, tau):
+    return _McDiv.apply(y1, y2, b, margin, tau)
+
+
+def mse(a, b):
+    return _Mse.apply(a, b)
+
+
+def sure_loss(y1, y2, y, b, margin_mse, margin_div, tau, sigma2, averaged_cst):
+    loss, aux = _SureLoss.apply(y1, y2, y, b, margin_mse, margin_div, tau, sigma2, averaged_cst)
+    return loss, aux

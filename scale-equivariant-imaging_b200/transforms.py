@@ -1,0 +1,122 @@
+"""Random scale transform (reference: src/transforms.py) on the libsei_b200 kernels.
+
+Same public names and call signatures: sample_from, sample_downsampling_parameters,
+get_downsampling_grid, padded_downsampling_transform, PaddedDownsamplingTransform,
+ScalingTransform, CombinedTransform.  The sampling grid is never materialised on the hot path:
+the kernel recomputes its coordinates with the reference's fp32 rounding sequence."""
+import torch
+from torch.nn import Module
+
+from sei_b200 import draws, ops
+
+
+def sample_from(values, shape=(1,), dtype=torch.float32, device="cpu"):
+    """values[floor(len(values) * U)], U ~ rand(shape)   (reference :5-11)."""
+    u = draws.rand(tuple(shape), device, dtype)
+    idx = torch.floor(len(values) * u).to(torch.int)
+    return torch.tensor(values, device=device, dtype=dtype)[idx]
+
+
+def sample_downsampling_parameters(image_count, device, dtype, rates):
+    """Draw order and shapes of the reference (:14-24): rand((B,)) for the rates, then
+    rand((B, 2)) for the centres.  Returns rate (B,) and center (B,1,1,2) in [-1, 1]."""
+    u_rate = draws.rand((image_count,), device, dtype)
+    u_center = draws.rand((image_count, 2), device, dtype)
+    if u_rate.is_cuda and dtype == torch.float32:
+        return ops.scale_params(u_rate, u_center, rates)
+    values = torch.tensor(rates, device=device, dtype=dtype)
+    idx = torch.floor(len(rates) * u_rate).to(torch.int)
+    return values[idx], 2 * u_center.view(image_count, 1, 1, 2) - 1
+
+
+def get_downsampling_grid(shape, downsampling_rate, center, dtype, device):
+    """The sampling grid of the reference (:27-43), for inspection only: the kernels evaluate it
+    analytically.  Square images only, like the reference (its .view scrambles h != w)."""
+    b, _, h, w = shape
+    u = 2 / w * torch.arange(w, dtype=dtype, device=device) - 1
+    v = 2 / h * torch.arange(h, dtype=dtype, device=device) - 1
+    U, V = torch.meshgrid(u, v, indexing="ij")
+    grid = torch.stack([V, U], dim=-1).view(1, h, w, 2).repeat(b, 1, 1, 1)
+    inv = 1 / downsampling_rate.view(b, 1, 1, 1).expand_as(grid)
+    return inv * (grid - center) + center
+
+
+def padded_downsampling_transform(x, downsampling_rate, center, mode, padding_mode, antialiased):
+    """Zoom-out of each image by its rate about its centre; bicubic taps, reflection padding,
+    same output size (reference :60-83).  downsampling_rate: (B,), center: (B,1,1,2)."""
+    if mode != "bicubic" or padding_mode != "reflection":
+        raise NotImplementedError("only mode='bicubic', padding_mode='reflection' (the only combination the "
+                                  "reference ever passes, src/transforms.py:105-106) is built")
+    if antialiased:
+        raise NotImplementedError("ScalingTransform(antialias=True) (per-image pre-filter) is not built yet; "
+                                  "the reference default is antialias=False (demo/train.py:49-51)")
+    return ops._ScaleTransform.apply(x, downsampling_rate, center, ops.PATH_AUTO)
+
+
+class PaddedDownsamplingTransform(Module):
+    def __init__(self, antialias, downsampling_rates):
+        super().__init__()
+        self.antialias = antialias
+        self.downsampling_rates = downsampling_rates
+
+    def _sample(self, x):
+        return sample_downsampling_parameters(image_count=x.shape[0], device=x.device, dtype=x.dtype,
+                                              rates=self.downsampling_rates)
+
+    def forward(self, x):
+        rate, center = self._sample(x)
+        return padded_downsampling_transform(x, downsampling_rate=rate, center=center, antialiased=self.antialias,
+                                             mode="bicubic", padding_mode="reflection")
+
+    def fused_remeasure(self, x_net, physics, apply_noise=True):
+        """x2 = T(x_net) and y = A(x2) + sigma * n in one kernel (sei_ei_remeasure_f32).  The
+        random tensors are drawn in the reference's order: rates, centres, then the noise."""
+        args = physics.ei_remeasure_args()
+        if self.antialias or args is None:
+            return None
+        rate, center = self._sample(x_net)
+        B, C, S, _ = x_net.shape
+        r = args["rate_sr"]
+        So = S if r == 1 else ops.down_out_size(S, r)
+        noise = draws.randn((B, C, So, So), x_net.device, x_net.dtype) if apply_noise else None
+        sigma = physics.noise_model.sigma_value() if apply_noise else 0.0
+        return ops.ei_remeasure(x_net, rate, center, args["kernel_host"], r, noise, sigma)
+
+
+class NormalDownsamplingTransform(Module):
+    def __init__(self, antialias, downsampling_rates):
+        super().__init__()
+        raise NotImplementedError("ScalingTransform(kind='normal') is not built yet (SURVEY.md section 8f, N3)")
+
+
+class ScalingTransform(Module):
+    def __init__(self, kind, antialias):
+        super().__init__()
+        downsampling_rates = [0.75, 0.5]
+        if kind == "padded":
+            self.transform = PaddedDownsamplingTransform(antialias=antialias, downsampling_rates=downsampling_rates)
+        elif kind == "normal":
+            self.transform = NormalDownsamplingTransform(antialias=antialias, downsampling_rates=downsampling_rates)
+        else:
+            raise ValueError(f"Unknown kind: {kind}")
+
+    def forward(self, x):
+        return self.transform(x)
+
+    def fused_remeasure(self, x_net, physics, apply_noise=True):
+        out = self.transform.fused_remeasure(x_net, physics, apply_noise=apply_noise)
+        if out is None:
+            x2 = self.transform(x_net)
+            return x2, (physics(x2) if apply_noise else physics.A(x2))
+        return out
+
+
+class CombinedTransform(Module):
+    def __init__(self, transforms):
+        super().__init__()
+        self.transforms = transforms
+
+    def forward(self, x):
+        for transform in self.transforms:
+            x = transform(x)
+        return x

@@ -1,0 +1,186 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, argument
+validation fails loudly without touching a device, the host-side mirrors of the reference's
+glue (kernels, crop, factories, draw order) behave like the reference (golden vectors)."""
+import os
+import re
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+import sei_b200
+from sei_b200 import _lib, draws, ops
+from util import rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def base_args(**kw):
+    a = dict(task="deblurring", noise_level=5, physics_v2=True, kernel="Gaussian_R2", sr_factor=None,
+             physics_true_adjoint=False, partial_sure=True, sure_margin=None, partial_sure_sr=False,
+             Loss__crop_training_pairs=False, Loss__crop_size=48, ProposedLoss__stop_gradient=True,
+             ProposedLoss__sure_alternative=None, ProposedLoss__alpha_tradeoff=1.0,
+             ProposedLoss__transforms="Scaling_Transforms", ScalingTransform__kind="padded",
+             ScalingTransform__antialias=False, method="proposed", sure_cropped_div=True,
+             sure_averaged_cst=None)
+    a.update(kw)
+    return Namespace(**a)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sei_b200.h")).read()
+    declared = set(re.findall(r"\b(sei_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"libsei_b200.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sei_abi_version() == 1
+    assert lib.sei_reduce_workspace_bytes() > 0
+
+
+def test_sass_is_blackwell_native():
+    """the tiled kernels stage their tiles with the TMA engine (bulk async copies -> UBLKCP)"""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert out.count("UBLKCP") >= 8
+    assert "SYNCS.ARRIVE.TRANS64" in out
+
+
+def test_argument_validation_needs_no_device():
+    lib = _lib.load()
+    k = np.ones((3, 3))
+    rc = lib.sei_blur_circular_f32(None, None, 1, 8, 8, k.ctypes.data, 3, 3, 0, None, 0.0, 0, None)
+    assert rc == -22 and b"null" in lib.sei_last_error()
+    rc = lib.sei_down_aa_f32(1, 1, 1, 8, 8, 7, None, 0.0, 0, None)
+    assert rc == -22 and b"rate" in lib.sei_last_error()
+    with pytest.raises(_lib.SeiError):
+        _lib.check(rc)
+
+
+def test_cpu_tensors_fail_loudly():
+    x = torch.rand(1, 3, 16, 16)
+    k = ops.kernel_to_host(torch.ones(1, 1, 3, 3) / 9)
+    with pytest.raises(sei_b200.SeiError, match="no CPU fallback"):
+        ops.blur_circular(x, k)
+    with pytest.raises(sei_b200.SeiError):
+        ops.mse(x, x)
+    import physics
+    phys = physics.get_physics(base_args(), device="cpu")
+    with pytest.raises(sei_b200.SeiError):
+        phys.A(x)
+    if not torch.cuda.is_available():
+        lib = _lib.load()
+        assert lib.sei_device_info(None, None, None, None) != 0   # no device -> error code, not a fallback
+
+
+def test_float64_is_rejected():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a device to get past the device check")
+    with pytest.raises(sei_b200.SeiError, match="float32"):
+        ops.blur_circular(torch.rand(1, 1, 16, 16, dtype=torch.float64, device="cuda"), np.ones((3, 3)) / 9)
+
+
+def test_named_kernels(golden):
+    from physics.kernels import get_kernel
+    g = golden("kernels")
+    for name, ref in g.items():
+        k = get_kernel(name)
+        assert k.dtype == torch.float64
+        assert rel_err(k.numpy(), ref) < 1e-15
+    with pytest.raises(AssertionError):
+        get_kernel("Gaussian_R7")
+
+
+def test_factories_build_the_reference_objects():
+    import losses
+    import physics
+    for kw, cls, margin in [(dict(), physics.BlurV2, 6), (dict(physics_v2=False), physics.Blur, 6),
+                            (dict(kernel="Box_R3"), physics.BlurV2, 3),
+                            (dict(task="sr", kernel=None, sr_factor=2), physics.Downsampling, 0),
+                            (dict(task="sr", kernel=None, sr_factor=4, partial_sure_sr=True), physics.Downsampling, 2)]:
+        args = base_args(**kw)
+        phys = physics.get_physics(args, device="cpu")
+        assert isinstance(phys, cls)
+        assert phys.task == args.task
+        mgr = getattr(phys, "__manager")
+        assert mgr.physics is phys and mgr.task == args.task
+        assert abs(float(phys.noise_model.sigma) - 5 / 255) < 1e-8
+        if args.task == "deblurring":
+            assert phys.filter.shape[:2] == (1, 1) and phys.filter.dtype == torch.float64
+            assert not hasattr(phys, "rate")
+        else:
+            assert phys.rate == args.sr_factor
+        loss = losses.get_loss(args, phys)
+        assert isinstance(loss.loss, losses.ProposedLoss)
+        sure, ei = loss.loss.loss_fns
+        assert sure.margin == margin and sure.cropped_div and not sure.averaged_cst
+        assert abs(sure.sigma2 - (5 / 255) ** 2) < 1e-12 and sure.tau == 1e-2
+        assert ei.no_grad and ei.weight == 1.0 and ei.noise
+        assert loss.crop_fn is None
+    with pytest.raises(ValueError):
+        physics.get_physics(base_args(task="nope"), device="cpu")
+    phys = physics.get_physics(base_args(), device="cpu")
+    with pytest.raises(ValueError):
+        losses.get_loss(base_args(method="ei-shift"), phys)   # README names the code does not accept
+    for m, cls in [("supervised", losses.SupervisedLoss), ("css", losses.CSSLoss), ("sure", losses.SURELoss),
+                   ("noise2inverse", losses.Noise2InverseLoss)]:
+        assert isinstance(losses.get_loss(base_args(method=m), phys).loss, cls)
+    crop_loss = losses.get_loss(base_args(Loss__crop_training_pairs=True), phys)
+    assert crop_loss.crop_fn is not None and crop_loss.xy_size_ratio == 1
+
+
+def test_crop_pair_matches_reference(golden):
+    from crop import CropPair
+    g = golden("crop")
+    x3, y3 = torch.from_numpy(g["d3_x"]), torch.from_numpy(g["d3_y"])
+    torch.manual_seed(11)
+    xc, yc = CropPair(location="random", size=24)(x3, y3, xy_size_ratio=2)
+    assert np.array_equal(xc.numpy(), g["d3_xc"]) and np.array_equal(yc.numpy(), g["d3_yc"])
+    xc, yc = CropPair(location="center", size=24)(x3, y3)
+    assert np.array_equal(xc.numpy(), g["d3c_xc"]) and np.array_equal(yc.numpy(), g["d3c_yc"])
+    # batched inputs: the reference pads size - C zero rows before cropping (quirk kept)
+    x4, y4 = torch.from_numpy(g["d4_x"]), torch.from_numpy(g["d4_y"])
+    for seed in (0, 1, 2, 3):
+        torch.manual_seed(seed)
+        xc, yc = CropPair(location="random", size=48)(x4, y4, xy_size_ratio=1)
+        assert np.array_equal(xc.numpy(), g[f"d4_s{seed}_xc"]) and np.array_equal(yc.numpy(), g[f"d4_s{seed}_yc"])
+
+
+def test_transform_parameter_draw_order(golden):
+    """rates first, then centres; same mapping from uniforms as the reference (CPU branch)"""
+    import transforms
+    g = golden("transform")
+    torch.manual_seed(0)
+    rate, center = transforms.sample_downsampling_parameters(16, "cpu", torch.float32, [0.75, 0.5])
+    assert np.array_equal(rate.numpy(), g["params_rate"])
+    assert np.array_equal(center.numpy(), g["params_center"])
+    with draws.inject([g["params_draw0_rand"], g["params_draw1_rand"]]):
+        rate2, center2 = transforms.sample_downsampling_parameters(16, "cpu", torch.float32, [0.75, 0.5])
+    assert torch.equal(rate, rate2) and torch.equal(center, center2)
+    grid = transforms.get_downsampling_grid((4, 3, 24, 24), torch.from_numpy(g["c0_rate"]).float(),
+                                            torch.from_numpy(g["c0_center"]).float(), torch.float32, "cpu")
+    assert np.array_equal(grid.numpy(), g["c0_grid_f32"])
+
+
+def test_draw_injection_is_strict():
+    with pytest.raises(RuntimeError, match="shape"):
+        with draws.inject([np.zeros((2, 2), np.float32)]):
+            draws.rand((3,), "cpu", torch.float32)
+    with pytest.raises(RuntimeError, match="not consumed"):
+        with draws.inject([np.zeros((2,), np.float32)]):
+            pass
+
+
+def test_unbuilt_variants_say_so():
+    import transforms
+    with pytest.raises(NotImplementedError):
+        transforms.ScalingTransform(kind="normal", antialias=False)
+    with pytest.raises(ValueError):
+        transforms.ScalingTransform(kind="other", antialias=False)
