@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Kernel-time breakdown of one eager `proposed` training step with the CNN (torch.profiler, CUDA activity):
+which kernels the step's GPU time goes to.  Shares only -- absolute numbers come from bench.py."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "scale-equivariant-imaging_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--cnn-hidden", type=int, default=32)
+    ap.add_argument("--cnn-scales", type=int, default=5)
+    ap.add_argument("--rows", type=int, default=45)
+    args = ap.parse_args()
+    import losses
+    import models
+    import physics
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    phys = physics.get_physics(bench.loss_args(), device=dev)
+    loss_fn = losses.get_loss(bench.loss_args(), phys)
+    model = models.get_model(bench.model_args(args.cnn_hidden, args.cnn_scales), physics=phys, device=dev).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    x = torch.rand(args.batch, 3, 256, 256, device=dev)
+    y = phys(x)
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = loss_fn(x=x, y=y, model=model)
+        loss.backward()
+        opt.step()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    evs = prof.key_averages()
+    total = sum(e.device_time_total for e in evs)
+    print(f"# batch {args.batch}, total CUDA time of one step: {total / 1e3:.1f} ms")
+    print("| share | calls | total ms | kernel |")
+    print("|---|---|---|---|")
+    for e in sorted(evs, key=lambda e: -e.device_time_total)[: args.rows]:
+        print(f"| {100 * e.device_time_total / total:.1f}% | {e.count} | {e.device_time_total / 1e3:.2f} | {e.key[:110]} |")
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,18 @@ int sei_sure_perturb_f32(const float* y, const float* draw, int B, int C, int H,
 int sei_add_noise_f32(const float* y, const float* noise, long long n, float sigma, float* out,
                       void* stream);
 
+/* ---- restoration CNN: dense contractions ---------------------------------------------------
+ * bf16 x bf16 -> fp32-accumulate GEMM on tcgen05 tensor cores (TMEM accumulator, TMA operand tiles):
+ *     D[M, N] = A[M, K] * B[N, K]^T (+ bias[N])
+ * A, B: bf16 row-major with leading dimensions lda, ldb (elements, multiples of 8); D: bf16
+ * (out_f32 == 0) or fp32 row-major with leading dimension ldd; bias: fp32 or NULL.
+ * Replaces the cuDNN/cuBLAS calls behind nn.Conv2d(kernel_size=1) of the reference's
+ * ConvolutionalModel (src/models/convolutional.py:40-42,106,143) on channels-last activations
+ * (M = B*H*W pixels, K = C_in, N = C_out, B = weight); dgrad and wgrad use the same entry with the
+ * operand roles permuted.  tile_n: 0 = auto, or 32 / 64 / 128 / 256. */
+int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
+                     long long lda, long long ldb, long long ldd, int out_f32, int tile_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

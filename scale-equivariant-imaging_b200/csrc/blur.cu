@@ -19,7 +19,6 @@
 
 namespace sei {
 
-constexpr int kBandThreads = 256;
 
 struct BlurBandParams {
     const float* x;
@@ -27,45 +26,65 @@ struct BlurBandParams {
     const float* noise;
     float sigma;
     int H, W, TH, nbands;
+    long long total_bands;
     float cv[kMaxK];   // correlation-form taps: y[n] = sum_t c[t] x[n + t - P]
     float ch[kMaxK];
 };
 
-template <int K, bool NOISE>
-__global__ void __launch_bounds__(kBandThreads, 2) blur_band_kernel(const __grid_constant__ BlurBandParams p)
+// Persistent, software-pipelined: each CTA walks bands blockIdx.x, blockIdx.x + gridDim.x, ... and keeps
+// two input stages in shared memory, so the bulk copy of band i+1 is in flight while band i is filtered.
+template <int K, bool NOISE, int NT, int WT>
+__global__ void __launch_bounds__(NT) blur_band_kernel(const __grid_constant__ BlurBandParams p)
 {
     constexpr int P = K / 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
 
-    const int H = p.H, W = p.W;
-    const int band = blockIdx.x % p.nbands;
-    const long long plane = blockIdx.x / p.nbands;
-    const int r0 = band * p.TH;
-    const int th = min(p.TH, H - r0);
-    const int rin = th + 2 * P;
+    const int H = p.H, W = WT ? WT : p.W;
+    const size_t stage_floats = (size_t)(p.TH + 2 * P) * W;
+    float* sIn = reinterpret_cast<float*>(smem_raw);      // [2][TH + 2P][W]
+    float* sMid = sIn + 2 * stage_floats;                  // [TH][W]
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+    const long long total = p.total_bands;
 
-    float* sIn = reinterpret_cast<float*>(smem_raw);      // [TH + 2P][W]
-    float* sMid = sIn + (size_t)(p.TH + 2 * P) * W;       // [TH][W]
+    auto issue = [&](long long w, int buf) {
+        const int band = (int)(w % p.nbands);
+        const long long plane = w / p.nbands;
+        const int r0 = band * p.TH;
+        const int rin = min(p.TH, H - r0) + 2 * P;
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)rin * row_bytes);
+        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sIn + buf * stage_floats),
+                                reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * H * W), H, row_bytes,
+                                r0 - P, rin, &bar[buf]);
+    };
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t row_bytes = (uint32_t)W * 4u;
-        mbar_arrive_expect_tx(&bar, (uint32_t)rin * row_bytes);
-        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sIn),
-                                reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * H * W), H, row_bytes,
-                                r0 - P, rin, &bar);
-    }
-    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0 && (long long)blockIdx.x < total) issue(blockIdx.x, 0);
 
-    blur_vpass<K, kBandThreads>(sIn, sMid, W, th, p.cv);
-    __syncthreads();
-    const size_t row0 = ((size_t)plane * H + r0) * W;
-    blur_hpass<K, kBandThreads, NOISE>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
+    int it = 0;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (threadIdx.x == 0 && w + gridDim.x < total) {
+            fence_proxy_async();              // stage buf^1 was read by generic loads in iteration it-1
+            issue(w + gridDim.x, buf ^ 1);
+        }
+        const int band = (int)(w % p.nbands);
+        const long long plane = w / p.nbands;
+        const int r0 = band * p.TH;
+        const int th = min(p.TH, H - r0);
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+
+        blur_vpass<K, NT, WT, true>(sIn + buf * stage_floats, sMid, W, th, p.cv);
+        __syncthreads();
+        const size_t row0 = ((size_t)plane * H + r0) * W;
+        blur_hpass<K, NT, NOISE, WT, true>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
+        __syncthreads();
+    }
 }
 
 struct BlurDirectParams {
@@ -124,41 +143,68 @@ bool factor_separable_public(const double* k, int kh, int kw, double* v, double*
     return factor_separable(k, kh, kw, v, h);
 }
 
-template <int K>
-static int launch_band(const BlurBandParams& p, long long planes, size_t smem, cudaStream_t st)
-{
-    const unsigned grid = (unsigned)(planes * p.nbands);
-    if (p.noise) {
-        SEI_CUDA(allow_smem(blur_band_kernel<K, true>, smem));
-        blur_band_kernel<K, true><<<grid, kBandThreads, smem, st>>>(p);
-        return finish_launch("blur_band_kernel<noise>");
-    }
-    SEI_CUDA(allow_smem(blur_band_kernel<K, false>, smem));
-    blur_band_kernel<K, false><<<grid, kBandThreads, smem, st>>>(p);
-    return finish_launch("blur_band_kernel");
-}
-
 static int env_int(const char* name, int dflt)
 {
     const char* s = getenv(name);
     return s && *s ? atoi(s) : dflt;
 }
 
-// pick the band height: largest multiple of 8 (<= 64) such that two CTAs fit per SM
-int blur_pick_band_rows(int H, int W, int P, int smem_optin)
+template <int K, bool NOISE, int WT>
+static int launch_band_w(const BlurBandParams& p, size_t smem, int ctas_per_sm, int sm_count, cudaStream_t st)
 {
-    const int forced = env_int("SEI_BLUR_TH", 0);
-    const size_t budget = std::min((size_t)smem_optin, (size_t)110 * 1024);
+    constexpr int NT = 256;
+    SEI_CUDA(allow_smem(blur_band_kernel<K, NOISE, NT, WT>, smem));
+    const long long want = (long long)sm_count * ctas_per_sm;
+    const unsigned grid = (unsigned)std::min<long long>(p.total_bands, want);
+    blur_band_kernel<K, NOISE, NT, WT><<<grid, NT, smem, st>>>(p);
+    return finish_launch(NOISE ? "blur_band_kernel<noise>" : "blur_band_kernel");
+}
+
+// width-specialised instantiations for the benchmark shapes (256: cfg2/cfg4, 512: cfg5), run-time width otherwise
+template <int K>
+static int launch_band(const BlurBandParams& p, size_t smem, int ctas_per_sm, int sm_count, cudaStream_t st)
+{
+    const bool spec = env_int("SEI_BLUR_NOSPEC", 0) == 0;
+    if (spec && p.W == 256)
+        return p.noise ? launch_band_w<K, true, 256>(p, smem, ctas_per_sm, sm_count, st)
+                       : launch_band_w<K, false, 256>(p, smem, ctas_per_sm, sm_count, st);
+    if (spec && p.W == 512)
+        return p.noise ? launch_band_w<K, true, 512>(p, smem, ctas_per_sm, sm_count, st)
+                       : launch_band_w<K, false, 512>(p, smem, ctas_per_sm, sm_count, st);
+    return p.noise ? launch_band_w<K, true, 0>(p, smem, ctas_per_sm, sm_count, st)
+                   : launch_band_w<K, false, 0>(p, smem, ctas_per_sm, sm_count, st);
+}
+
+struct BandConfig {
+    int TH, threads, ctas_per_sm;
+    size_t smem;
+};
+
+// two input stages of (th + 2P) rows + one halo-padded intermediate of th rows (pitch W + 2 * 4 * ceil(P/4))
+static size_t blur_band_smem(int th, int P, int W)
+{
+    return ((size_t)(2 * th + 4 * P) * W + (size_t)th * (W + 8 * ((P + 3) / 4))) * 4;
+}
+
+// Band height / CTA shape: prefer TH = 32 (halo re-read factor (TH+2P)/TH from L2), two pipelined stages per CTA.
+// Overridable for tuning: SEI_BLUR_TH, SEI_BLUR_THREADS, SEI_BLUR_CTAS.
+BandConfig blur_pick_band_config(int H, int W, int P, int smem_optin)
+{
+    BandConfig c = {0, 256, 1, 0};
+    const int per_sm = 227 * 1024;
     int best = 0;
-    for (int th = 8; th <= 64; th += 8) {
-        const size_t need = (size_t)(2 * th + 2 * P) * W * 4;
-        if (need <= budget) best = th;
-    }
-    if (best == 0 && (size_t)(16 + 2 * P) * W * 4 <= (size_t)smem_optin) best = 8;   // one CTA per SM
-    if (forced > 0 && forced % 8 == 0 && (size_t)(2 * forced + 2 * P) * W * 4 <= (size_t)smem_optin) best = forced;
-    if (best == 0) return 0;
-    const int hceil = ((H + 7) / 8) * 8;
-    return std::min(best, hceil);
+    for (int th = 8; th <= 16; th += 8)   // TH = 16 with three CTAs per SM measured best on B200 (profiles/r01_blur_tuning.md)
+        if (blur_band_smem(th, P, W) + 1024 <= (size_t)smem_optin) best = th;
+    const int forced = env_int("SEI_BLUR_TH", 0);
+    if (forced > 0 && forced % 8 == 0 && blur_band_smem(forced, P, W) + 1024 <= (size_t)smem_optin) best = forced;
+    if (best == 0) return c;
+    c.TH = std::min(best, ((H + 7) / 8) * 8);
+    c.smem = blur_band_smem(c.TH, P, W);
+    c.ctas_per_sm = std::max(1, std::min(4, (int)(per_sm / (c.smem + 1024))));
+    c.threads = 256;
+    const int fc = env_int("SEI_BLUR_CTAS", 0);
+    if (fc >= 1 && fc <= c.ctas_per_sm) c.ctas_per_sm = fc;
+    return c;
 }
 
 }  // namespace sei
@@ -185,7 +231,9 @@ extern "C" int sei_blur_circular_f32(const float* x, float* y, long long planes,
     const bool sep = kh == kw && (kh % 2 == 1) && factor_separable(kernel_host, kh, kw, v, h);
     const bool ksupported = kh == 5 || kh == 7 || kh == 9 || kh == 13 || kh == 19;
     const int P = kh / 2;
-    const int TH = sep && ksupported && (W % 4 == 0) && W >= 4 * ((P + 3) / 4) ? blur_pick_band_rows(H, W, P, dp.smem_optin) : 0;
+    BandConfig cfg = {0, 256, 1, 0};
+    if (sep && ksupported && (W % 4 == 0) && W >= 4 * ((P + 3) / 4)) cfg = blur_pick_band_config(H, W, P, dp.smem_optin);
+    const int TH = cfg.TH;
     const bool aligned = aligned16(x) && aligned16(y) && (!noise || aligned16(noise));
     const bool tiled_ok = TH > 0 && aligned && planes * ((H + TH - 1) / TH) < (1ll << 31);
     SEI_REQUIRE(path != SEI_PATH_TILED || tiled_ok,
@@ -195,18 +243,18 @@ extern "C" int sei_blur_circular_f32(const float* x, float* y, long long planes,
         BlurBandParams p;
         p.x = x; p.y = y; p.noise = noise; p.sigma = sigma;
         p.H = H; p.W = W; p.TH = TH; p.nbands = (H + TH - 1) / TH;
+        p.total_bands = planes * p.nbands;
         for (int t = 0; t < kh; ++t) {
             // forward (convolution): c[t] = h[K-1-t]; transpose (correlation): c[t] = h[t]
             p.cv[t] = (float)(adjoint ? v[t] : v[kh - 1 - t]);
             p.ch[t] = (float)(adjoint ? h[t] : h[kh - 1 - t]);
         }
-        const size_t smem = (size_t)(2 * TH + 2 * P) * W * 4;
         switch (kh) {
-        case 5: return launch_band<5>(p, planes, smem, st);
-        case 7: return launch_band<7>(p, planes, smem, st);
-        case 9: return launch_band<9>(p, planes, smem, st);
-        case 13: return launch_band<13>(p, planes, smem, st);
-        default: return launch_band<19>(p, planes, smem, st);
+        case 5: return launch_band<5>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
+        case 7: return launch_band<7>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
+        case 9: return launch_band<9>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
+        case 13: return launch_band<13>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
+        default: return launch_band<19>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
         }
     }
 

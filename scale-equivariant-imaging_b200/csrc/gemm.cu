@@ -1,0 +1,344 @@
+// gemm.cu -- bf16 x bf16 -> fp32-accumulate GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA),
+// the dense contraction of the restoration CNN (reference: src/models/convolutional.py, the 1x1
+// convolutions :40-42,106,143 and, through an unfold, the 3x3 in/out convolutions :175-176).
+//
+//     D[M, N] = A[M, K] * B[N, K]^T (+ bias[N])          A, B: bf16 row-major (K contiguous, "TN")
+//
+// A pointwise convolution on channels-last activations is exactly this GEMM with M = B*H*W pixels,
+// K = C_in, N = C_out, B = the (C_out, C_in) weight -- no layout change, and dgrad / wgrad are the
+// same kernel with the operand roles permuted.
+//
+// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0   TMA producer: one elected lane streams 128x64 (A) and BNx64 (B) bf16 boxes into a
+//            ring of shared-memory stages (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier tx completion)
+//   warp 1   allocates BN TMEM columns, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16,
+//            both operands from shared-memory descriptors, fp32 accumulator in TMEM) and releases each
+//            stage with tcgen05.commit
+//   warps 2-5  epilogue: tcgen05.ld the accumulator (each warp its 32-lane quarter), add the bias,
+//            convert, store 16-byte vectors
+// Out-of-range rows/columns/k are zero-filled by TMA on load and masked on store.
+#include "sei_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <mutex>
+
+namespace sei {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;          // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kGemmThreads = 192;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major bf16 tile stored by TMA with SWIZZLE_128B:
+// rows of 128 B, 8-row groups of 1024 B (SBO), 16-byte chunks XOR-swizzled inside a group.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;                   // stride byte offset = 8 rows * 128 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100), bits [46,48)
+    d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+
+// instruction descriptor: dense, D = f32, A = B = bf16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmParams {
+    void* D;
+    const float* bias;
+    int M, N, K, ldd;
+    int kb_per_split;    // k-blocks per grid.z slice (split-K: fp32 output only, slices accumulate with atomics)
+    int splits;
+};
+
+template <int BN, int STAGES, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ GemmParams p)
+{
+    constexpr int BM = kGemmBM, BK = kGemmBK;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32 for BN in {32, 64, 128, 256}
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    // SWIZZLE_128B tiles must start on a 1024-byte boundary
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nk_total = (p.K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;      // k-blocks of this split (>= 1 by construction)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t use = kb / STAGES;
+                if (kb >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
+                tma_load_2d(a_dst, &map_a, (kb0 + kb) * BK, m0, &full_bar[s]);
+                tma_load_2d(a_dst + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);             // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            tmem_ld_wait();
+            const int col0 = n0 + c;
+            if (row < p.M && col0 < p.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias && blockIdx.z == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                }
+                if (OUT_F32 && p.splits > 1) {
+                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+                } else if (OUT_F32) {
+                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+                    if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
+                    }
+                } else {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+                    if (col0 + 32 <= p.N && (p.ldd & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                                           t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows rows, SWIZZLE_128B
+static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    SEI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SEI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, bool out_f32, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024;
+    dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN, p.splits);
+    if (out_f32) {
+        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true>, smem));
+        gemm_bf16_tn_kernel<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+    } else {
+        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false>, smem));
+        gemm_bf16_tn_kernel<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+    }
+    return finish_launch("gemm_bf16_tn_kernel");
+}
+
+}  // namespace sei
+
+using namespace sei;
+
+extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
+                                long long lda, long long ldb, long long ldd, int out_f32, int tile_n, void* stream)
+{
+    SEI_REQUIRE(A && B && D, "null pointer argument");
+    SEI_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "bad shape M=%lld N=%d K=%d", M, N, K);
+    SEI_REQUIRE(lda >= K && ldb >= K && ldd >= N, "leading dimensions smaller than the rows");
+    SEI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA row pitch); pad K");
+    SEI_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), "A, B, D must be 16-byte aligned");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    SEI_REQUIRE(dp.cc_major == 10, "tcgen05 GEMM needs an sm_100 device");
+    int bn = tile_n;
+    if (bn == 0) bn = N >= 256 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+    SEI_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "tile_n must be 0, 32, 64, 128 or 256");
+    SEI_REQUIRE((M + kGemmBM - 1) / kGemmBM <= 2147483647ll && (N + bn - 1) / bn <= 65535, "grid too large");
+    CUtensorMap ma, mb;
+    rc = make_map_bf16(&ma, A, M, K, lda, kGemmBM);
+    if (rc) return rc;
+    rc = make_map_bf16(&mb, B, N, K, ldb, bn);
+    if (rc) return rc;
+    GemmParams p;
+    p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // split-K for the weight-gradient shapes (few output tiles, very long K = pixels): fp32 output only
+    const int nk = (K + kGemmBK - 1) / kGemmBK;
+    const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * (long long)((N + bn - 1) / bn);
+    p.splits = 1;
+    p.kb_per_split = nk;
+    if (out_f32 && tiles < dp.sm_count && nk >= 8 && ldd == N) {
+        int want = (int)std::min<long long>((2ll * dp.sm_count + tiles - 1) / tiles, nk / 4);
+        want = std::max(1, std::min(want, 512));
+        p.kb_per_split = (nk + want - 1) / want;
+        p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
+        if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+    }
+    switch (bn) {
+    case 32: return launch_gemm<32, 8>(ma, mb, p, out_f32 != 0, st);
+    case 64: return launch_gemm<64, 8>(ma, mb, p, out_f32 != 0, st);
+    case 128: return launch_gemm<128, 6>(ma, mb, p, out_f32 != 0, st);
+    default: return launch_gemm<256, 4>(ma, mb, p, out_f32 != 0, st);
+    }
+}

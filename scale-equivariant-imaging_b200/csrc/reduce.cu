@@ -115,7 +115,7 @@ struct SureParams {
     float* g2;
     const float* gscale;
     RedWorkspace* ws;
-    int B, C, H, W, margin_mse, margin_div, averaged_cst;
+    int B, C, H, W, margin_mse, margin_div, averaged_cst, vec;
     float tau, sigma2;
     long long total;
 };
@@ -127,16 +127,38 @@ __global__ void __launch_bounds__(kRedThreads) sure_loss_kernel(const __grid_con
     __shared__ double scratch[64];
     __shared__ bool s_last;
     float mse = 0.f, div = 0.f;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(idx % p.W);
-        const int i = (int)((idx / p.W) % p.H);
-        const float a1 = __ldcs(p.y1 + idx);
-        if (interior(i, j, p.H, p.W, p.margin_mse)) {
-            const float d = a1 - __ldcs(p.y + idx);
-            mse = fmaf(d, d, mse);
+    if (p.vec) {
+        // one float4 (4 consecutive columns of one row) per thread and iteration, 32-bit index math
+        const unsigned CW = (unsigned)p.W >> 2, n4 = (unsigned)(p.total >> 2);
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+            const unsigned row = q / CW;
+            const int j0 = (int)(q - row * CW) * 4, i = (int)(row % (unsigned)p.H);
+            const size_t idx = (size_t)q * 4;
+            const float4 a1 = ld_stream4(p.y1 + idx), a2 = ld_stream4(p.y2 + idx), yy = ld_stream4(p.y + idx),
+                         bb = ld_stream4(p.b + idx);
+            const float v1[4] = {a1.x, a1.y, a1.z, a1.w}, v2[4] = {a2.x, a2.y, a2.z, a2.w},
+                        vy[4] = {yy.x, yy.y, yy.z, yy.w}, vb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (interior(i, j0 + e, p.H, p.W, p.margin_mse)) {
+                    const float d = v1[e] - vy[e];
+                    mse = fmaf(d, d, mse);
+                }
+                if (interior(i, j0 + e, p.H, p.W, p.margin_div)) div = fmaf(vb[e], v2[e] - v1[e], div);
+            }
         }
-        if (interior(i, j, p.H, p.W, p.margin_div)) div = fmaf(__ldcs(p.b + idx), __ldcs(p.y2 + idx) - a1, div);
+    } else {
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+             idx += (long long)gridDim.x * blockDim.x) {
+            const int j = (int)(idx % p.W);
+            const int i = (int)((idx / p.W) % p.H);
+            const float a1 = __ldcs(p.y1 + idx);
+            if (interior(i, j, p.H, p.W, p.margin_mse)) {
+                const float d = a1 - __ldcs(p.y + idx);
+                mse = fmaf(d, d, mse);
+            }
+            if (interior(i, j, p.H, p.W, p.margin_div)) div = fmaf(__ldcs(p.b + idx), __ldcs(p.y2 + idx) - a1, div);
+        }
     }
     double v[2] = {(double)mse, (double)div};
     if (grid_finish<2>(v, p.ws, scratch, &s_last)) {
@@ -159,6 +181,27 @@ __global__ void __launch_bounds__(kRedThreads) sure_loss_backward_kernel(const _
     const float g = __ldg(p.gscale);
     const float k_mse = g * (float)(2.0 / n_mse);
     const float k_div = g * (float)(2.0 * (double)p.sigma2 / ((double)p.tau * n_div));
+    if (p.vec) {
+        const unsigned CW = (unsigned)p.W >> 2, n4 = (unsigned)(p.total >> 2);
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+            const unsigned row = q / CW;
+            const int j0 = (int)(q - row * CW) * 4, i = (int)(row % (unsigned)p.H);
+            const size_t idx = (size_t)q * 4;
+            const float4 a1 = ld_stream4(p.y1 + idx), yy = ld_stream4(p.y + idx), bb = ld_stream4(p.b + idx);
+            const float v1[4] = {a1.x, a1.y, a1.z, a1.w}, vy[4] = {yy.x, yy.y, yy.z, yy.w}, vb[4] = {bb.x, bb.y, bb.z, bb.w};
+            float o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = interior(i, j0 + e, p.H, p.W, p.margin_mse) ? k_mse * (v1[e] - vy[e]) : 0.f;
+                const float d = interior(i, j0 + e, p.H, p.W, p.margin_div) ? k_div * vb[e] : 0.f;
+                o1[e] = a - d;
+                o2[e] = d;
+            }
+            st_stream4(p.g1 + idx, make_float4(o1[0], o1[1], o1[2], o1[3]));
+            st_stream4(p.g2 + idx, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        }
+        return;
+    }
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % p.W);
@@ -168,6 +211,32 @@ __global__ void __launch_bounds__(kRedThreads) sure_loss_backward_kernel(const _
         if (interior(i, j, p.H, p.W, p.margin_div)) d = k_div * __ldcs(p.b + idx);
         __stcs(p.g1 + idx, a - d);
         __stcs(p.g2 + idx, d);
+    }
+}
+
+__global__ void __launch_bounds__(256) sure_perturb_vec_kernel(const float* __restrict__ y, const float* __restrict__ draw,
+                                                               int H, int W, int margin, float tau, long long total,
+                                                               float* out, float* b_out)
+{
+    const int Hi = H - 2 * margin, Wi = W - 2 * margin;
+    const unsigned CW = (unsigned)W >> 2, n4 = (unsigned)(total >> 2);
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+        const unsigned row = q / CW;
+        const int j0 = (int)(q - row * CW) * 4;
+        const unsigned plane = row / (unsigned)H;
+        const int i = (int)(row - plane * (unsigned)H);
+        const size_t idx = (size_t)q * 4;
+        const float4 yy = ld_stream4(y + idx);
+        float b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i >= margin && i < H - margin) {
+            const float* drow = draw + ((size_t)plane * Hi + (i - margin)) * Wi - margin;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j0 + e >= margin && j0 + e < W - margin) b[e] = __ldcs(drow + j0 + e);
+        }
+        st_stream4(out + idx, make_float4(__fadd_rn(yy.x, __fmul_rn(b[0], tau)), __fadd_rn(yy.y, __fmul_rn(b[1], tau)),
+                                          __fadd_rn(yy.z, __fmul_rn(b[2], tau)), __fadd_rn(yy.w, __fmul_rn(b[3], tau))));
+        if (b_out) st_stream4(b_out + idx, make_float4(b[0], b[1], b[2], b[3]));
     }
 }
 
@@ -185,6 +254,16 @@ __global__ void __launch_bounds__(256) sure_perturb_kernel(const float* __restri
         if (interior(i, j, H, W, margin)) b = __ldcs(draw + ((t / H) * Hi + (i - margin)) * Wi + (j - margin));
         out[idx] = __fadd_rn(y[idx], __fmul_rn(b, tau));
         if (b_out) b_out[idx] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) add_noise_vec_kernel(const float* __restrict__ y, const float* __restrict__ n,
+                                                            long long total4, float sigma, float* out)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
+        const float4 a = ld_stream4(y + 4 * q), b = ld_stream4(n + 4 * q);
+        st_stream4(out + 4 * q, make_float4(__fadd_rn(a.x, __fmul_rn(b.x, sigma)), __fadd_rn(a.y, __fmul_rn(b.y, sigma)),
+                                            __fadd_rn(a.z, __fmul_rn(b.z, sigma)), __fadd_rn(a.w, __fmul_rn(b.w, sigma))));
     }
 }
 
@@ -267,6 +346,7 @@ extern "C" int sei_sure_loss_f32(const float* y1, const float* y2, const float* 
     if (rc) return rc;
     p.y1 = y1; p.y2 = y2; p.y = y; p.b = b; p.out = out; p.averaged_cst = averaged_cst;
     p.ws = reinterpret_cast<RedWorkspace*>(workspace);
+    p.vec = (W % 4 == 0) && p.total < (1ll << 32) && aligned16(y1) && aligned16(y2) && aligned16(y) && aligned16(b);
     sure_loss_kernel<<<red_grid(p.total, dp.sm_count), kRedThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return finish_launch("sure_loss_kernel");
 }
@@ -284,7 +364,8 @@ extern "C" int sei_sure_loss_backward_f32(const float* y1, const float* y, const
     rc = get_device_props(&dp);
     if (rc) return rc;
     p.y1 = y1; p.y = y; p.b = b; p.gscale = gscale; p.g1 = g1; p.g2 = g2;
-    sure_loss_backward_kernel<<<ew_grid(p.total, dp.sm_count), kRedThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    p.vec = (W % 4 == 0) && p.total < (1ll << 32) && aligned16(y1) && aligned16(y) && aligned16(b) && aligned16(g1) && aligned16(g2);
+    sure_loss_backward_kernel<<<ew_grid(p.vec ? p.total / 4 : p.total, dp.sm_count), kRedThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return finish_launch("sure_loss_backward_kernel");
 }
 
@@ -297,6 +378,11 @@ extern "C" int sei_sure_perturb_f32(const float* y, const float* draw, int B, in
     int rc = get_device_props(&dp);
     if (rc) return rc;
     const long long total = (long long)B * C * H * W;
+    if ((W % 4 == 0) && total < (1ll << 32) && aligned16(y) && aligned16(out) && (!b_out || aligned16(b_out))) {
+        sure_perturb_vec_kernel<<<ew_grid(total / 4, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            y, draw, H, W, margin, tau, total, out, b_out);
+        return finish_launch("sure_perturb_vec_kernel");
+    }
     sure_perturb_kernel<<<ew_grid(total, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         y, draw, H, W, margin, tau, total, out, b_out);
     return finish_launch("sure_perturb_kernel");
@@ -309,6 +395,10 @@ extern "C" int sei_add_noise_f32(const float* y, const float* noise, long long n
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
+    if (n % 4 == 0 && aligned16(y) && aligned16(noise) && aligned16(out)) {
+        add_noise_vec_kernel<<<ew_grid(n / 4, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, noise, n / 4, sigma, out);
+        return finish_launch("add_noise_vec_kernel");
+    }
     add_noise_kernel<<<ew_grid(n, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, noise, n, sigma, out);
     return finish_launch("add_noise_kernel");
 }

@@ -5,87 +5,131 @@
 namespace sei {
 
 constexpr int kMaxK = 31;
-constexpr int kRH = 8;   // output rows per vertical-pass work item
 
 // ---------------------------------------------------------------- separable circular blur passes
-// vertical: sMid[o][c] = sum_t cv[t] * sIn[o + t][c],  o in [0, th), rows of sIn in [0, rin = th + K - 1)
+// Template parameter WT: compile-time image width (0 = use the run-time width).  With WT > 0 every
+// shared-memory address below is "base + immediate" and the work-item decode is shifts and masks; the
+// ncu profile of the run-time-width version showed 58 % of its issued instructions were such index math.
+// PAD: the intermediate band keeps 4*LCH halo columns on both sides of every row (circular copies, written
+// by the vertical pass), so the horizontal pass needs no wrap-around logic.
+template <int K> struct BlurGeom {
+    static constexpr int P = K / 2;
+    static constexpr int LCH = (P + 3) / 4;          // float4 chunks of halo on each side
+    static constexpr int NCH = 2 * LCH + 1;
+    static constexpr int LEFT = 4 * LCH;
+};
+
+template <int K, bool PAD> __host__ __device__ constexpr int blur_mid_pitch(int W)
+{
+    return PAD ? W + 2 * BlurGeom<K>::LEFT : W;
+}
+
+// vertical: sMid[o][c] = sum_t cv[t] * sIn[o + t][c],  o in [0, th), rows of sIn in [0, th + K - 1)
 // Register-blocked: each work item owns kRH output rows x 4 columns and streams kRH + K - 1 input
 // rows through a scatter-form accumulation, so every shared load feeds up to kRH * 4 FMAs and the
 // taps are compile-time-indexed constant-bank operands.
-template <int K, int NT>
-__device__ __forceinline__ void blur_vpass(const float* __restrict__ sIn, float* __restrict__ sMid, int W, int th,
-                                           const float* __restrict__ cv)
+template <int K, int kRH, bool PAD, bool FULL>
+__device__ __forceinline__ void blur_vpass_item(const float* __restrict__ base, float* __restrict__ dst, int W, int pitch,
+                                                int nvalid, int nout, int c4, int CW, const float* __restrict__ cv)
 {
-    const int CW = W >> 2, rin = th + K - 1;
-    const int ngroups = (th + kRH - 1) / kRH;
-    for (int item = threadIdx.x; item < ngroups * CW; item += NT) {
-        const int g = item / CW, c4 = item - g * CW;
-        const int o0 = g * kRH;
-        const float* base = sIn + (size_t)o0 * W + c4 * 4;
-        float4 acc[kRH];
+    using G = BlurGeom<K>;
+    float4 acc[kRH];
 #pragma unroll
-        for (int o = 0; o < kRH; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o0 + kRH <= th) {
+    for (int o = 0; o < kRH; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < kRH + K - 1; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * W);
+    for (int i = 0; i < kRH + K - 1; ++i) {
+        if (FULL || i < nvalid) {
+            const float4 v = *reinterpret_cast<const float4*>(base + i * W);
 #pragma unroll
-                for (int o = 0; o < kRH; ++o) {
-                    const int t = i - o;
-                    if (t >= 0 && t < K) {
-                        const float c = cv[t];
-                        acc[o].x = fmaf(c, v.x, acc[o].x); acc[o].y = fmaf(c, v.y, acc[o].y);
-                        acc[o].z = fmaf(c, v.z, acc[o].z); acc[o].w = fmaf(c, v.w, acc[o].w);
-                    }
+            for (int o = 0; o < kRH; ++o) {
+                const int t = i - o;
+                if (t >= 0 && t < K) {
+                    const float c = cv[t];
+                    acc[o].x = fmaf(c, v.x, acc[o].x); acc[o].y = fmaf(c, v.y, acc[o].y);
+                    acc[o].z = fmaf(c, v.z, acc[o].z); acc[o].w = fmaf(c, v.w, acc[o].w);
                 }
             }
+        }
+    }
 #pragma unroll
-            for (int o = 0; o < kRH; ++o) *reinterpret_cast<float4*>(sMid + (size_t)(o0 + o) * W + c4 * 4) = acc[o];
-        } else {
-            const int nvalid = rin - o0;
-#pragma unroll
-            for (int i = 0; i < kRH + K - 1; ++i) {
-                if (i < nvalid) {
-                    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * W);
-#pragma unroll
-                    for (int o = 0; o < kRH; ++o) {
-                        const int t = i - o;
-                        if (t >= 0 && t < K) {
-                            const float c = cv[t];
-                            acc[o].x = fmaf(c, v.x, acc[o].x); acc[o].y = fmaf(c, v.y, acc[o].y);
-                            acc[o].z = fmaf(c, v.z, acc[o].z); acc[o].w = fmaf(c, v.w, acc[o].w);
-                        }
-                    }
-                }
-            }
+    for (int o = 0; o < kRH; ++o)
+        if (FULL || o < nout) *reinterpret_cast<float4*>(dst + o * pitch) = acc[o];
+    if (PAD) {
+        // circular halo copies: the first LCH chunks also go right of the row, the last LCH chunks left of it
+        if (c4 < G::LCH) {
 #pragma unroll
             for (int o = 0; o < kRH; ++o)
-                if (o0 + o < th) *reinterpret_cast<float4*>(sMid + (size_t)(o0 + o) * W + c4 * 4) = acc[o];
+                if (FULL || o < nout) *reinterpret_cast<float4*>(dst + o * pitch + W) = acc[o];
+        }
+        if (c4 >= CW - G::LCH) {
+#pragma unroll
+            for (int o = 0; o < kRH; ++o)
+                if (FULL || o < nout) *reinterpret_cast<float4*>(dst + o * pitch - W) = acc[o];
         }
     }
 }
 
+template <int K, int NT, int kRH, int WT, bool PAD>
+__device__ __forceinline__ void blur_vpass_rh(const float* __restrict__ sIn, float* __restrict__ sMid, int Wrt, int th,
+                                              const float* __restrict__ cv)
+{
+    using G = BlurGeom<K>;
+    const int W = WT ? WT : Wrt;
+    const int CW = W >> 2, rin = th + K - 1;
+    const int pitch = blur_mid_pitch<K, PAD>(W);
+    const int HL = PAD ? G::LEFT : 0;
+    const int ngroups = (th + kRH - 1) / kRH;
+    for (int item = threadIdx.x; item < ngroups * CW; item += NT) {
+        const int g = item / CW, c4 = item - g * CW;
+        const int o0 = g * kRH;
+        const float* base = sIn + o0 * W + c4 * 4;
+        float* dst = sMid + o0 * pitch + HL + c4 * 4;
+        if (o0 + kRH <= th)
+            blur_vpass_item<K, kRH, PAD, true>(base, dst, W, pitch, 0, 0, c4, CW, cv);
+        else
+            blur_vpass_item<K, kRH, PAD, false>(base, dst, W, pitch, rin - o0, th - o0, c4, CW, cv);
+    }
+}
+
+// kRH = 8 output rows per work item (2.5 shared loads per output vector at K = 13) when that still gives
+// every thread an item, otherwise 4 rows per item (more items, 4 loads per output vector)
+template <int K, int NT, int WT = 0, bool PAD = false>
+__device__ __forceinline__ void blur_vpass(const float* __restrict__ sIn, float* __restrict__ sMid, int Wrt, int th,
+                                           const float* __restrict__ cv)
+{
+    const int W = WT ? WT : Wrt;
+    if (((th + 7) >> 3) * (W >> 2) >= NT)
+        blur_vpass_rh<K, NT, 8, WT, PAD>(sIn, sMid, Wrt, th, cv);
+    else
+        blur_vpass_rh<K, NT, 4, WT, PAD>(sIn, sMid, Wrt, th, cv);
+}
+
 // horizontal (circular in x): y[r][n] = sum_t ch[t] * sMid[r][(n + t - P) mod W] (+ sigma * noise)
 // yrow0 / nrow0 point at the first output row of the band in global memory (row pitch W).
-template <int K, int NT, bool NOISE>
-__device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int W, int th, const float* __restrict__ ch,
+template <int K, int NT, bool NOISE, int WT = 0, bool PAD = false>
+__device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int Wrt, int th, const float* __restrict__ ch,
                                            float* __restrict__ yrow0, const float* __restrict__ nrow0, float sigma)
 {
-    constexpr int P = K / 2;
-    constexpr int LCH = (P + 3) / 4;         // float4 chunks to the left of the output chunk
-    constexpr int NCH = 2 * LCH + 1;
-    constexpr int LEFT = 4 * LCH;
+    using G = BlurGeom<K>;
+    constexpr int P = G::P, LCH = G::LCH, NCH = G::NCH, LEFT = G::LEFT;
+    const int W = WT ? WT : Wrt;
     const int CW = W >> 2;
+    const int pitch = blur_mid_pitch<K, PAD>(W);
     for (int item = threadIdx.x; item < th * CW; item += NT) {
         const int r = item / CW, c4 = item - r * CW;
-        const float* row = sMid + (size_t)r * W;
+        const float* row = sMid + r * pitch;
         float v[4 * NCH];
 #pragma unroll
         for (int q = 0; q < NCH; ++q) {
-            int cc = c4 - LCH + q;
-            if (cc < 0) cc += CW;
-            if (cc >= CW) cc -= CW;
-            const float4 t = *reinterpret_cast<const float4*>(row + cc * 4);
+            float4 t;
+            if (PAD) {
+                t = *reinterpret_cast<const float4*>(row + (c4 + q) * 4);      // padded column 4*(c4 - LCH + q) + LEFT
+            } else {
+                int cc = c4 - LCH + q;
+                if (cc < 0) cc += CW;
+                if (cc >= CW) cc -= CW;
+                t = *reinterpret_cast<const float4*>(row + cc * 4);
+            }
             v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
         }
         float out[4] = {0.f, 0.f, 0.f, 0.f};
@@ -95,7 +139,7 @@ __device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int W
 #pragma unroll
             for (int o = 0; o < 4; ++o) out[o] = fmaf(c, v[LEFT + o + t - P], out[o]);
         }
-        const size_t g = (size_t)r * W + c4 * 4;
+        const int g = r * W + c4 * 4;
         if (NOISE) {
             const float4 n = ld_stream4(nrow0 + g);
             out[0] = fmaf(sigma, n.x, out[0]); out[1] = fmaf(sigma, n.y, out[1]);

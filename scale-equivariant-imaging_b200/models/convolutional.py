@@ -1,0 +1,289 @@
+"""The restoration CNN (reference: src/models/convolutional.py) with its dense contractions on the
+tcgen05 tensor cores.
+
+Same module tree and parameter names as the reference's ConvolutionalModel, so its state dicts load
+unchanged.  What differs is where the arithmetic runs:
+  * every 1x1 convolution (ConvBlock.conv2 / conv3, Downsample.conv, Upsample.seq[2]) and, through an
+    unfold, the two 3x3 in/out convolutions are ONE kernel, sei_gemm_bf16_tn (bf16 operands, fp32
+    accumulation in TMEM), on channels-last activations: pixels x C_in  @  (C_out x C_in)^T.  dgrad and
+    wgrad call the same kernel with the operand roles permuted;
+  * activations travel through the network in bf16, channels-last; parameters stay fp32 masters and are
+    cast once per optimizer step;
+  * everything else (depthwise 7x7, channel LayerNorm, GELU, the FFT "ideal" resamplers, including the
+    reference's quirks: fftshift applied to the half-spectrum axis, ifftshift results discarded) stays
+    PyTorch library code.
+"""
+from math import ceil
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Conv2d, GELU, LayerNorm as BaseLayerNorm, Module, ModuleList, Sequential
+
+from sei_b200 import ops
+
+CL = torch.channels_last
+# activation / GEMM operand dtype.  bf16 is the only dtype the tcgen05 kernel takes; the unit tests set this to
+# float32 together with a patched _gemm_tn to check the network's structure against the reference at fp32 accuracy.
+COMPUTE_DTYPE = torch.bfloat16
+
+
+def _gemm_tn(a, b, bias, out_dtype):
+    """D = a @ b^T (+ bias) on the tcgen05 tensor cores (include/sei_b200.h: sei_gemm_bf16_tn)"""
+    return ops.gemm_bf16_tn(a, b, bias, out_dtype=out_dtype)
+
+
+class _GemmTN(torch.autograd.Function):
+    """out[T, N] = x[T, K] @ w[N, K]^T + bias[N]; all three passes on sei_gemm_bf16_tn."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_bf16):
+        ctx.save_for_backward(x, w_bf16)
+        ctx.has_bias = bias is not None
+        return _gemm_tn(x, w_bf16, bias, COMPUTE_DTYPE)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w_bf16 = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _gemm_tn(_pad_k(gy), _pad_k(w_bf16.t()), None, COMPUTE_DTYPE)                                  # gy[T,N] @ w[N,K]
+        if ctx.needs_input_grad[1]:
+            gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)                          # gy^T[N,T] @ x[T,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.float().sum(0)
+        return gx, gw, gb, None
+
+
+def _pad_k(a):
+    """contiguous copy of a 2-D bf16 matrix with its last (contraction) dimension padded to a multiple of 8"""
+    a = a.contiguous()
+    k = a.shape[1]
+    return a if k % 8 == 0 else F.pad(a, (0, 8 - k % 8))
+
+
+class _GemmConv2d(Conv2d):
+    """nn.Conv2d whose forward/backward contractions run on the tcgen05 GEMM.  Supports what the reference's
+    network uses: 1x1 stride 1, and 3x3 stride 1 with 'same' zero padding; groups = 1."""
+
+    def _weight_matrix(self):
+        w = self.weight
+        if self.kernel_size == (1, 1):
+            w2 = w.reshape(w.shape[0], w.shape[1])
+        else:
+            w2 = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)        # (C_out, ky, kx, C_in): matches _unfold3x3
+        key = (w._version, w.data_ptr(), COMPUTE_DTYPE)
+        if getattr(self, "_w_key", None) != key:
+            with torch.no_grad():
+                self._w_cache = _pad_k(w2.detach().to(COMPUTE_DTYPE))
+            self._w_key = key
+        return w2, self._w_cache
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)      # (B, H, W, C) view
+        if self.kernel_size == (3, 3):
+            xl = _unfold3x3(xl)
+        x2 = xl.reshape(B * H * W, xl.shape[-1])
+        w2, w_bf16 = self._weight_matrix()
+        if x2.shape[1] != w_bf16.shape[1]:
+            x2 = F.pad(x2, (0, w_bf16.shape[1] - x2.shape[1]))
+        w2p = w2 if w2.shape[1] == w_bf16.shape[1] else F.pad(w2, (0, w_bf16.shape[1] - w2.shape[1]))
+        out = _GemmTN.apply(x2, w2p, self.bias, w_bf16)
+        return out.view(B, H, W, -1).permute(0, 3, 1, 2)                        # logical NCHW, channels-last memory
+
+
+def _unfold3x3(xl):
+    """(B, H, W, C) -> (B, H, W, 9C): the 3x3 neighbourhood with zero padding, ordered (ky, kx, c)."""
+    B, H, W, C = xl.shape
+    xp = F.pad(xl, (0, 0, 1, 1, 1, 1))
+    return torch.cat([xp[:, ky:ky + H, kx:kx + W, :] for ky in range(3) for kx in range(3)], dim=-1)
+
+
+def _conv(in_channels, out_channels, kernel_size, **kw):
+    return _GemmConv2d(in_channels, out_channels, kernel_size=kernel_size, **kw)
+
+
+class LayerNorm(Module):
+    """layer norm over the channels (reference :21-30: swapaxes(-3, -1) / nn.LayerNorm / swap back)"""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.ln = BaseLayerNorm(*args, **kwargs)
+
+    def forward(self, x):
+        xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)                   # channels last: a view
+        out = F.layer_norm(xl, self.ln.normalized_shape, self.ln.weight.to(xl.dtype), self.ln.bias.to(xl.dtype),
+                           self.ln.eps)
+        return out.permute(0, 3, 1, 2)
+
+
+class ConvBlock(Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.conv1 = Conv2d(in_channels=dim, out_channels=dim, kernel_size=7, padding=3, groups=dim)
+        self.ln = LayerNorm(dim, eps=1e-6)
+        self.conv2 = _conv(dim, 4 * dim, 1)
+        self.gelu = GELU()
+        self.conv3 = _conv(4 * dim, dim, 1)
+
+    def forward(self, x):
+        x1 = F.conv2d(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype), padding=3, groups=x.shape[1])
+        x1 = self.ln(x1)
+        x1 = self.conv2(x1)
+        x1 = self.gelu(x1)
+        x1 = self.conv3(x1)
+        return x + x1
+
+
+class IdealUpsample(Module):
+    """zero-padding of the (fftshift-ed) half spectrum, exactly as the reference does it (:54-92)"""
+
+    def __init__(self, rate=2):
+        super().__init__()
+        self.rate = rate
+
+    def forward(self, x):
+        dtype = x.dtype
+        r = self.rate
+        s = (x.shape[-2], x.shape[-1])
+        X = torch.fft.fftshift(torch.fft.rfft2(x.float(), dim=(-2, -1)), dim=(-2, -1))
+        hs, ws = X.shape[-2], X.shape[-1]
+        X2 = torch.zeros((X.shape[0], X.shape[1], hs * r, ws * r), device=X.device, dtype=X.dtype)
+        mv, mh = (hs * (r - 1)) // 2, (ws * (r - 1)) // 2
+        mt, mb = (mv + 1, mv) if hs % 2 == 1 else (mv, mv)
+        ml, mr = (mh + 1, mh) if ws % 2 == 1 else (mh, mh)
+        X2[:, :, mt:-mb, ml:-mr] = X
+        out = torch.fft.irfft2(X2, dim=(-2, -1), s=(s[0] * r, s[1] * r))
+        return out.to(dtype)
+
+
+class Upsample(Module):
+    def __init__(self, in_channels, out_channels=None, rate=2):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels or in_channels // (rate ** 2)
+        self.rate = rate
+        self.seq = Sequential()
+        self.seq.append(IdealUpsample(rate=self.rate))
+        self.seq.append(LayerNorm(self.in_channels, eps=1e-6))
+        self.seq.append(_conv(self.in_channels, self.out_channels, 1, stride=1))
+
+    def forward(self, x):
+        return self.seq(x)
+
+
+class IdealDownsample(Module):
+    """mask of the (fftshift-ed) half spectrum then stride-`rate` subsampling (:113-133)"""
+
+    def __init__(self, rate=2):
+        super().__init__()
+        self.rate = rate
+
+    def forward(self, x):
+        dtype = x.dtype
+        s = (x.shape[-2], x.shape[-1])
+        X = torch.fft.fftshift(torch.fft.rfft2(x.float(), dim=(-2, -1)), dim=(-2, -1))
+        hcsh = ceil(X.shape[-2] / (2 * self.rate))
+        hcsw = ceil(X.shape[-1] / (2 * self.rate))
+        otf = torch.zeros_like(X)
+        otf[:, :, hcsh:-hcsh, hcsw:-hcsw] = 1
+        out = torch.fft.irfft2(otf * X, dim=(-2, -1), s=s)
+        return out[:, :, :: self.rate, :: self.rate].to(dtype)
+
+
+class Downsample(Module):
+    def __init__(self, in_channels, out_channels=None, rate=2):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels or in_channels * (rate ** 2)
+        self.rate = rate
+        self.ln = LayerNorm(self.in_channels, eps=1e-6)
+        self.conv = _conv(self.in_channels, self.out_channels, 1, stride=1)
+        self.ideal_downsample = IdealDownsample(rate=self.rate)
+
+    def forward(self, x):
+        return self.ideal_downsample(self.conv(self.ln(x)))
+
+
+class UNet(Module):
+    def __init__(self, in_channels, hidden_channels, inout_convs, scales, num_conv_blocks, rate, residual,
+                 inner_residual):
+        super().__init__()
+        self.scales = scales
+        self.residual = residual
+        self.inner_residual = inner_residual
+        self.conv_sequences = ModuleList()
+        self.downsampling_layers = ModuleList()
+        self.upsampling_layers = ModuleList()
+
+        if inout_convs:
+            self.in_conv = _conv(in_channels, hidden_channels, 3, padding="same")
+            self.out_conv = _conv(hidden_channels, in_channels, 3, padding="same")
+            width = hidden_channels
+        else:
+            width = in_channels
+
+        def blocks(dim):
+            return Sequential(*[ConvBlock(dim=dim) for _ in range(num_conv_blocks)])
+
+        for _ in range(scales - 1):
+            self.conv_sequences.append(blocks(width))
+            self.downsampling_layers.append(Downsample(in_channels=width))
+            width *= rate ** 2
+        self.conv_sequences.append(blocks(width))
+        for _ in range(scales - 1):
+            self.upsampling_layers.append(Upsample(in_channels=width, rate=rate))
+            width //= rate ** 2
+            self.conv_sequences.append(blocks(width))
+
+    def forward(self, x):
+        x0 = x
+        convs, downs, ups = iter(self.conv_sequences), iter(self.downsampling_layers), iter(self.upsampling_layers)
+        skips = []
+        if hasattr(self, "in_conv"):
+            x = self.in_conv(x)
+        for _ in range(self.scales - 1):
+            xb = x
+            x = next(convs)(x)
+            if self.inner_residual:
+                x = x + xb
+            skips.append(x)
+            x = next(downs)(x)
+        x = next(convs)(x)
+        for _ in range(self.scales - 1):
+            x = next(ups)(x)
+            x = x + skips.pop()
+            x = next(convs)(x)
+        if hasattr(self, "out_conv"):
+            x = self.out_conv(x)
+        if self.residual:
+            x = x + x0
+        return x
+
+
+class ConvolutionalModel(Module):
+    def __init__(self, in_channels, upsampling_rate, residual, inner_residual, num_conv_blocks, hidden_channels,
+                 inout_convs, scales):
+        super().__init__()
+        self.seq = Sequential()
+        self.scales = scales
+        if upsampling_rate != 1:
+            self.seq.append(Upsample(in_channels=in_channels, out_channels=in_channels, rate=upsampling_rate))
+        self.seq.append(UNet(in_channels=in_channels, hidden_channels=hidden_channels, inout_convs=inout_convs,
+                             scales=scales, num_conv_blocks=num_conv_blocks, residual=residual,
+                             inner_residual=inner_residual, rate=2))
+
+    def forward(self, y):
+        div = 2 ** (self.scales - 1)
+        pad_h = (div - y.shape[-2] % div) % div
+        pad_w = (div - y.shape[-1] % div) % div
+        if pad_h != 0 or pad_w != 0:
+            y = F.pad(y, (0, pad_w, 0, pad_h), mode="reflect")
+        x_hat = self.seq(y.to(dtype=COMPUTE_DTYPE, memory_format=CL))
+        x_hat = x_hat.to(dtype=y.dtype).contiguous()
+        if pad_h != 0:
+            x_hat = x_hat[:, :, :-pad_h, :]
+        if pad_w != 0:
+            x_hat = x_hat[:, :, :, :-pad_w]
+        return x_hat

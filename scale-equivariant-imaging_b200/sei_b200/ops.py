@@ -196,6 +196,27 @@ def sure_perturb(y, draw, margin, tau):
     return out, b
 
 
+def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
+    """D[M,N] = a[M,K] @ b[N,K]^T (+ bias[N]) on the tcgen05 tensor cores; a, b bf16 row-major (last dim
+    contiguous, row pitch a multiple of 8 elements); fp32 accumulation; D bf16 or fp32."""
+    for t, name in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise SeiError(f"gemm_bf16_tn: {name} must be a 2-D CUDA bf16 tensor with a contiguous last dimension")
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2:
+        raise SeiError(f"gemm_bf16_tn: inner dimensions differ ({K} vs {K2})")
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise SeiError("gemm_bf16_tn: out_dtype must be bfloat16 or float32")
+    if bias is not None:
+        bias = _t(bias, "bias")
+    d = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn(_ptr(a), _ptr(b), _ptr(d), _ptr(bias), M, N, K, a.stride(0), b.stride(0), N,
+                                           int(out_dtype == torch.float32), int(tile_n), _stream(a)))
+    return d
+
+
 # ------------------------------------------------------------------------------ autograd
 class _BlurCircular(torch.autograd.Function):
     """y = A x (adjoint=False) or A^T x; backward applies the other one (hand-written transpose)."""

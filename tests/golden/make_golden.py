@@ -351,7 +351,93 @@ def gen_degrade():
     save("degrade", **out)
 
 
+def gen_model():
+    """The reference's ConvolutionalModel (src/models/convolutional.py) at a small configuration: state dict,
+    forward output and parameter gradients in fp32 on the CPU.  Loaded by file path because
+    src/models/__init__.py imports deepinv.models / bm3d, which are not installed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_convolutional", os.path.join(REF_SRC, "models", "convolutional.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, kw, shape in [
+        ("deblur", dict(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+                        hidden_channels=8, inout_convs=True, scales=3), (2, 3, 32, 32)),
+        ("sr2", dict(in_channels=3, upsampling_rate=2, residual=True, inner_residual=True, num_conv_blocks=2,
+                     hidden_channels=8, inout_convs=True, scales=2), (2, 3, 16, 16)),
+        ("pad", dict(in_channels=3, upsampling_rate=1, residual=False, inner_residual=False, num_conv_blocks=1,
+                     hidden_channels=8, inout_convs=False, scales=3), (1, 3, 30, 27)),
+    ]:
+        torch.manual_seed(7)
+        model = mod.ConvolutionalModel(**kw)
+        # non-trivial biases / norm parameters so that every term is exercised
+        with torch.no_grad():
+            for p_ in model.parameters():
+                if p_.dim() == 1:
+                    p_.add_(0.1 * torch.randn_like(p_))
+        y = torch.rand(shape)
+        out = model(y)
+        gout = torch.randn_like(out)
+        (out * gout).sum().backward()
+        arrays = {"y": np_(y), "out": np_(out), "gout": np_(gout)}
+        for k_, v_ in model.state_dict().items():
+            arrays[f"sd::{k_}"] = np_(v_)
+        for k_, p_ in model.named_parameters():
+            arrays[f"grad::{k_}"] = np_(p_.grad)
+        arrays["kwargs"] = np.array(repr(kw))
+        save(f"model_{name}", **arrays)
+    # default flags (hidden 32, 5 scales): names and shapes only (645 M parameters)
+    with torch.device("meta"):
+        big = mod.ConvolutionalModel(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True,
+                                     num_conv_blocks=1, hidden_channels=32, inout_convs=True, scales=5)
+    names = sorted(big.state_dict().keys())
+    shapes = [list(big.state_dict()[n].shape) for n in names]
+    save("model_default_layout", names=np.array(names), shapes=np.array([repr(s_) for s_ in shapes]),
+         n_params=np.array(sum(p_.numel() for p_ in big.parameters())))
+
+
+def gen_step():
+    """BASELINE configs[0]: deblurring Gaussian_R2, method=proposed, one training step's loss + gradients on
+    synthetic 48x48 RGB crops, batch 8, on the CPU in fp32, with the reference's own ConvolutionalModel (small
+    flags: hidden 8, 3 scales) and the reference's own losses/physics."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_convolutional", os.path.join(REF_SRC, "models", "convolutional.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    kw = dict(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+              hidden_channels=8, inout_convs=True, scales=3)
+    torch.manual_seed(11)
+    net = mod.ConvolutionalModel(**kw)
+
+    class Wrapped(torch.nn.Module):     # Model.forward(x, *args) of src/models/__init__.py:148-149
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, *args):
+            return self.m(x)
+
+    model = Wrapped(net)
+    args = base_args()
+    physics = get_physics(args, device="cpu")
+    loss_fn = ref_losses.get_loss(args=args, physics=physics)
+    gen = torch.Generator().manual_seed(2024)
+    x = torch.rand((8, 3, 48, 48), generator=gen)
+    with torch.no_grad():
+        y = physics.A(x) + (5 / 255) * torch.randn((8, 3, 48, 48), generator=gen)
+    with DrawRecorder() as rec:
+        torch.manual_seed(3)
+        loss = loss_fn(x=x, y=y, model=model)
+    loss.backward()
+    out = {"x": np_(x), "y": np_(y), "loss": np_(loss), "kwargs": np.array(repr(kw))}
+    out.update(rec.as_dict())
+    for k_, v_ in net.state_dict().items():
+        out[f"sd::{k_}"] = np_(v_)
+    for k_, p_ in net.named_parameters():
+        out[f"grad::{k_}"] = np_(p_.grad)
+    save("step_cfg1_cnn", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kernels", "blur", "downsampling", "transform", "losses", "crop", "degrade"]
+    which = sys.argv[1:] or ["step", "kernels", "blur", "downsampling", "transform", "losses", "crop", "degrade", "model"]
     for w in which:
         globals()[f"gen_{w}"]()
