@@ -135,17 +135,13 @@ def run_b200(args):
     from sei_b200 import ops
     from toy_model import ToyModel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from sei_b200 import parallel
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sei_b200 hot path has no CPU fallback "
                          "(use --impl reference for the CPU restatement)")
+    rank, world, local_rank = parallel.init_distributed(backend="nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     global BATCH
@@ -172,15 +168,7 @@ def run_b200(args):
     host_y = [y.cpu().pin_memory() for y in ys[:2]]
     x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
     loss_static = torch.zeros((), device=dev)
-    buckets, cur, cur_n = [], [], 0            # gradient buckets of <= 64 Mi elements for the NCCL all-reduce
-    for p_ in params:
-        cur.append(p_)
-        cur_n += p_.numel()
-        if cur_n >= 64 * 2 ** 20:
-            buckets.append(cur)
-            cur, cur_n = [], 0
-    if cur:
-        buckets.append(cur)
+    allreduce_grads = parallel.GradAllReducer(params)      # one bucketed NCCL all-reduce (average) per step
 
     def fwd_bwd():
         opt.zero_grad(set_to_none=False)
@@ -188,25 +176,18 @@ def run_b200(args):
         loss.backward()
         loss_static.copy_(loss.detach())
 
-    def allreduce_grads():
-        """data parallel: average the parameter gradients over the ranks (NCCL over NVLink), bucketed"""
-        if world > 1:
-            for bucket in buckets:
-                grads = [p_.grad for p_ in bucket]
-                flat = torch._utils._flatten_dense_tensors(grads)
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-                for g_, f_ in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                    g_.copy_(f_)
-
     # capture forward+backward and the optimizer step as CUDA graphs (the step is ~40 small launches)
     use_graph = not args.no_graph
     g_fb = g_opt = None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
+    launches_per_step = 0
     with torch.cuda.stream(side):
         x_static.copy_(xs[0]); y_static.copy_(ys[0])
         for _ in range(3):
+            n_before = sei_b200.launch_count()
             fwd_bwd(); allreduce_grads(); opt.step()
+            launches_per_step = sei_b200.launch_count() - n_before
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     import gc
@@ -228,9 +209,6 @@ def run_b200(args):
             gc.collect()
             torch.cuda.empty_cache()
 
-    n_before = sei_b200.launch_count()
-    fwd_bwd()
-    launches_per_step = sei_b200.launch_count() - n_before
     torch.cuda.synchronize()
 
     def step_resident(i):
