@@ -402,8 +402,9 @@ def reference_step_factory(args, batch):
 
 def run_reference_sample(args, seconds_budget=25.0, batch=None, steps=None, warmup=1):
     """Time the CPU restatement of the step on a bounded sample, using every host core."""
+    from oracle import oracle as orc
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    orc.set_threads(cores)               # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
     torch.set_num_threads(cores)
     batch = batch or (1 if args.network == "cnn" else 8)
     step = reference_step_factory(args, batch)

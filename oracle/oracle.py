@@ -51,6 +51,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """number of OpenMP threads the oracle's loops use (overrides OMP_NUM_THREADS); returns the effective count"""
+    return int(lib().orc_set_threads(int(n)))
+
+
 def _sfx(a):
     if a.dtype == np.float32:
         return "f32", C.c_float

@@ -49,3 +49,11 @@ int orc_named_kernel(const char* name, double* out)
 }
 
 int orc_abi_version(void) { return 1; }
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU-baseline leg of bench.py asks for every host core explicitly */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int orc_set_threads(int n) { (void)n; return 1; }
+#endif
