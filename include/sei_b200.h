@@ -106,11 +106,15 @@ int sei_scale_params_f32(const float* u_rate, const float* u_center, int B,
  * in one kernel, so x2 is written once and never re-read from HBM.
  * Deblurring: rate_sr = 1 and kernel_host != NULL (circular blur).
  * SR: rate_sr in {2,3,4} and kernel_host == NULL (antialiased bicubic decimation).
- * x_net, x2: B x C x S x S;  y_out, noise: B x C x S/rate_sr x S/rate_sr. */
+ * x_net, x2: B x C x S x S;  y_out, noise: B x C x S/rate_sr x S/rate_sr.
+ * workspace: optional device scratch of sei_ei_workspace_bytes(B, S) bytes (16-byte aligned); with it the
+ * resampling taps of every row and column are computed once per image by a small pre-kernel instead of once
+ * per band inside the fused kernel.  NULL is allowed. */
+long long sei_ei_workspace_bytes(int B, int S);
 int sei_ei_remeasure_f32(const float* x_net, float* x2, float* y_out, int B, int C, int S,
                          const float* rate, const float* center,
                          const double* kernel_host, int kh, int kw, int rate_sr,
-                         const float* noise, float sigma, void* stream);
+                         const float* noise, float sigma, void* workspace, void* stream);
 
 /* ---- loss reductions -----------------------------------------------------------------
  * All reductions are deterministic (fixed-order two-stage tree, double accumulation of

@@ -16,6 +16,7 @@
 // horizontal 4-tap polyphase passes.  Direct kernels cover every other shape.
 #include "sei_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sei {
 
@@ -42,15 +43,19 @@ struct BorderTab {      // weights of the 4 border outputs of one axis: indices 
 
 __device__ __forceinline__ int border_slot(int i, int n) { return i < 2 ? i : (i >= n - 2 ? i - (n - 4) : -1); }
 
-template <int R>
-__global__ void __launch_bounds__(kDownThreads, 2) down_band_kernel(const __grid_constant__ DownParams p)
+// WT: compile-time INPUT width (0 = run time).  Interior outputs (all but the first / last two of an axis) use the
+// fixed polyphase taps from the constant bank in branch-free loops; the few border outputs are handled by separate
+// small loops with per-CTA weight tables, so no warp ever executes both paths (the first version did, in every warp).
+template <int R, int WT>
+__global__ void __launch_bounds__(kDownThreads) down_band_kernel(const __grid_constant__ DownParams p)
 {
     constexpr int T = 4 * R, OFF = aa_off(R);
+    constexpr int NT = kDownThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
     __shared__ BorderTab colTab, rowTab;
 
-    const int H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo, CW = Wo >> 2;
+    const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R, CW = Wo >> 2;
     const int band = blockIdx.x % p.nbands;
     const long long plane = blockIdx.x / p.nbands;
     const int i0 = band * p.TH;
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(kDownThreads, 2) down_band_kernel(const __grid
     const int nchunks = (nin + CH - 1) / CH;
 
     float* sTmp = reinterpret_cast<float*>(smem_raw);                  // [R*TH + 3R][Wo]
-    float* sStage = sTmp + (size_t)(R * p.TH + 3 * R) * Wo;             // [2][CH][W]
+    float* sStage = sTmp + (R * p.TH + 3 * R) * Wo;                     // [2][CH][W]
     const unsigned char* xplane = reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * H * W);
     const uint32_t row_bytes = (uint32_t)W * 4u;
 
@@ -73,13 +78,11 @@ __global__ void __launch_bounds__(kDownThreads, 2) down_band_kernel(const __grid
     }
     if (threadIdx.x >= 32 && threadIdx.x < 36) {
         const int k = threadIdx.x - 32;
-        const int j = k < 2 ? k : Wo - 4 + k;
-        aa_axis_weights(j, W, R, colTab.w[k], colTab.xmin[k], colTab.xsize[k]);
+        aa_axis_weights(k < 2 ? k : Wo - 4 + k, W, R, colTab.w[k], colTab.xmin[k], colTab.xsize[k]);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 68) {
         const int k = threadIdx.x - 64;
-        const int i = k < 2 ? k : Ho - 4 + k;
-        aa_axis_weights(i, H, R, rowTab.w[k], rowTab.xmin[k], rowTab.xsize[k]);
+        aa_axis_weights(k < 2 ? k : Ho - 4 + k, H, R, rowTab.w[k], rowTab.xmin[k], rowTab.xsize[k]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -88,95 +91,94 @@ __global__ void __launch_bounds__(kDownThreads, 2) down_band_kernel(const __grid
         bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sStage), xplane, H, row_bytes, in_lo, n, &bar[0]);
     }
 
+    constexpr int SKIP = 4 * ((OFF + 3) / 4) - OFF;
+    constexpr int NV = (SKIP + 7 * R + 3) / 4;
+    const int IW = CW - 2;                                             // interior 4-output groups per row
     for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
-        // prefetch the next chunk into the other buffer (its previous contents were consumed
-        // before the __syncthreads that ended iteration c-1)
         if (threadIdx.x == 0 && c + 1 < nchunks) {
             const int n = min(CH, nin - (c + 1) * CH);
             fence_proxy_async();
             mbar_arrive_expect_tx(&bar[buf ^ 1], (uint32_t)n * row_bytes);
-            bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sStage + (size_t)(buf ^ 1) * CH * W), xplane, H,
+            bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sStage + (buf ^ 1) * CH * W), xplane, H,
                                     row_bytes, in_lo + (c + 1) * CH, n, &bar[buf ^ 1]);
         }
         mbar_wait(&bar[buf], (c >> 1) & 1);
         const int nrows = min(CH, nin - c * CH);
-        const float* stage = sStage + (size_t)buf * CH * W;
-        // ---- horizontal pass over this chunk: sTmp[row][j] = sum_t w[t] * in[row][R*j - OFF + t]
-        for (int item = threadIdx.x; item < nrows * CW; item += kDownThreads) {
-            const int r = item / CW, j4 = item - r * CW;
-            const float* row = stage + (size_t)r * W;
-            float out[4];
-            if (j4 > 0 && j4 < CW - 1) {
-                constexpr int SKIP = 4 * ((OFF + 3) / 4) - OFF;
-                constexpr int NV = (SKIP + 7 * R + 3) / 4;
-                const float* src = row + 4 * R * j4 - (OFF + SKIP);
-                float v[4 * NV];
+        const float* stage = sStage + buf * CH * W;
+        float* tmp = sTmp + c * CH * Wo;
+        // ---- horizontal pass, interior groups: tmp[row][j] = sum_t w[t] * in[row][R*j - OFF + t]
+        for (int item = threadIdx.x; item < nrows * IW; item += NT) {
+            const int r = item / IW, j4 = 1 + item - r * IW;
+            const float* src = stage + r * W + 4 * R * j4 - (OFF + SKIP);
+            float v[4 * NV];
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-                }
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], v[SKIP + R * o + t], a);
-                    out[o] = a;
-                }
-            } else {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int j = 4 * j4 + o;
-                    const int k = border_slot(j, Wo);
-                    float a = 0.f;
-                    if (k >= 0) {
-                        const float* src = row + colTab.xmin[k];
-                        for (int t = 0; t < colTab.xsize[k]; ++t) a = fmaf(colTab.w[k][t], src[t], a);
-                    } else {
-                        const float* src = row + R * j - OFF;
-#pragma unroll
-                        for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], src[t], a);
-                    }
-                    out[o] = a;
-                }
+            for (int q = 0; q < NV; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
             }
-            *reinterpret_cast<float4*>(sTmp + (size_t)(c * CH + r) * Wo + 4 * j4) = make_float4(out[0], out[1], out[2], out[3]);
+            float out[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], v[SKIP + R * o + t], a);
+                out[o] = a;
+            }
+            *reinterpret_cast<float4*>(tmp + r * Wo + 4 * j4) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+        // ---- horizontal pass, the 8 outputs of the first and last group of every row
+        for (int item = threadIdx.x; item < nrows * 8; item += NT) {
+            const int r = item >> 3, e = item & 7;
+            const int j = e < 4 ? e : Wo - 8 + e;
+            const int k = border_slot(j, Wo);
+            const float* row = stage + r * W;
+            float a = 0.f;
+            if (k >= 0) {
+                const float* src = row + colTab.xmin[k];
+                for (int t = 0; t < colTab.xsize[k]; ++t) a = fmaf(colTab.w[k][t], src[t], a);
+            } else {
+                const float* src = row + R * j - OFF;
+#pragma unroll
+                for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], src[t], a);
+            }
+            tmp[r * Wo + j] = a;
         }
         __syncthreads();
     }
 
-    // ---- vertical pass: y[i][j] = sum_t w[t] * sTmp[R*i - OFF + t - in_lo][j]
+    // ---- vertical pass: y[i][j] = sum_t w[t] * sTmp[R*i - OFF + t - in_lo][j]   (rows are warp-uniform)
     float* yplane = p.y + (size_t)plane * Ho * Wo;
     const float* nplane = p.noise ? p.noise + (size_t)plane * Ho * Wo : nullptr;
-    for (int item = threadIdx.x; item < th * CW; item += kDownThreads) {
+    for (int item = threadIdx.x; item < th * CW; item += NT) {
         const int r = item / CW, j4 = item - r * CW;
         const int i = i0 + r;
+        const int g = i * Wo + 4 * j4;
+        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nplane) nz = ld_stream4(nplane + g);
         const int k = border_slot(i, Ho);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < 0) {
-            const float* src = sTmp + (size_t)(R * i - OFF - in_lo) * Wo + 4 * j4;
+            const float* src = sTmp + (R * i - OFF - in_lo) * Wo + 4 * j4;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * Wo);
+                const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
                 const float w = p.wint[t];
                 acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                 acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
             }
         } else {
-            const float* src = sTmp + (size_t)(rowTab.xmin[k] - in_lo) * Wo + 4 * j4;
+            const float* src = sTmp + (rowTab.xmin[k] - in_lo) * Wo + 4 * j4;
             for (int t = 0; t < rowTab.xsize[k]; ++t) {
-                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * Wo);
+                const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
                 const float w = rowTab.w[k][t];
                 acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                 acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
             }
         }
-        const size_t g = (size_t)i * Wo + 4 * j4;
         if (nplane) {
-            const float4 n = ld_stream4(nplane + g);
-            acc.x = fmaf(p.sigma, n.x, acc.x); acc.y = fmaf(p.sigma, n.y, acc.y);
-            acc.z = fmaf(p.sigma, n.z, acc.z); acc.w = fmaf(p.sigma, n.w, acc.w);
+            acc.x = fmaf(p.sigma, nz.x, acc.x); acc.y = fmaf(p.sigma, nz.y, acc.y);
+            acc.z = fmaf(p.sigma, nz.z, acc.z); acc.w = fmaf(p.sigma, nz.w, acc.w);
         }
         st_stream4(yplane + g, acc);
     }
@@ -220,32 +222,37 @@ __device__ __forceinline__ void aa_contributors(int m, int in_size, int out_size
 
 constexpr int kBorderCols = 32;   // per side, >= 5*rate - off + slack
 
-template <int R>
-__global__ void __launch_bounds__(kDownThreads, 2) down_t_band_kernel(const __grid_constant__ DownParams p)
+// gx = A^T gy.  Interior rows / columns of gx receive exactly four outputs each, (m+OFF)/R - q with tap
+// (m+OFF)%R + R*q, q = 0..3 (a 4-tap polyphase upsampler); rows / columns near the border go through
+// contributor tables.  Interior and border are separate loops (no divergent warps).
+template <int R, int WT>
+__global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_constant__ DownParams p)
 {
     constexpr int OFF = aa_off(R);
+    constexpr int NT = kDownThreads;
     constexpr bool kStaticPhase = (4 % R) == 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ Contrib colL[kBorderCols], colR[kBorderCols];
 
-    const int H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo, CWo = Wo >> 2, CW = W >> 2;
+    const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R, CWo = Wo >> 2;
     const int band = blockIdx.x % p.nbands;
     const long long plane = blockIdx.x / p.nbands;
     const int m0 = band * p.TH;
     const int th = min(p.TH, H - m0);
-    // gradient rows that can contribute to rows [m0, m0+th)
     const int g_lo = max(0, (m0 + OFF) / R - 4);
     const int g_hi = min(Ho, (m0 + th - 1 + OFF) / R + 2);
     const int ng = g_hi - g_lo;
     const int GR = p.TH / R + 8;                     // allocated gradient rows
 
     float* sG = reinterpret_cast<float*>(smem_raw);             // [GR][Wo]
-    float* sTmp = sG + (size_t)GR * Wo;                          // [TH][Wo]
-    Contrib* rowC = reinterpret_cast<Contrib*>(sTmp + (size_t)p.TH * Wo);   // [TH]
+    float* sTmp = sG + GR * Wo;                                  // [TH][Wo]
+    Contrib* rowC = reinterpret_cast<Contrib*>(sTmp + p.TH * Wo);   // [TH] (used by border rows only)
 
     const int NL = min(W, 5 * R - OFF);                          // columns [0, NL) are border
     const int NR0 = max(NL, R * (Wo - 2) - OFF);                 // columns [NR0, W) are border
+    const int ML = min(H, 5 * R - OFF), MR0 = max(ML, R * (Ho - 2) - OFF);   // same for rows
+    const int n4_lo = (NL + 3) >> 2, n4_hi = max(n4_lo, NR0 >> 2);         // float4 groups that are fully interior
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -259,56 +266,78 @@ __global__ void __launch_bounds__(kDownThreads, 2) down_t_band_kernel(const __gr
                                 reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * Ho * Wo), Ho, row_bytes,
                                 g_lo, ng, &bar);
     }
-    // contributor tables (overlaps the copy)
-    for (int t = threadIdx.x; t < th; t += kDownThreads) aa_contributors(m0 + t, H, Ho, R, rowC[t]);
-    for (int t = threadIdx.x; t < NL; t += kDownThreads) aa_contributors(t, W, Wo, R, colL[t]);
-    for (int t = threadIdx.x; t < W - NR0; t += kDownThreads) aa_contributors(NR0 + t, W, Wo, R, colR[t]);
+    // contributor tables of the border rows of this band and of the border columns (overlaps the copy)
+    for (int t = threadIdx.x; t < th; t += NT) {
+        const int m = m0 + t;
+        if (m < ML || m >= MR0) aa_contributors(m, H, Ho, R, rowC[t]);
+    }
+    for (int t = threadIdx.x; t < 4 * n4_lo; t += NT) aa_contributors(t, W, Wo, R, colL[t]);
+    for (int t = threadIdx.x; t < W - 4 * n4_hi; t += NT) aa_contributors(4 * n4_hi + t, W, Wo, R, colR[t]);
     __syncthreads();
     if (ng > 0) mbar_wait(&bar, 0);
 
-    // ---- vertical pass: sTmp[m][j] = sum_q w_q * gy[i_q][j]
-    for (int item = threadIdx.x; item < th * CWo; item += kDownThreads) {
+    // ---- vertical pass: sTmp[m][j] = sum_q w_q * gy[i_q][j]   (rows are warp-uniform)
+    for (int item = threadIdx.x; item < th * CWo; item += NT) {
         const int r = item / CWo, j4 = item - r * CWo;
-        const Contrib& c = rowC[r];
+        const int m = m0 + r;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= ML && m < MR0) {
+            const int ph = (m + OFF) % R, ib = (m + OFF) / R;
+            const float* src = sG + (ib - g_lo) * Wo + 4 * j4;
 #pragma unroll
-        for (int q = 0; q < kNQ; ++q) {
-            const float w = c.w[q];
-            if (w != 0.f) {
-                const float4 v = *reinterpret_cast<const float4*>(sG + (size_t)(c.idx[q] - g_lo) * Wo + 4 * j4);
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(src - q * Wo);
+                const float w = p.wint[ph + R * q];
                 acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                 acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
             }
+        } else {
+            const Contrib& c = rowC[r];
+#pragma unroll
+            for (int q = 0; q < kNQ; ++q) {
+                const float w = c.w[q];
+                if (w != 0.f) {
+                    const float4 v = *reinterpret_cast<const float4*>(sG + (c.idx[q] - g_lo) * Wo + 4 * j4);
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+            }
         }
-        *reinterpret_cast<float4*>(sTmp + (size_t)r * Wo + 4 * j4) = acc;
+        *reinterpret_cast<float4*>(sTmp + r * Wo + 4 * j4) = acc;
     }
     __syncthreads();
 
-    // ---- horizontal pass: gx[m][n] = sum_q w_q * sTmp[m][j_q]
+    // ---- horizontal pass, interior float4 groups: gx[m][n] = sum_q wint[ph + R q] * sTmp[m][jb - q]
     float* gplane = p.y + (size_t)plane * H * W;
-    for (int item = threadIdx.x; item < th * CW; item += kDownThreads) {
-        const int r = item / CW, n4 = item - r * CW;
-        const float* row = sTmp + (size_t)r * Wo;
+    const int IWn = n4_hi - n4_lo;
+    for (int item = threadIdx.x; item < th * IWn; item += NT) {
+        const int r = item / IWn, n4 = n4_lo + item - r * IWn;
+        const float* row = sTmp + r * Wo;
         float out[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             const int n = 4 * n4 + o;
+            const int ph = kStaticPhase ? (o + OFF) % R : (n + OFF) % R;
+            const int jb = kStaticPhase ? (4 / R) * n4 + (o + OFF) / R : (n + OFF) / R;
             float a = 0.f;
-            if (n >= NL && n < NR0) {
-                // interior: outputs j = (n+OFF)/R - q, tap (n+OFF)%R + R*q, q = 0..3
-                const int ph = kStaticPhase ? (o + OFF) % R : (n + OFF) % R;
-                const int jb = kStaticPhase ? (4 / R) * n4 + (o + OFF) / R : (n + OFF) / R;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a = fmaf(p.wint[ph + R * q], row[jb - q], a);
-            } else {
-                const Contrib& c = n < NL ? colL[n] : colR[n - NR0];
-#pragma unroll
-                for (int q = 0; q < kNQ; ++q)
-                    if (c.w[q] != 0.f) a = fmaf(c.w[q], row[c.idx[q]], a);
-            }
+            for (int q = 0; q < 4; ++q) a = fmaf(p.wint[ph + R * q], row[jb - q], a);
             out[o] = a;
         }
         st_stream4(gplane + (size_t)(m0 + r) * W + 4 * n4, make_float4(out[0], out[1], out[2], out[3]));
+    }
+    // ---- horizontal pass, border columns
+    const int nbl = 4 * n4_lo, nbr = W - 4 * n4_hi;
+    for (int item = threadIdx.x; item < th * (nbl + nbr); item += NT) {
+        const int r = item / (nbl + nbr), e = item - r * (nbl + nbr);
+        const int n = e < nbl ? e : 4 * n4_hi + (e - nbl);
+        const Contrib& c = e < nbl ? colL[e] : colR[e - nbl];
+        const float* row = sTmp + r * Wo;
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q)
+            if (c.w[q] != 0.f) a = fmaf(c.w[q], row[c.idx[q]], a);
+        gplane[(size_t)(m0 + r) * W + n] = a;
     }
 }
 
@@ -428,18 +457,26 @@ static void interior_weights(int rate, float* wint)
     for (int t = 0; t < kAaMaxTaps; ++t) wint[t] = w[t];
 }
 
-template <int R>
-static int launch_down(const DownParams& p, long long planes, size_t smem, cudaStream_t st, bool transpose)
+template <int R, int WT>
+static int launch_down_w(const DownParams& p, long long planes, size_t smem, cudaStream_t st, bool transpose)
 {
     const unsigned grid = (unsigned)(planes * p.nbands);
     if (transpose) {
-        SEI_CUDA(allow_smem(down_t_band_kernel<R>, smem));
-        down_t_band_kernel<R><<<grid, kDownThreads, smem, st>>>(p);
+        SEI_CUDA(allow_smem(down_t_band_kernel<R, WT>, smem));
+        down_t_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(p);
         return finish_launch("down_t_band_kernel");
     }
-    SEI_CUDA(allow_smem(down_band_kernel<R>, smem));
-    down_band_kernel<R><<<grid, kDownThreads, smem, st>>>(p);
+    SEI_CUDA(allow_smem(down_band_kernel<R, WT>, smem));
+    down_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(p);
     return finish_launch(p.noise ? "down_band_kernel<noise>" : "down_band_kernel");
+}
+
+// width-specialised for measurements of 256 x 256 (input width 256 * rate), run-time width otherwise
+template <int R>
+static int launch_down(const DownParams& p, long long planes, size_t smem, cudaStream_t st, bool transpose)
+{
+    if (p.W == 256 * R) return launch_down_w<R, 256 * R>(p, planes, smem, st, transpose);
+    return launch_down_w<R, 0>(p, planes, smem, st, transpose);
 }
 
 static int down_common(const float* in, float* out, long long planes, int H, int W, int rate,
@@ -469,7 +506,8 @@ static int down_common(const float* in, float* out, long long planes, int H, int
         if (!transpose) {
             p.CH = std::max(1, (int)(16384 / ((size_t)W * 4)));
             int best = 0;
-            for (int th = 4; th <= 32; th += 4) {
+            const int th_max = getenv("SEI_DOWN_TH") ? atoi(getenv("SEI_DOWN_TH")) : 16;
+            for (int th = 4; th <= th_max; th += 4) {
                 const size_t need = ((size_t)(rate * th + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
                 if (need <= budget) best = th;
             }
@@ -478,7 +516,8 @@ static int down_common(const float* in, float* out, long long planes, int H, int
             smem = ((size_t)(rate * p.TH + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
         } else {
             int best = 0;
-            for (int th = 8; th <= 64; th += 8) {
+            const int th_max = getenv("SEI_DOWNT_TH") ? atoi(getenv("SEI_DOWNT_TH")) : 32;
+            for (int th = 8; th <= th_max; th += 8) {
                 const size_t need = ((size_t)(th / rate + 8) * Wo + (size_t)th * Wo) * 4 + (size_t)th * sizeof(Contrib);
                 if (need <= budget) best = th;
             }
@@ -487,8 +526,10 @@ static int down_common(const float* in, float* out, long long planes, int H, int
             p.nbands = p.TH ? (H + p.TH - 1) / p.TH : 0;
             smem = ((size_t)(p.TH / rate + 8) * Wo + (size_t)p.TH * Wo) * 4 + (size_t)p.TH * sizeof(Contrib);
             // border-column tables hold kBorderCols entries per side
-            tiled_ok = tiled_ok && (5 * rate - aa_off(rate)) <= kBorderCols &&
-                       (W - std::max(5 * rate - aa_off(rate), rate * (Wo - 2) - aa_off(rate))) <= kBorderCols;
+            // border-column tables hold kBorderCols entries per side (columns outside the interior float4 groups)
+            const int NL = 5 * rate - aa_off(rate), NR0 = std::max(NL, rate * (Wo - 2) - aa_off(rate));
+            const int n4_lo = (NL + 3) / 4, n4_hi = std::max(n4_lo, NR0 / 4);
+            tiled_ok = tiled_ok && 4 * n4_lo <= kBorderCols && (W - 4 * n4_hi) <= kBorderCols;
         }
         tiled_ok = tiled_ok && p.TH > 0 && planes * p.nbands < (1ll << 31);
     }

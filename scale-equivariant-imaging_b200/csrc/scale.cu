@@ -28,13 +28,14 @@ struct ScaleParams {
     float two_over_S;
 };
 
+template <int ST>
 __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __grid_constant__ ScaleParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ int s_lo, s_hi;
 
-    const int S = p.S, CW = S >> 2;
+    const int S = ST ? ST : p.S;
     const int band = blockIdx.x % p.nbands;
     const long long plane = blockIdx.x / p.nbands;
     const int b = (int)(plane / p.C);
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __gr
             for (int a = 0; a < 4; ++a) rowT[threadIdx.x].idx[a] -= lo;
         }
         __syncthreads();
-        scale_vpass<kScaleThreads>(sSrc, sTmp, S, th, rowT);
+        scale_vpass<kScaleThreads, ST>(sSrc, sTmp, S, th, rowT);
     } else {
         __syncthreads();
-        scale_vpass<kScaleThreads>(xplane, sTmp, S, th, rowT);
+        scale_vpass<kScaleThreads, ST>(xplane, sTmp, S, th, rowT);
     }
     __syncthreads();
 
@@ -103,9 +104,9 @@ __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __gr
     if (grp < ngrp) {
         for (int j = threadIdx.x - grp * S; j < S; j += kScaleThreads) {
             const AxisTap t = colT[j];
-            for (int r = grp; r < th; r += ngrp) {
-                __stcs(oplane + (size_t)(r0 + r) * S + j, scale_hgather(sTmp + (size_t)r * S, t));
-            }
+#pragma unroll 4
+            for (int r = grp; r < th; r += ngrp)
+                __stcs(oplane + (size_t)(r0 + r) * S + j, scale_hgather(sTmp + r * S, t));
         }
     }
 }
@@ -206,8 +207,17 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
         p.x = x; p.out = out; p.rate = rate; p.center = center;
         p.C = C; p.S = S; p.TH = TH; p.nbands = (S + TH - 1) / TH; p.SRC_MAX = scale_src_rows(TH);
         p.two_over_S = two_over_S;
-        SEI_CUDA(allow_smem(scale_band_kernel, smem));
-        scale_band_kernel<<<(unsigned)(planes * p.nbands), kScaleThreads, smem, st>>>(p);
+        const unsigned grid = (unsigned)(planes * p.nbands);
+        if (S == 256) {
+            SEI_CUDA(allow_smem(scale_band_kernel<256>, smem));
+            scale_band_kernel<256><<<grid, kScaleThreads, smem, st>>>(p);
+        } else if (S == 512) {
+            SEI_CUDA(allow_smem(scale_band_kernel<512>, smem));
+            scale_band_kernel<512><<<grid, kScaleThreads, smem, st>>>(p);
+        } else {
+            SEI_CUDA(allow_smem(scale_band_kernel<0>, smem));
+            scale_band_kernel<0><<<grid, kScaleThreads, smem, st>>>(p);
+        }
         return finish_launch("scale_band_kernel");
     }
     ScaleDirectParams d;

@@ -23,7 +23,8 @@ SIGNATURES = {
     "sei_up_bicubic_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp]),
     "sei_scale_transform_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sei_scale_params_f32": (C.c_int, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
-    "sei_ei_remeasure_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp]),
+    "sei_ei_workspace_bytes": (C.c_longlong, [_i, _i]),
+    "sei_ei_remeasure_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _vp]),
     "sei_reduce_workspace_bytes": (C.c_longlong, []),
     "sei_mse_f32": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _vp]),
     "sei_mse_backward_f32": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _vp, _vp]),

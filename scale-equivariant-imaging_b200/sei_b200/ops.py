@@ -156,7 +156,19 @@ def scale_transform(x, rate, center, path=PATH_AUTO):
     return out
 
 
-def ei_remeasure(x_net, rate, center, kernel_host, rate_sr, noise, sigma):
+_ei_workspaces = {}
+
+
+def _ei_workspace(x, B, S):
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream, B, S)
+    ws = _ei_workspaces.get(key)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().sei_ei_workspace_bytes(B, S)), dtype=torch.uint8, device=x.device)
+        _ei_workspaces[key] = ws
+    return ws
+
+
+def ei_remeasure(x_net, rate, center, kernel_host, rate_sr, noise, sigma, use_workspace=True):
     x_net = _t(x_net, "x_net")
     B, Cc, S, S2 = x_net.shape
     if S != S2:
@@ -172,9 +184,11 @@ def ei_remeasure(x_net, rate, center, kernel_host, rate_sr, noise, sigma):
         kh, kw = k.shape
     else:
         kp, kh, kw = None, 0, 0
+    ws = _ei_workspace(x_net, B, S) if use_workspace else None
     with torch.cuda.device(x_net.device):
         check(_lib.load().sei_ei_remeasure_f32(_ptr(x_net), _ptr(x2), _ptr(y), B, Cc, S, _ptr(rate), _ptr(center),
-                                               kp, kh, kw, int(rate_sr), _ptr(n), float(sigma), _stream(x_net)))
+                                               kp, kh, kw, int(rate_sr), _ptr(n), float(sigma), _ptr(ws),
+                                               _stream(x_net)))
     return x2, y
 
 

@@ -217,7 +217,8 @@ def test_scale_params_and_module(golden, dev):
 @pytest.mark.parametrize("kname,B,C,S", [("Gaussian_R2", 4, 3, 48), ("Gaussian_R2", 2, 3, 256), ("Box_R3", 3, 3, 256),
                                          ("Gaussian_R1", 2, 1, 64), ("Gaussian_R3", 1, 3, 128), ("Box_R2", 2, 2, 32),
                                          ("Gaussian_R2", 1, 1, 16), ("Gaussian_R2", 1, 3, 1024)])
-def test_ei_remeasure_blur_vs_oracle(dev, kname, B, C, S):
+@pytest.mark.parametrize("fused", [True, False])
+def test_ei_remeasure_blur_vs_oracle(dev, kname, B, C, S, fused, monkeypatch):
     from sei_b200 import ops, last_kernel
     rng = np.random.default_rng(9)
     x = rng.random((B, C, S, S), dtype=np.float32)
@@ -227,8 +228,9 @@ def test_ei_remeasure_blur_vs_oracle(dev, kname, B, C, S):
     n = rng.standard_normal((B, C, S, S)).astype(np.float32)
     kern = orc.named_kernel(kname)
     sigma = float(np.float32(5 / 255))
+    monkeypatch.setenv("SEI_EI_FUSED", "1" if fused else "0")
     x2, y = ops.ei_remeasure(cu(x, dev), cu(rate, dev), cu(center, dev), kern, 1, cu(n, dev), sigma)
-    assert last_kernel() == ("ei_blur_band_kernel" if S <= 512 else "blur_band_kernel<noise>")
+    assert last_kernel() == ("ei_blur_band_kernel" if (fused and S <= 512) else "blur_band_kernel<noise>")
     x2_ref = orc.scale_transform(x, rate, center)
     assert rel_err(npy(x2), x2_ref) < TOL
     y_ref = orc.add_noise(orc.blur_circular(x2_ref.astype(np.float64), kern), n.astype(np.float64), sigma)
@@ -237,6 +239,9 @@ def test_ei_remeasure_blur_vs_oracle(dev, kname, B, C, S):
     x2u = ops.scale_transform(cu(x, dev), cu(rate, dev), cu(center, dev))
     yu = ops.blur_circular(x2u, kern, noise=cu(n, dev), sigma=sigma)
     assert rel_err(npy(x2), npy(x2u)) < 2e-6 and rel_err(npy(y), npy(yu)) < 2e-6
+    # taps computed inside the fused kernel (no workspace) give the same result
+    x2n, yn = ops.ei_remeasure(cu(x, dev), cu(rate, dev), cu(center, dev), kern, 1, cu(n, dev), sigma, use_workspace=False)
+    assert torch.equal(x2n, x2) and torch.equal(yn, y)
     # no noise
     _, y0 = ops.ei_remeasure(cu(x, dev), cu(rate, dev), cu(center, dev), kern, 1, None, 0.0)
     assert rel_err(npy(y0), orc.blur_circular(x2_ref.astype(np.float64), kern)) < TOL
