@@ -93,6 +93,10 @@ int sei_up_bicubic_f32(const float* y, float* x, long long planes, int h, int w,
  * (they are drawn on the device; no host sync). */
 int sei_scale_transform_f32(const float* x, float* out, int B, int C, int S,
                             const float* rate, const float* center, int path, void* stream);
+/* transpose of the above w.r.t. x (autograd through grid_sample; only reached with
+ * --no-ProposedLoss__stop_gradient).  gx is overwritten. */
+int sei_scale_transform_backward_f32(const float* gout, float* gx, int B, int C, int S,
+                                     const float* rate, const float* center, void* stream);
 /* sample_from + sample_downsampling_parameters (src/transforms.py:5-24) given the two
  * uniform draws u_rate (B) and u_center (B x 2):
  *   rate_b = rates[floor(n_rates * u_rate_b)],  center_b = 2 * u_center_b - 1. */
@@ -148,6 +152,11 @@ int sei_sure_loss_backward_f32(const float* y1, const float* y, const float* b,
  * margin == 0).  b_out (optional) receives the zero-bordered b. */
 int sei_sure_perturb_f32(const float* y, const float* draw, int B, int C, int H, int W,
                          int margin, float tau, float* out, float* b_out, void* stream);
+
+/* torch.roll(x, (shift_h, shift_w), (-2, -1)) per plane: the action of deepinv's Shift transform
+ * (ProposedLoss__transforms=Shifts, src/losses/__init__.py:91-94) */
+int sei_roll_f32(const float* in, float* out, long long planes, int H, int W, int shift_h, int shift_w,
+                 void* stream);
 
 /* deepinv GaussianNoise.forward: out = y + sigma * noise */
 int sei_add_noise_f32(const float* y, const float* noise, long long n, float sigma, float* out,

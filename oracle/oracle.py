@@ -175,6 +175,18 @@ def scale_transform(x, rate, center):
     return out
 
 
+def scale_transform_vjp(gout, rate, center):
+    """transpose of scale_transform w.r.t. its image argument (autograd through grid_sample)"""
+    gout = _c(gout)
+    sfx, _ = _sfx(gout)
+    B, Cc, S, _ = gout.shape
+    rate = _c(rate, gout.dtype).reshape(B)
+    center = _c(center, gout.dtype).reshape(B, 2)
+    gx = np.empty_like(gout)
+    getattr(lib(), f"orc_scale_transform_vjp_{sfx}")(_p(gout), _p(gx), B, Cc, S, _p(rate), _p(center))
+    return gx
+
+
 def sample_params_from_uniforms(u_rate, u_center, rates=(0.75, 0.5)):
     """sample_from + sample_downsampling_parameters (src/transforms.py:5-24) given the two
     uniform draws (shape (B,) then (B, 2)) the reference takes from torch.rand, in order."""
@@ -275,6 +287,13 @@ def pointwise_model(w, c, rate=1):
         g = g.astype(np.float64)
         return np.array([(g * u).sum(), (g * np.roll(u, (1, 2), (-2, -1))).sum(), (g * u * u).sum()]), g.sum()
 
+    def input_vjp(v, g):
+        """d<g, fwd(v)>/dv (rate 1 only: nearest upsampling is not needed by the tests that use this)"""
+        assert rate == 1
+        dt = v.dtype.type
+        return dt(w[0]) * g + dt(w[1]) * np.roll(g, (-1, -2), (-2, -1)) + dt(2) * dt(w[2]) * v * g
+
+    fwd.input_vjp = input_vjp
     return fwd, param_grad
 
 
@@ -304,3 +323,20 @@ def proposed_step(physics, w, c, y, draws, margin, rate=1, alpha=1.0, tau=1e-2, 
         gc += b_
     out.update(grad_w=gw, grad_c=gc, g_xnet=g_xnet, g_xnet2=g_xnet2, g_x3=g_x3)
     return out
+
+
+def r2r_ei_loss(physics, model, y, draws, eta, alpha_r2r=0.5):
+    """R2REILoss.forward (src/losses/r2r.py:26-57) with every random tensor supplied:
+    draws = dict(pert=, eps1=, u_rate=, u_center=, eps2=) in the reference's draw order; eta = sigma."""
+    dt = y.dtype.type
+    pert = draws["pert"] * dt(eta)
+    y_plus, y_minus = y + pert * dt(alpha_r2r), y - pert / dt(alpha_r2r)
+    out0 = model(y_plus)
+    l_r2r = mse(physics.A(out0), y_minus)
+    x1 = model(y + dt(0.5) * dt(eta) * draws["eps1"])
+    rate, center = sample_params_from_uniforms(draws["u_rate"], draws["u_center"])
+    x2 = scale_transform(x1, rate, center)
+    y2 = physics.A(x2)
+    x3 = model(y2 + dt(1.5) * dt(eta) * draws["eps2"])
+    l_ei = mse(x3, x2)
+    return dict(loss=l_r2r + l_ei, out0=out0, x1=x1, x2=x2, x3=x3)

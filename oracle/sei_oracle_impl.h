@@ -412,6 +412,39 @@ void FN(orc_scale_transform)(const REAL* x, REAL* out, int B, int C, int S,
         }
 }
 
+/* transpose of orc_scale_transform w.r.t. x: what autograd computes through grid_sample when
+ * ProposedLoss__stop_gradient is off (deepinv EILoss no_grad=False; src/losses/__init__.py:117-122). */
+void FN(orc_scale_transform_vjp)(const REAL* gout, REAL* gx, int B, int C, int S,
+                                 const REAL* rate, const REAL* center)
+{
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c) {
+            const REAL inv_rate = (REAL)1.0 / rate[b];
+            const REAL* gp = gout + ((long)b * C + c) * S * S;
+            REAL* xp = gx + ((long)b * C + c) * S * S;
+            for (long i = 0; i < (long)S * S; ++i) xp[i] = 0;
+            for (int i = 0; i < S; ++i) {
+                const REAL gy = FN(orc_grid_coord)(i, S, inv_rate, center[2 * b + 1]);
+                const REAL py = ((gy + 1) / 2) * (REAL)(S - 1);
+                const REAL fy = (REAL)floor((double)py);
+                REAL cy[4]; FN(orc_cubic_coeffs)(py - fy, cy);
+                int ry[4];
+                for (int a = 0; a < 4; ++a) ry[a] = FN(orc_reflect_clip)((int)fy - 1 + a, S);
+                for (int j = 0; j < S; ++j) {
+                    const REAL gxc = FN(orc_grid_coord)(j, S, inv_rate, center[2 * b + 0]);
+                    const REAL px = ((gxc + 1) / 2) * (REAL)(S - 1);
+                    const REAL fx = (REAL)floor((double)px);
+                    REAL cx[4]; FN(orc_cubic_coeffs)(px - fx, cx);
+                    const REAL g = gp[(long)i * S + j];
+                    for (int a = 0; a < 4; ++a)
+                        for (int t = 0; t < 4; ++t)
+                            xp[(long)ry[a] * S + FN(orc_reflect_clip)((int)fx - 1 + t, S)] += g * cy[a] * cx[t];
+                }
+            }
+        }
+}
+
 /* ------------------------------------------------------------------------------------
  * Loss assembly.
  * SureGaussianLoss.forward + mc_div (src/losses/sure.py:7-76), given the operator

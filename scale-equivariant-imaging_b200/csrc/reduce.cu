@@ -275,6 +275,23 @@ __global__ void __launch_bounds__(256) add_noise_kernel(const float* __restrict_
         out[idx] = __fadd_rn(y[idx], __fmul_rn(n[idx], sigma));
 }
 
+// circular shift of every plane by (sy, sx): out[i][j] = in[(i - sy) mod H][(j - sx) mod W]   (torch.roll; the
+// group action of deepinv's Shift transform used by the "ei-shift" ablation, src/losses/__init__.py:91-94)
+__global__ void __launch_bounds__(256) roll_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                   int sy, int sx, long long total)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % W);
+        const long long t = idx / W;
+        const int i = (int)(t % H);
+        int si = i - sy, sj = j - sx;
+        si += si < 0 ? H : 0;
+        sj += sj < 0 ? W : 0;
+        out[idx] = __ldg(in + (t / H) * (long long)H * W + (long long)si * W + sj);
+    }
+}
+
 static unsigned red_grid(long long n, int sm_count)
 {
     const long long want = (n + (long long)kRedThreads * 16 - 1) / ((long long)kRedThreads * 16);
@@ -386,6 +403,20 @@ extern "C" int sei_sure_perturb_f32(const float* y, const float* draw, int B, in
     sure_perturb_kernel<<<ew_grid(total, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         y, draw, H, W, margin, tau, total, out, b_out);
     return finish_launch("sure_perturb_kernel");
+}
+
+extern "C" int sei_roll_f32(const float* in, float* out, long long planes, int H, int W, int shift_h, int shift_w, void* stream)
+{
+    SEI_REQUIRE(in && out && in != out, "null or aliased pointer argument");
+    SEI_REQUIRE(planes >= 0 && H > 0 && W > 0, "bad shape");
+    if (planes == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const int sy = ((shift_h % H) + H) % H, sx = ((shift_w % W) + W) % W;
+    const long long total = planes * (long long)H * W;
+    roll_kernel<<<ew_grid(total, dp.sm_count), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, H, W, sy, sx, total);
+    return finish_launch("roll_kernel");
 }
 
 extern "C" int sei_add_noise_f32(const float* y, const float* noise, long long n, float sigma, float* out, void* stream)

@@ -150,6 +150,34 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const __grid_constant
     }
 }
 
+// transpose of the transform w.r.t. the image (autograd through grid_sample when stop_gradient is off, reference
+// src/losses/__init__.py:117-122 with no_grad=False): every output gradient is scattered to its 4x4 taps with
+// fp32 atomics into a zeroed buffer.  Not on the default path (stop_gradient=True), so a direct kernel.
+__global__ void __launch_bounds__(256) scale_backward_kernel(const __grid_constant__ ScaleDirectParams p)
+{
+    const int S = p.S;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % S);
+        const long long t = idx / S;
+        const int i = (int)(t % S);
+        const long long plane = t / S;
+        const int b = (int)(plane / p.C);
+        const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
+        AxisTap ty, tx;
+        scale_axis_tap(i, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b + 1), ty);
+        scale_axis_tap(j, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b), tx);
+        float* gx = p.out + plane * (long long)S * S;
+        const float g = __ldg(p.x + idx);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float ga = g * ty.w[a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(gx + (size_t)ty.idx[a] * S + tx.idx[c], ga * tx.w[c]);
+        }
+    }
+}
+
 __global__ void scale_params_kernel(const float* u_rate, const float* u_center, int B, int n_rates,
                                     float r0, float r1, float r2, float r3, float* rate, float* center)
 {
@@ -227,6 +255,26 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
     const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
     scale_direct_kernel<<<grid, 256, 0, st>>>(d);
     return finish_launch("scale_direct_kernel");
+}
+
+extern "C" int sei_scale_transform_backward_f32(const float* gout, float* gx, int B, int C, int S,
+                                                const float* rate, const float* center, void* stream)
+{
+    SEI_REQUIRE(gout && gx && rate && center, "null pointer argument");
+    SEI_REQUIRE(B >= 0 && C > 0 && S > 0, "bad shape B=%d C=%d S=%d", B, C, S);
+    if (B == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    ScaleDirectParams d;
+    d.x = gout; d.out = gx; d.rate = rate; d.center = center; d.C = C; d.S = S;
+    d.two_over_S = (float)(2.0 / (double)S);
+    d.total = (long long)B * C * S * S;
+    SEI_CUDA(cudaMemsetAsync(gx, 0, (size_t)d.total * sizeof(float), st));
+    const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
+    scale_backward_kernel<<<grid, 256, 0, st>>>(d);
+    return finish_launch("scale_backward_kernel");
 }
 
 extern "C" int sei_scale_params_f32(const float* u_rate, const float* u_center, int B,

@@ -7,8 +7,9 @@ from torch.nn import Module
 from torch.nn.functional import l1_loss
 
 from crop import CropPair
-from sei_b200.linear_physics import SupLoss, EILoss, mse
+from sei_b200.linear_physics import SupLoss, EILoss, Shift, mse
 from transforms import ScalingTransform, CombinedTransform  # noqa: F401
+from .r2r import R2REILoss
 from .sure import SureGaussianLoss
 
 
@@ -53,8 +54,10 @@ class SURELoss(_ModelThenLoss):
 def _ei_transform(transforms, blueprint):
     if transforms == "Scaling_Transforms":
         return ScalingTransform(**blueprint[ScalingTransform.__name__])
-    if transforms in ("Rotations+Shifts", "Rotations", "Shifts"):
-        raise NotImplementedError(f"ProposedLoss__transforms={transforms} (deepinv Rotate/Shift) is not built yet "
+    if transforms == "Shifts":
+        return Shift()
+    if transforms in ("Rotations+Shifts", "Rotations"):
+        raise NotImplementedError(f"ProposedLoss__transforms={transforms} (deepinv Rotate) is not built yet "
                                   "(SURVEY.md section 8f, N3)")
     raise ValueError(f"Unknown transforms: {transforms}")
 
@@ -69,13 +72,15 @@ class ProposedLoss(Module):
         ei_transform = _ei_transform(transforms, blueprint)
         assert sure_alternative in [None, "r2r"]
         if sure_alternative == "r2r":
-            raise NotImplementedError("ProposedLoss__sure_alternative=r2r is not built yet (SURVEY.md section 8f, N3)")
-        self.loss_fns = [
-            SureGaussianLoss(sigma=noise_level / 255, cropped_div=sure_cropped_div,
-                             averaged_cst=sure_averaged_cst, margin=sure_margin),
-            EILoss(metric=mse(), transform=ei_transform, no_grad=stop_gradient, weight=alpha_tradeoff),
-        ]
-        self.compute_x_net = True
+            self.loss_fns = [R2REILoss(transform=ei_transform, sigma=noise_level / 255, no_grad=stop_gradient,
+                                       metric=mse())]
+        else:
+            self.loss_fns = [
+                SureGaussianLoss(sigma=noise_level / 255, cropped_div=sure_cropped_div,
+                                 averaged_cst=sure_averaged_cst, margin=sure_margin),
+                EILoss(metric=mse(), transform=ei_transform, no_grad=stop_gradient, weight=alpha_tradeoff),
+            ]
+        self.compute_x_net = sure_alternative != "r2r"
 
     def forward(self, x, y, model):
         x_net = model(y) if self.compute_x_net else None

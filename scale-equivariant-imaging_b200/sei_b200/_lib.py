@@ -22,6 +22,7 @@ SIGNATURES = {
     "sei_down_aa_transpose_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "sei_up_bicubic_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp]),
     "sei_scale_transform_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sei_scale_transform_backward_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_params_f32": (C.c_int, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "sei_ei_workspace_bytes": (C.c_longlong, [_i, _i]),
     "sei_ei_remeasure_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _vp]),
@@ -31,6 +32,7 @@ SIGNATURES = {
     "sei_sure_loss_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp]),
     "sei_sure_loss_backward_f32": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
     "sei_sure_perturb_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "sei_roll_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "sei_add_noise_f32": (C.c_int, [_vp, _vp, _ll, _f, _vp, _vp]),
     "sei_gemm_bf16_tn": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),
 }

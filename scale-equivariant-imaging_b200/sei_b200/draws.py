@@ -47,3 +47,10 @@ def randn(shape, device, dtype):
 
 def randn_like(x):
     return randn(tuple(x.shape), x.device, x.dtype)
+
+
+def randperm(n):
+    """torch.randperm(n) on the CPU generator (deepinv's Shift / Rotate draw their group element this way)"""
+    if _queue is not None:
+        return _next((n,), "cpu", torch.int64)
+    return torch.randperm(n)

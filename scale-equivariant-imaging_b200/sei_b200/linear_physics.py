@@ -153,3 +153,23 @@ class EILoss(nn.Module):
         x2, y = self._remeasure(x_net, physics)
         x3 = model(y, physics)
         return self.weight * self.metric(x3, x2)
+
+
+class Shift(nn.Module):
+    """deepinv.transform.Shift (v0.2.0, n_trans = 1): one random circular shift of the whole batch in both axes.
+    Draws follow tests/golden/deepinv_shim (two CPU randperm draws); the roll itself is sei_roll_f32."""
+
+    def __init__(self, n_trans=1, shift_max=1.0):
+        super().__init__()
+        if n_trans != 1:
+            raise NotImplementedError("Shift(n_trans != 1) is not used by the reference's losses")
+        self.n_trans = n_trans
+        self.shift_max = shift_max
+
+    def forward(self, x):
+        H, W = x.shape[-2:]
+        assert self.n_trans <= H - 1 and self.n_trans <= W - 1
+        H_max, W_max = int(self.shift_max * H), int(self.shift_max * W)
+        sh = int(torch.arange(-H_max, H_max)[draws.randperm(2 * H_max)][0])
+        sw = int(torch.arange(-W_max, W_max)[draws.randperm(2 * W_max)][0])
+        return ops._Roll.apply(x, sh, sw)

@@ -192,6 +192,26 @@ def ei_remeasure(x_net, rate, center, kernel_host, rate_sr, noise, sigma, use_wo
     return x2, y
 
 
+def roll(x, shift_h, shift_w):
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_roll_f32(_ptr(x), _ptr(out), B * Cc, H, W, int(shift_h), int(shift_w), _stream(x)))
+    return out
+
+
+class _Roll(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift_h, shift_w):
+        ctx.shift = (shift_h, shift_w)
+        return roll(x, shift_h, shift_w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return roll(g, -ctx.shift[0], -ctx.shift[1]), None, None
+
+
 def add_noise(y, noise, sigma):
     y, noise = _t(y, "y"), _t(noise, "noise")
     out = torch.empty_like(y)
@@ -303,16 +323,28 @@ class _AddNoise(torch.autograd.Function):
         return g, None, None
 
 
+def scale_transform_backward(g, rate, center):
+    g = _t(g, "grad")
+    B, Cc, S, _ = g.shape
+    rate, center = _t(rate, "downsampling_rate").reshape(-1), _t(center, "center").reshape(-1)
+    gx = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        check(_lib.load().sei_scale_transform_backward_f32(_ptr(g), _ptr(gx), B, Cc, S, _ptr(rate), _ptr(center), _stream(g)))
+    return gx
+
+
 class _ScaleTransform(torch.autograd.Function):
+    """x -> T(x); backward (only reached with --no-ProposedLoss__stop_gradient) is the scatter kernel."""
+
     @staticmethod
     def forward(ctx, x, rate, center, path):
+        ctx.save_for_backward(rate, center)
         return scale_transform(x, rate, center, path=path)
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError(
-            "backward through the scale transform (--no-ProposedLoss__stop_gradient) is not implemented yet; "
-            "the reference default is stop_gradient=True (demo/train.py:47-49)")
+        rate, center = ctx.saved_tensors
+        return scale_transform_backward(g, rate, center), None, None, None
 
 
 class _Mse(torch.autograd.Function):

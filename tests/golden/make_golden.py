@@ -59,7 +59,7 @@ torch.set_num_threads(4)
 class DrawRecorder:
     """Wrap torch.rand / randn / randn_like / randint so every draw is logged in order."""
 
-    NAMES = ("rand", "randn", "randn_like", "randint")
+    NAMES = ("rand", "randn", "randn_like", "randint", "randperm")
 
     def __init__(self):
         self.draws = []
@@ -271,8 +271,17 @@ def gen_losses():
         ("sr2_css", dict(task="sr", kernel=None, sr_factor=2, method="css"), (2, 3, 16, 16)),
         ("deblur_gauss2_proposed_alpha", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__alpha_tradeoff=0.3), (2, 3, 32, 32)),
         ("cfg1_deblur_gauss2_proposed", dict(task="deblurring", kernel="Gaussian_R2", method="proposed"), (8, 3, 48, 48)),
+        # section 8(f) N3 variants
+        ("deblur_gauss2_r2r", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__sure_alternative="r2r"), (2, 3, 32, 32)),
+        ("sr2_r2r", dict(task="sr", kernel=None, sr_factor=2, method="proposed", ProposedLoss__sure_alternative="r2r"), (2, 3, 16, 16)),
+        ("deblur_gauss2_nostopgrad", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__stop_gradient=False), (2, 3, 32, 32)),
+        ("deblur_gauss2_shifts", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Shifts"), (2, 3, 32, 32)),
+        ("sr2_nostopgrad", dict(task="sr", kernel=None, sr_factor=2, method="proposed", ProposedLoss__stop_gradient=False), (2, 3, 16, 16)),
     ]
+    only = os.environ.get("GOLDEN_ONLY", "")
     for name, kw, yshape in cases:
+        if only and only not in name:
+            continue
         for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
             if tag == "f64" and kw.get("physics_v2") is False:
                 continue  # v1 Blur is fp32-only

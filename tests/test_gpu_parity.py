@@ -213,6 +213,22 @@ def test_scale_params_and_module(golden, dev):
     assert float(center.min()) >= -1 and float(center.max()) <= 1 and center.shape == (4096, 1, 1, 2)
 
 
+def test_scale_transform_backward_vs_oracle(dev):
+    from sei_b200 import ops
+    rng = np.random.default_rng(13)
+    for B, C, S in [(3, 2, 40), (2, 3, 256)]:
+        g = rng.standard_normal((B, C, S, S)).astype(np.float32)
+        rate = rng.choice(np.array([0.75, 0.5], np.float32), size=B)
+        center = (2 * rng.random((B, 1, 1, 2), dtype=np.float32) - 1).astype(np.float32)
+        gx = ops.scale_transform_backward(cu(g, dev), cu(rate, dev), cu(center, dev))
+        assert rel_err(npy(gx), orc.scale_transform_vjp(g, rate, center)) < TOL
+        # adjointness with the forward kernel
+        x = rng.random((B, C, S, S), dtype=np.float32)
+        Tx = ops.scale_transform(cu(x, dev), cu(rate, dev), cu(center, dev))
+        lhs, rhs = (Tx.double() * cu(g, dev).double()).sum(), (cu(x, dev).double() * gx.double()).sum()
+        assert abs(float(lhs - rhs)) < 1e-5 * abs(float(lhs))
+
+
 # ------------------------------------------------------------------------------------ fused EI re-measurement
 @pytest.mark.parametrize("kname,B,C,S", [("Gaussian_R2", 4, 3, 48), ("Gaussian_R2", 2, 3, 256), ("Box_R3", 3, 3, 256),
                                          ("Gaussian_R1", 2, 1, 64), ("Gaussian_R3", 1, 3, 128), ("Box_R2", 2, 2, 32),
@@ -372,7 +388,7 @@ def test_randomly_degrade(golden, dev):
 LOSS_CASES = ["deblur_gauss2_proposed", "deblur_box3_proposed", "deblur_gauss2_v1_proposed", "sr2_proposed",
               "sr4_proposed", "sr2_partial_proposed", "deblur_gauss2_sure", "deblur_gauss2_sure_avgcst",
               "deblur_gauss2_sure_nocrop", "deblur_gauss2_supervised", "sr2_css", "deblur_gauss2_proposed_alpha",
-              "cfg1_deblur_gauss2_proposed"]
+              "cfg1_deblur_gauss2_proposed", "deblur_gauss2_r2r", "sr2_r2r", "deblur_gauss2_nostopgrad", "sr2_nostopgrad", "deblur_gauss2_shifts"]
 LOSS_ARGS = {
     "deblur_gauss2_proposed": dict(), "deblur_box3_proposed": dict(kernel="Box_R3"),
     "deblur_gauss2_v1_proposed": dict(physics_v2=False),
@@ -383,6 +399,11 @@ LOSS_ARGS = {
     "deblur_gauss2_supervised": dict(method="supervised"), "sr2_css": dict(task="sr", kernel=None, sr_factor=2, method="css"),
     "deblur_gauss2_proposed_alpha": dict(ProposedLoss__alpha_tradeoff=0.3),
     "cfg1_deblur_gauss2_proposed": dict(),
+    "deblur_gauss2_r2r": dict(ProposedLoss__sure_alternative="r2r"),
+    "sr2_r2r": dict(task="sr", kernel=None, sr_factor=2, ProposedLoss__sure_alternative="r2r"),
+    "deblur_gauss2_nostopgrad": dict(ProposedLoss__stop_gradient=False),
+    "sr2_nostopgrad": dict(task="sr", kernel=None, sr_factor=2, ProposedLoss__stop_gradient=False),
+    "deblur_gauss2_shifts": dict(ProposedLoss__transforms="Shifts"),
 }
 
 

@@ -186,3 +186,47 @@ def test_noise_and_degrade(golden):
     assert rel_err(y, g["deblur_y"]) < TOL32
     y = orc.add_noise(orc.down_aa(g["sr2_x"], 2), g["sr2_draw0_randn_like"], float(g["sr2_sigma"]))
     assert rel_err(y, g["sr2_y"]) < TOL32
+
+
+@pytest.mark.parametrize("name,task,kname,rate", [("deblur_gauss2_r2r", "deblurring", "Gaussian_R2", 1), ("sr2_r2r", "sr", None, 2)])
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_r2r_loss(golden, name, task, kname, rate, tag):
+    g = golden(f"loss_{name}_{tag}")
+    phys = orc.OraclePhysics(task, kernel=orc.named_kernel(kname) if kname else None, rate=rate)
+    draws = dict(pert=g["draw0_randn_like"], eps1=g["draw1_randn_like"], u_rate=g["draw2_rand"], u_center=g["draw3_rand"],
+                 eps2=g["draw4_randn_like"])
+    out = orc.r2r_ei_loss(phys, _toy_model_np(g, rate), g["y"], draws, eta=5 / 255)
+    tol = 1e-10 if tag == "f64" else 2e-5
+    assert abs(out["loss"] - float(g["loss"])) <= tol * abs(float(g["loss"]))
+    etol = TOL64 if tag == "f64" else 5e-6
+    for ours, ref in ((out["out0"], "model_out0"), (out["x1"], "model_out1"), (out["x3"], "model_out2")):
+        assert rel_err(ours, g[ref]) < etol
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_scale_transform_vjp_through_no_stop_gradient_loss(golden, tag):
+    """dL/dx_net of the proposed loss with stop_gradient off contains T^T: pins orc.scale_transform_vjp"""
+    g = golden(f"loss_deblur_gauss2_nostopgrad_{tag}")
+    dt = g["y"].dtype.type
+    kern = orc.named_kernel("Gaussian_R2")
+    phys = orc.OraclePhysics("deblurring", kernel=kern, sigma=float(np.float32(5 / 255)))
+    fwd, _ = orc.pointwise_model(g["param_w"], g["param_c"], 1)
+    y, m = g["y"], 6
+    b = np.zeros_like(y)
+    b[:, :, m:-m, m:-m] = g["draw0_randn"]
+    draws = dict(b=b, u_rate=g["draw1_rand"], u_center=g["draw2_rand"], noise=g["draw3_randn_like"])
+    out = orc.proposed_loss(phys, fwd, y, draws, m)
+    assert abs(out["loss"] - float(g["loss"])) <= (1e-10 if tag == "f64" else 2e-5) * abs(float(g["loss"]))
+    B, C, H, W = y.shape
+    n_int = B * C * (H - 2 * m) * (W - 2 * m)
+    mask = np.zeros_like(y)
+    mask[:, :, m:-m, m:-m] = 1
+    g_y2 = dt(2 * (5 / 255) ** 2 / (1e-2 * n_int)) * b * mask
+    g_y1 = dt(2.0 / n_int) * (out["y1"] - y) * mask - g_y2
+    g_x3 = dt(2.0 / out["x3"].size) * (out["x3"] - out["x2"])
+    rate, center = orc.sample_params_from_uniforms(draws["u_rate"], draws["u_center"])
+    g_x2 = phys.A_vjp(fwd.input_vjp(out["y_ei"], g_x3)) - g_x3          # through physics(x2) -> model, and the target
+    g_xnet = phys.A_vjp(g_y1) + orc.scale_transform_vjp(g_x2, rate, center)
+    tol = 1e-9 if tag == "f64" else 2e-5
+    assert rel_err(g_xnet, g["model_out0_grad"]) < tol
+    assert rel_err(g_x3, g["model_out2_grad"]) < tol
