@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace sei {
 
@@ -83,6 +84,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// bulk tensor store shared -> global through a tensor map (clipped at the matrix edge), tracked by bulk groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor of a K-major bf16 tile stored by TMA with SWIZZLE_128B:
@@ -110,11 +122,13 @@ struct GemmParams {
     int M, N, K, ldd;
     int kb_per_split;    // k-blocks per grid.z slice (split-K: fp32 output only, slices accumulate with atomics)
     int splits;
+    int tma_store;       // bf16 output staged through shared memory and written with bulk tensor stores
 };
 
+// first version: one output tile per CTA (kept for A/B measurements: SEI_GEMM_V1=1)
 template <int BN, int STAGES, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+gemm_bf16_tn_kernel_v1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ GemmParams p)
 {
     constexpr int BM = kGemmBM, BK = kGemmBK;
@@ -245,6 +259,220 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// epilogue of one 32-column chunk held in registers: bias, convert, store (masked at the matrix edge)
+template <bool OUT_F32>
+__device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, int col0, bool add_bias)
+{
+    if (row >= p.M || col0 >= p.N) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias && add_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+    if (OUT_F32 && p.splits > 1) {
+        float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+    } else if (OUT_F32) {
+        float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+        if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
+        }
+    } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+        if (col0 + 32 <= p.N && (p.ldd & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                               t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+}
+
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the work items (output tile x K-split), m fastest so that the
+// CTAs running together share the B (weight) tile through L2.  The shared-memory ring and its mbarrier phases
+// run continuously across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue
+// warps drain tile i (tcgen05.ld -> bias -> store) while the MMA thread is already accumulating tile i+1.
+template <int BN, int STAGES, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
+{
+    constexpr int BM = kGemmBM, BK = kGemmBK;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;               // two accumulator stages; 64..512, a power of two
+    constexpr uint32_t SLAB_BYTES = 32 * 128;            // epilogue staging: 32 rows x 64 bf16 per warp and buffer
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B tiles: 1024-byte aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int nk_total = (p.K + BK - 1) / BK;
+    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const long long total = tiles_mn * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 128);           // every epilogue thread arrives
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+                const int split = (int)(w / tiles_mn);
+                const long long rem = w - split * tiles_mn;
+                const int m0 = (int)(rem % tiles_m) * BM, n0 = (int)(rem / tiles_m) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
+                    tma_load_2d(a_dst, &map_a, (kb0 + kb) * BK, m0, &full_bar[s]);
+                    tma_load_2d(a_dst + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            uint32_t it = 0, tcount = 0;
+            for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
+                const int split = (int)(w / tiles_mn);
+                const int kb0 = split * p.kb_per_split;
+                const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
+                const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+                if (tcount >= 2) mbar_wait(&tmem_empty_bar[acc], (acc_use - 1) & 1);     // epilogue drained this stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)       // +32 B along K inside the swizzle row = +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);              // frees the stage when these MMAs have read it
+                }
+                umma_commit(&tmem_full_bar[acc]);            // accumulator stage complete
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        uint32_t tcount = 0, chunk_count = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
+            const int split = (int)(w / tiles_mn);
+            const long long rem = w - split * tiles_mn;
+            const int m0 = (int)(rem % tiles_m) * BM, n0 = (int)(rem / tiles_m) * BN;
+            const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            mbar_wait(&tmem_full_bar[acc], acc_use & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            if (!OUT_F32 && p.tma_store && BN >= 64) {
+                // coalesced path: each warp converts its 32 x 64 sub-tile to bf16, writes it to its own SWIZZLE_128B
+                // staging slab (16-byte chunk j of row r at position j ^ (r & 7): conflict-free) and one lane hands
+                // the slab to the TMA engine; two slabs per warp so the next chunk is staged while the store drains
+                unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * 2 * SLAB_BYTES;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
+                    tmem_ld_wait();
+                    unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;   // alternates across tiles too
+                    if (lane == 0) bulk_wait_read<1>();      // the store that last read this slab has finished reading
+                    __syncwarp();
+                    const int col0 = n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {            // 8 chunks of 8 bf16
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int cc = 8 * j + e;
+                            v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
+                            if (p.bias && split == 0 && col0 + cc < p.N) v[e] += __ldg(p.bias + col0 + cc);
+                        }
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
+                                       t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+                    }
+                    fence_proxy_async();                     // generic-proxy writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
+                        tma_store_2d(&map_d, slab, col0, m0 + q * 32);
+                        bulk_commit();
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r);
+                    tmem_ld_wait();
+                    gemm_store_chunk<OUT_F32>(p, r, row, n0 + c, split == 0);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);               // this thread is done reading the accumulator stage
+        }
+    }
+    if (!OUT_F32 && p.tma_store && warp >= 2 && lane == 0) bulk_wait_all();   // outstanding stores still read shared memory
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -267,6 +495,7 @@ static EncodeTiledFn get_encode_fn()
 // 2-D bf16 row-major matrix [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows rows, SWIZZLE_128B
 static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows)
 {
+    // box = 64 columns (128 B, the swizzle span) x box_rows rows
     EncodeTiledFn fn = get_encode_fn();
     SEI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -281,16 +510,30 @@ static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, lon
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, bool out_f32, cudaStream_t st)
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p, bool out_f32,
+                       int sm_count, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024;
-    dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN, p.splits);
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
+    const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
+    const char* v1 = getenv("SEI_GEMM_V1");
+    if (v1 && *v1 == '1') {
+        dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN, p.splits);
+        if (out_f32) {
+            SEI_CUDA(allow_smem(gemm_bf16_tn_kernel_v1<BN, STAGES, true>, smem));
+            gemm_bf16_tn_kernel_v1<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+        } else {
+            SEI_CUDA(allow_smem(gemm_bf16_tn_kernel_v1<BN, STAGES, false>, smem));
+            gemm_bf16_tn_kernel_v1<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+        }
+        return finish_launch("gemm_bf16_tn_kernel");
+    }
+    const unsigned grid = (unsigned)std::min<long long>(tiles * p.splits, sm_count);
     if (out_f32) {
         SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+        gemm_bf16_tn_kernel<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, md, p);
     } else {
         SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
+        gemm_bf16_tn_kernel<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, md, p);
     }
     return finish_launch("gemm_bf16_tn_kernel");
 }
@@ -322,6 +565,14 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd;
+    // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
+    const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
+    p.tma_store = (!out_f32 && bn >= 64 && ldd % 8 == 0 && !(nts && *nts == '1')) ? 1 : 0;
+    CUtensorMap md = ma;
+    if (p.tma_store) {
+        rc = make_map_bf16(&md, D, M, N, ldd, 32);
+        if (rc) return rc;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // split-K for the weight-gradient shapes (few output tiles, very long K = pixels): fp32 output only
     const int nk = (K + kGemmBK - 1) / kGemmBK;
@@ -336,9 +587,9 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
         if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
     }
     switch (bn) {
-    case 32: return launch_gemm<32, 8>(ma, mb, p, out_f32 != 0, st);
-    case 64: return launch_gemm<64, 8>(ma, mb, p, out_f32 != 0, st);
-    case 128: return launch_gemm<128, 6>(ma, mb, p, out_f32 != 0, st);
-    default: return launch_gemm<256, 4>(ma, mb, p, out_f32 != 0, st);
+    case 32: return launch_gemm<32, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 64: return launch_gemm<64, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 128: return launch_gemm<128, 6>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    default: return launch_gemm<256, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
     }
 }

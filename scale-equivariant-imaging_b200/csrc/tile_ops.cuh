@@ -106,49 +106,72 @@ __device__ __forceinline__ void blur_vpass(const float* __restrict__ sIn, float*
 
 // horizontal (circular in x): y[r][n] = sum_t ch[t] * sMid[r][(n + t - P) mod W] (+ sigma * noise)
 // yrow0 / nrow0 point at the first output row of the band in global memory (row pitch W).
+// one horizontal work item: 4 outputs of row r starting at column 4*c4
+template <int K, bool NOISE, bool PAD>
+__device__ __forceinline__ void blur_hpass_item(const float* __restrict__ row, int c4, int CW, const float (&tap)[K],
+                                                float* __restrict__ ydst, const float* __restrict__ ndst, float sigma)
+{
+    using G = BlurGeom<K>;
+    constexpr int P = G::P, LCH = G::LCH, NCH = G::NCH, LEFT = G::LEFT;
+    // issue the noise load first: its DRAM latency hides behind the shared loads and the K*4 FMAs below
+    // (ncu: 22 % of the fused kernel's stall samples sat on the first use of this value)
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NOISE) nz = ld_stream4(ndst);
+    float v[4 * NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        float4 t;
+        if (PAD) {
+            t = *reinterpret_cast<const float4*>(row + (c4 + q) * 4);      // padded column 4*(c4 - LCH + q) + LEFT
+        } else {
+            int cc = c4 - LCH + q;
+            if (cc < 0) cc += CW;
+            if (cc >= CW) cc -= CW;
+            t = *reinterpret_cast<const float4*>(row + cc * 4);
+        }
+        v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) out[o] = fmaf(tap[t], v[LEFT + o + t - P], out[o]);
+    }
+    if (NOISE) {
+        out[0] = fmaf(sigma, nz.x, out[0]); out[1] = fmaf(sigma, nz.y, out[1]);
+        out[2] = fmaf(sigma, nz.z, out[2]); out[3] = fmaf(sigma, nz.w, out[3]);
+    }
+    st_stream4(ydst, make_float4(out[0], out[1], out[2], out[3]));
+}
+
+// horizontal (circular in x): y[r][n] = sum_t ch[t] * sMid[r][(n + t - P) mod W] (+ sigma * noise)
+// yrow0 / nrow0 point at the first output row of the band in global memory (row pitch W).
+// The taps are pulled into registers once per call (the constant-bank loads showed up as 17 % of the stall
+// samples), and two independent work items are in flight per thread so one item's shared loads overlap the
+// other's FMA chain.
 template <int K, int NT, bool NOISE, int WT = 0, bool PAD = false>
 __device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int Wrt, int th, const float* __restrict__ ch,
                                            float* __restrict__ yrow0, const float* __restrict__ nrow0, float sigma)
 {
-    using G = BlurGeom<K>;
-    constexpr int P = G::P, LCH = G::LCH, NCH = G::NCH, LEFT = G::LEFT;
     const int W = WT ? WT : Wrt;
     const int CW = W >> 2;
     const int pitch = blur_mid_pitch<K, PAD>(W);
-    for (int item = threadIdx.x; item < th * CW; item += NT) {
-        const int r = item / CW, c4 = item - r * CW;
-        const float* row = sMid + r * pitch;
-        const int g = r * W + c4 * 4;
-        // issue the noise load first: its DRAM latency hides behind the shared loads and the K*4 FMAs below
-        // (ncu: 22 % of the fused kernel's stall samples sat on the first use of this value)
-        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (NOISE) nz = ld_stream4(nrow0 + g);
-        float v[4 * NCH];
+    float tap[K];
 #pragma unroll
-        for (int q = 0; q < NCH; ++q) {
-            float4 t;
-            if (PAD) {
-                t = *reinterpret_cast<const float4*>(row + (c4 + q) * 4);      // padded column 4*(c4 - LCH + q) + LEFT
-            } else {
-                int cc = c4 - LCH + q;
-                if (cc < 0) cc += CW;
-                if (cc >= CW) cc -= CW;
-                t = *reinterpret_cast<const float4*>(row + cc * 4);
-            }
-            v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-        float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int t = 0; t < K; ++t) {
-            const float c = ch[t];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) out[o] = fmaf(c, v[LEFT + o + t - P], out[o]);
-        }
-        if (NOISE) {
-            out[0] = fmaf(sigma, nz.x, out[0]); out[1] = fmaf(sigma, nz.y, out[1]);
-            out[2] = fmaf(sigma, nz.z, out[2]); out[3] = fmaf(sigma, nz.w, out[3]);
-        }
-        st_stream4(yrow0 + g, make_float4(out[0], out[1], out[2], out[3]));
+    for (int t = 0; t < K; ++t) asm volatile("mov.f32 %0, %1;" : "=f"(tap[t]) : "f"(ch[t]));
+    const int nitems = th * CW;
+    int item = threadIdx.x;
+    for (; item + NT < nitems; item += 2 * NT) {
+        const int r0 = item / CW, c0 = item - r0 * CW;
+        const int r1 = (item + NT) / CW, c1 = (item + NT) - r1 * CW;
+        const int g0 = r0 * W + c0 * 4, g1 = r1 * W + c1 * 4;
+        blur_hpass_item<K, NOISE, PAD>(sMid + r0 * pitch, c0, CW, tap, yrow0 + g0, NOISE ? nrow0 + g0 : nullptr, sigma);
+        blur_hpass_item<K, NOISE, PAD>(sMid + r1 * pitch, c1, CW, tap, yrow0 + g1, NOISE ? nrow0 + g1 : nullptr, sigma);
+    }
+    if (item < nitems) {
+        const int r0 = item / CW, c0 = item - r0 * CW;
+        const int g0 = r0 * W + c0 * 4;
+        blur_hpass_item<K, NOISE, PAD>(sMid + r0 * pitch, c0, CW, tap, yrow0 + g0, NOISE ? nrow0 + g0 : nullptr, sigma);
     }
 }
 
