@@ -351,6 +351,7 @@ def cpu_network(args):
     import models.convolutional as mc
     mc.COMPUTE_DTYPE = torch.float32
     mc._gemm_tn = lambda a, b, bias, out_dtype: (a @ b.t() + (bias if bias is not None else 0)).to(out_dtype)
+    mc._gemm_atb = lambda a, b: (a.t() @ b).float()
     torch.manual_seed(0)
     return models.get_model(model_args(args.cnn_hidden, args.cnn_scales), physics=None, device="cpu")
 

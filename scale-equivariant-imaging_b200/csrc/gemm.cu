@@ -110,10 +110,26 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr)
     return d;
 }
 
-// instruction descriptor: dense, D = f32, A = B = bf16, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+// shared-memory matrix descriptor of an MN-major bf16 tile (the contraction index is the ROW of the global matrix):
+// TMA boxes of 64 MN-elements x BK k-rows, SWIZZLE_128B.  Canonical layout (CUTLASS make_umma_desc<Major::MN>, in
+// 16-byte units): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -- 64 MN-elements contiguous, k-rows 128 B apart, 8-row groups
+// SBO = 1024 B apart, successive 64-element MN blocks LBO = box bytes apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_block_bytes)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFFu) << 16;     // leading byte offset: next 64-element MN block
+    d |= (uint64_t)(1024u >> 4) << 32;                            // stride byte offset: next group of 8 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: dense, D = f32, A = B = bf16, M = 128, N = BN; mn_major: both operands MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool mn_major = false)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (1u << 15) | (1u << 16) : 0u) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct GemmParams {
@@ -312,7 +328,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
 // CTAs running together share the B (weight) tile through L2.  The shared-memory ring and its mbarrier phases
 // run continuously across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue
 // warps drain tile i (tcgen05.ld -> bias -> store) while the MMA thread is already accumulating tile i+1.
-template <int BN, int STAGES, bool OUT_F32>
+// MN = false: A[M,K], B[N,K] row-major (K contiguous).  MN = true: A[K,M], B[K,N] row-major (the contraction index is
+// the row: D = A^T B), used by the weight gradient so that gy and x are read in place (no transposed copies).
+template <int BN, int STAGES, bool OUT_F32, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
@@ -370,15 +388,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
-                    tma_load_2d(a_dst, &map_a, (kb0 + kb) * BK, m0, &full_bar[s]);
-                    tma_load_2d(a_dst + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full_bar[s]);
+                    if (MN) {
+                        // boxes of 64 MN-elements x BK k-rows (8 KB each), one per 64-element MN block
+#pragma unroll
+                        for (int mb = 0; mb < BM / 64; ++mb)
+                            tma_load_2d(a_dst + mb * (BK * 128), &map_a, m0 + 64 * mb, (kb0 + kb) * BK, &full_bar[s]);
+#pragma unroll
+                        for (int nb = 0; nb < BN / 64; ++nb)
+                            tma_load_2d(a_dst + A_BYTES + nb * (BK * 128), &map_b, n0 + 64 * nb, (kb0 + kb) * BK, &full_bar[s]);
+                    } else {
+                        tma_load_2d(a_dst, &map_a, (kb0 + kb) * BK, m0, &full_bar[s]);
+                        tma_load_2d(a_dst + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full_bar[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MN);
             uint32_t it = 0, tcount = 0;
             for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
                 const int split = (int)(w / tiles_mn);
@@ -393,10 +421,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(&full_bar[s], (it / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                    const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+                    if (MN) {
+                        const uint64_t da = umma_smem_desc_mn_sw128(a_addr, BK * 128),
+                                       db = umma_smem_desc_mn_sw128(a_addr + A_BYTES, BK * 128);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)       // +32 B along K inside the swizzle row = +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k)   // 16 k-rows = 2048 B further = +128 in the (addr >> 4) field
+                            umma_bf16(tmem_d, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                    } else {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)   // +32 B along K inside the swizzle row = +2 in the (addr >> 4) field
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[s]);              // frees the stage when these MMAs have read it
                 }
                 umma_commit(&tmem_full_bar[acc]);            // accumulator stage complete
@@ -509,6 +545,33 @@ static int make_map_bf16(CUtensorMap* map, const void* base, long long rows, lon
     return 0;
 }
 
+// MN-major operand [K rows, MN cols] row-major with leading dimension ld: box = 64 MN-elements x BK k-rows
+static int make_map_bf16_mn(CUtensorMap* map, const void* base, long long k_rows, long long mn_cols, long long ld)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    SEI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)kGemmBK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SEI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_mn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int sm_count, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
+    const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
+    const unsigned grid = (unsigned)std::min<long long>(tiles * p.splits, sm_count);
+    SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true, true>, smem));
+    gemm_bf16_tn_kernel<BN, STAGES, true, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, ma, p);
+    return finish_launch("gemm_bf16_mn_kernel");
+}
+
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p, bool out_f32,
                        int sm_count, cudaStream_t st)
@@ -591,5 +654,47 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
     case 64: return launch_gemm<64, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
     case 128: return launch_gemm<128, 6>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
     default: return launch_gemm<256, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    }
+}
+
+
+// D[M, N] (fp32) = A[K, M]^T * B[K, N]: both operands MN-major (the contraction index is the row).  The weight
+// gradient of a pointwise convolution: A = dL/dy (pixels x C_out), B = x (pixels x C_in), D = dL/dW (C_out x C_in).
+extern "C" int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long long K, int M, int N,
+                                 long long lda, long long ldb, void* stream)
+{
+    SEI_REQUIRE(A && B && D, "null pointer argument");
+    SEI_REQUIRE(M > 0 && N > 0 && K > 0 && K < (1ll << 31), "bad shape M=%d N=%d K=%lld", M, N, K);
+    SEI_REQUIRE(lda >= M && ldb >= N, "leading dimensions smaller than the rows");
+    SEI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA row pitch)");
+    SEI_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), "A, B, D must be 16-byte aligned");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    SEI_REQUIRE(dp.cc_major == 10, "tcgen05 GEMM needs an sm_100 device");
+    const int bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+    CUtensorMap ma, mb;
+    rc = make_map_bf16_mn(&ma, A, K, M, lda);
+    if (rc) return rc;
+    rc = make_map_bf16_mn(&mb, B, K, N, ldb);
+    if (rc) return rc;
+    GemmParams p;
+    p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
+    const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
+    p.splits = 1;
+    p.kb_per_split = nk;
+    if (tiles < dp.sm_count && nk >= 8) {
+        int want = (int)std::min<long long>((2ll * dp.sm_count + tiles - 1) / tiles, nk / 4);
+        want = std::max(1, std::min(want, 512));
+        p.kb_per_split = (nk + want - 1) / want;
+        p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
+        if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+    }
+    switch (bn) {
+    case 64: return launch_gemm_mn<64, 8>(ma, mb, p, dp.sm_count, st);
+    case 128: return launch_gemm_mn<128, 6>(ma, mb, p, dp.sm_count, st);
+    default: return launch_gemm_mn<256, 4>(ma, mb, p, dp.sm_count, st);
     }
 }

@@ -32,13 +32,19 @@ def _gemm_tn(a, b, bias, out_dtype):
     return ops.gemm_bf16_tn(a, b, bias, out_dtype=out_dtype)
 
 
+def _gemm_atb(a, b):
+    """D (fp32) = a^T @ b with both operands read in place (sei_gemm_bf16_atb, MN-major UMMA operands)"""
+    return ops.gemm_bf16_atb(a, b)
+
+
 class _GemmTN(torch.autograd.Function):
     """out[T, N] = x[T, K] @ w[N, K]^T + bias[N]; all three passes on sei_gemm_bf16_tn."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16):
+    def forward(ctx, x, weight, bias, w_bf16, wt_getter):
         ctx.save_for_backward(x, w_bf16)
         ctx.has_bias = bias is not None
+        ctx.wt_getter = wt_getter
         return _gemm_tn(x, w_bf16, bias, COMPUTE_DTYPE)
 
     @staticmethod
@@ -47,12 +53,15 @@ class _GemmTN(torch.autograd.Function):
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = _gemm_tn(_pad_k(gy), _pad_k(w_bf16.t()), None, COMPUTE_DTYPE)                                  # gy[T,N] @ w[N,K]
+            gx = _gemm_tn(_pad_k(gy), ctx.wt_getter(), None, COMPUTE_DTYPE)          # dgrad: gy[T,N] @ w[N,K]
         if ctx.needs_input_grad[1]:
-            gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)                          # gy^T[N,T] @ x[T,K]
+            if gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0:
+                gw = _gemm_atb(gy, x)                                                # wgrad: gy[T,N]^T @ x[T,K], in place
+            else:                                                                    # 3-channel edges of the network
+                gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.float().sum(0)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 def _pad_k(a):
@@ -77,7 +86,15 @@ class _GemmConv2d(Conv2d):
             with torch.no_grad():
                 self._w_cache = _pad_k(w2.detach().to(COMPUTE_DTYPE))
             self._w_key = key
+            self._wt_cache = None
         return w2, self._w_cache
+
+    def _weight_matrix_t(self):
+        """(K, N) copy of the low-precision weight for dgrad, made once per weight version"""
+        if getattr(self, "_wt_cache", None) is None:
+            with torch.no_grad():
+                self._wt_cache = _pad_k(self._w_cache.t())
+        return self._wt_cache
 
     def forward(self, x):
         B, C, H, W = x.shape
@@ -89,7 +106,7 @@ class _GemmConv2d(Conv2d):
         if x2.shape[1] != w_bf16.shape[1]:
             x2 = F.pad(x2, (0, w_bf16.shape[1] - x2.shape[1]))
         w2p = w2 if w2.shape[1] == w_bf16.shape[1] else F.pad(w2, (0, w_bf16.shape[1] - w2.shape[1]))
-        out = _GemmTN.apply(x2, w2p, self.bias, w_bf16)
+        out = _GemmTN.apply(x2, w2p, self.bias, w_bf16, self._weight_matrix_t)
         return out.view(B, H, W, -1).permute(0, 3, 1, 2)                        # logical NCHW, channels-last memory
 
 

@@ -67,6 +67,20 @@ def test_gemm_split_k_weight_gradient_shapes(dev):
         assert float((d - ref - bias).abs().max() / ref.abs().max()) < 5e-5, (M, N, K)
 
 
+@pytest.mark.parametrize("K,M,N", [(4096, 128, 64), (65536, 128, 32), (10000, 512, 128), (2048, 2048, 512), (777, 136, 72),
+                                   (8192, 256, 1024)])
+def test_gemm_atb_mn_major(dev, K, M, N):
+    """D = A^T B with both operands read in place (MN-major UMMA descriptors): the weight-gradient shape"""
+    from sei_b200 import ops, last_kernel
+    torch.manual_seed(K + M + N)
+    a = torch.randn(K, M, device=dev).bfloat16()
+    b = torch.randn(K, N, device=dev).bfloat16()
+    ref = a.float().t() @ b.float()
+    d = ops.gemm_bf16_atb(a, b)
+    assert last_kernel() == "gemm_bf16_mn_kernel"
+    assert float((d - ref).abs().max() / ref.abs().max()) < 5e-5, float((d - ref).abs().max() / ref.abs().max())
+
+
 def test_gemm_throughput_smoke(dev):
     """not a benchmark: just exercises a deep-K, many-tile launch (scale-4 ConvBlock shape) for hangs"""
     from sei_b200 import ops

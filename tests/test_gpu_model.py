@@ -65,6 +65,7 @@ def test_cnn_forward_backward_bf16(golden, dev, name, monkeypatch):
     # (b) same precision, library matmul (fp32 accumulate, bf16 / fp32 output like the kernel)
     monkeypatch.setattr(mc, "_gemm_tn", lambda a, b, bias, out_dtype:
                         (a.float() @ b.float().t() + (bias if bias is not None else 0)).to(out_dtype))
+    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b: a.float().t() @ b.float())
     _, model_b = _load(golden, f"model_{name}", dev)
     out_b = model_b(y)
     (out_b * gout).sum().backward()
