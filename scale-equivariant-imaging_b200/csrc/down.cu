@@ -41,19 +41,28 @@ struct BorderTab {      // weights of the 4 border outputs of one axis: indices 
     int xsize[4];
 };
 
+// forward kernel parameters: border tables are computed on the host once per launch (the first version computed them
+// in 8 threads of every CTA while the other 248 waited at a barrier: 35 % of its stall samples)
+struct DownFwdParams {
+    DownParams d;
+    BorderTab colTab, rowTab;
+};
+
 __device__ __forceinline__ int border_slot(int i, int n) { return i < 2 ? i : (i >= n - 2 ? i - (n - 4) : -1); }
 
 // WT: compile-time INPUT width (0 = run time).  Interior outputs (all but the first / last two of an axis) use the
 // fixed polyphase taps from the constant bank in branch-free loops; the few border outputs are handled by separate
 // small loops with per-CTA weight tables, so no warp ever executes both paths (the first version did, in every warp).
 template <int R, int WT>
-__global__ void __launch_bounds__(kDownThreads) down_band_kernel(const __grid_constant__ DownParams p)
+__global__ void __launch_bounds__(kDownThreads) down_band_kernel(const __grid_constant__ DownFwdParams fp)
 {
     constexpr int T = 4 * R, OFF = aa_off(R);
     constexpr int NT = kDownThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
-    __shared__ BorderTab colTab, rowTab;
+    const DownParams& p = fp.d;
+    const BorderTab& colTab = fp.colTab;
+    const BorderTab& rowTab = fp.rowTab;
 
     const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R, CW = Wo >> 2;
     const int band = blockIdx.x % p.nbands;
@@ -75,14 +84,6 @@ __global__ void __launch_bounds__(kDownThreads) down_band_kernel(const __grid_co
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_fence_init();
-    }
-    if (threadIdx.x >= 32 && threadIdx.x < 36) {
-        const int k = threadIdx.x - 32;
-        aa_axis_weights(k < 2 ? k : Wo - 4 + k, W, R, colTab.w[k], colTab.xmin[k], colTab.xsize[k]);
-    }
-    if (threadIdx.x >= 64 && threadIdx.x < 68) {
-        const int k = threadIdx.x - 64;
-        aa_axis_weights(k < 2 ? k : Ho - 4 + k, H, R, rowTab.w[k], rowTab.xmin[k], rowTab.xsize[k]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -192,7 +193,7 @@ struct Contrib {
     float w[kNQ];
 };
 
-__device__ __forceinline__ void aa_contributors(int m, int in_size, int out_size, int rate, Contrib& c)
+SEI_HD void aa_contributors(int m, int in_size, int out_size, int rate, Contrib& c)
 {
     const int off = aa_off(rate);
     const int ic = (m + off) / rate;
@@ -220,20 +221,27 @@ __device__ __forceinline__ void aa_contributors(int m, int in_size, int out_size
     }
 }
 
-constexpr int kBorderCols = 32;   // per side, >= 5*rate - off + slack
+constexpr int kBorderCols = 20;   // border columns per side handled through contributor tables
+constexpr int kBorderRows = 16;   // border rows per side
+
+// transpose kernel parameters: contributor tables of the border rows / columns, computed on the host
+struct DownTParams {
+    DownParams d;
+    Contrib colL[kBorderCols], colR[kBorderCols], rowLo[kBorderRows], rowHi[kBorderRows];
+};
 
 // gx = A^T gy.  Interior rows / columns of gx receive exactly four outputs each, (m+OFF)/R - q with tap
 // (m+OFF)%R + R*q, q = 0..3 (a 4-tap polyphase upsampler); rows / columns near the border go through
 // contributor tables.  Interior and border are separate loops (no divergent warps).
 template <int R, int WT>
-__global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_constant__ DownParams p)
+__global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_constant__ DownTParams tp)
 {
     constexpr int OFF = aa_off(R);
     constexpr int NT = kDownThreads;
     constexpr bool kStaticPhase = (4 % R) == 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    __shared__ Contrib colL[kBorderCols], colR[kBorderCols];
+    const DownParams& p = tp.d;
 
     const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R, CWo = Wo >> 2;
     const int band = blockIdx.x % p.nbands;
@@ -247,7 +255,6 @@ __global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_
 
     float* sG = reinterpret_cast<float*>(smem_raw);             // [GR][Wo]
     float* sTmp = sG + GR * Wo;                                  // [TH][Wo]
-    Contrib* rowC = reinterpret_cast<Contrib*>(sTmp + p.TH * Wo);   // [TH] (used by border rows only)
 
     const int NL = min(W, 5 * R - OFF);                          // columns [0, NL) are border
     const int NR0 = max(NL, R * (Wo - 2) - OFF);                 // columns [NR0, W) are border
@@ -266,14 +273,6 @@ __global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_
                                 reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * Ho * Wo), Ho, row_bytes,
                                 g_lo, ng, &bar);
     }
-    // contributor tables of the border rows of this band and of the border columns (overlaps the copy)
-    for (int t = threadIdx.x; t < th; t += NT) {
-        const int m = m0 + t;
-        if (m < ML || m >= MR0) aa_contributors(m, H, Ho, R, rowC[t]);
-    }
-    for (int t = threadIdx.x; t < 4 * n4_lo; t += NT) aa_contributors(t, W, Wo, R, colL[t]);
-    for (int t = threadIdx.x; t < W - 4 * n4_hi; t += NT) aa_contributors(4 * n4_hi + t, W, Wo, R, colR[t]);
-    __syncthreads();
     if (ng > 0) mbar_wait(&bar, 0);
 
     // ---- vertical pass: sTmp[m][j] = sum_q w_q * gy[i_q][j]   (rows are warp-uniform)
@@ -292,7 +291,7 @@ __global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_
                 acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
             }
         } else {
-            const Contrib& c = rowC[r];
+            const Contrib& c = m < ML ? tp.rowLo[m] : tp.rowHi[m - MR0];
 #pragma unroll
             for (int q = 0; q < kNQ; ++q) {
                 const float w = c.w[q];
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_
     for (int item = threadIdx.x; item < th * (nbl + nbr); item += NT) {
         const int r = item / (nbl + nbr), e = item - r * (nbl + nbr);
         const int n = e < nbl ? e : 4 * n4_hi + (e - nbl);
-        const Contrib& c = e < nbl ? colL[e] : colR[e - nbl];
+        const Contrib& c = e < nbl ? tp.colL[e] : tp.colR[e - nbl];
         const float* row = sTmp + r * Wo;
         float a = 0.f;
 #pragma unroll
@@ -461,13 +460,29 @@ template <int R, int WT>
 static int launch_down_w(const DownParams& p, long long planes, size_t smem, cudaStream_t st, bool transpose)
 {
     const unsigned grid = (unsigned)(planes * p.nbands);
+    constexpr int OFF = aa_off(R);
     if (transpose) {
+        DownTParams tp;
+        tp.d = p;
+        const int NL = std::min(p.W, 5 * R - OFF), NR0 = std::max(NL, R * (p.Wo - 2) - OFF);
+        const int ML = std::min(p.H, 5 * R - OFF), MR0 = std::max(ML, R * (p.Ho - 2) - OFF);
+        const int n4_lo = (NL + 3) / 4, n4_hi = std::max(n4_lo, NR0 / 4);
+        for (int t = 0; t < 4 * n4_lo; ++t) aa_contributors(t, p.W, p.Wo, R, tp.colL[t]);
+        for (int t = 0; t < p.W - 4 * n4_hi; ++t) aa_contributors(4 * n4_hi + t, p.W, p.Wo, R, tp.colR[t]);
+        for (int m = 0; m < ML; ++m) aa_contributors(m, p.H, p.Ho, R, tp.rowLo[m]);
+        for (int m = MR0; m < p.H; ++m) aa_contributors(m, p.H, p.Ho, R, tp.rowHi[m - MR0]);
         SEI_CUDA(allow_smem(down_t_band_kernel<R, WT>, smem));
-        down_t_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(p);
+        down_t_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(tp);
         return finish_launch("down_t_band_kernel");
     }
+    DownFwdParams fp;
+    fp.d = p;
+    for (int k = 0; k < 4; ++k) {
+        aa_axis_weights(k < 2 ? k : p.Wo - 4 + k, p.W, R, fp.colTab.w[k], fp.colTab.xmin[k], fp.colTab.xsize[k]);
+        aa_axis_weights(k < 2 ? k : p.Ho - 4 + k, p.H, R, fp.rowTab.w[k], fp.rowTab.xmin[k], fp.rowTab.xsize[k]);
+    }
     SEI_CUDA(allow_smem(down_band_kernel<R, WT>, smem));
-    down_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(p);
+    down_band_kernel<R, WT><<<grid, kDownThreads, smem, st>>>(fp);
     return finish_launch(p.noise ? "down_band_kernel<noise>" : "down_band_kernel");
 }
 
@@ -518,18 +533,20 @@ static int down_common(const float* in, float* out, long long planes, int H, int
             int best = 0;
             const int th_max = getenv("SEI_DOWNT_TH") ? atoi(getenv("SEI_DOWNT_TH")) : 32;
             for (int th = 8; th <= th_max; th += 8) {
-                const size_t need = ((size_t)(th / rate + 8) * Wo + (size_t)th * Wo) * 4 + (size_t)th * sizeof(Contrib);
+                const size_t need = ((size_t)(th / rate + 8) * Wo + (size_t)th * Wo) * 4;
                 if (need <= budget) best = th;
             }
             p.TH = std::min(best, ((H + 7) / 8) * 8);
             p.CH = 0;
             p.nbands = p.TH ? (H + p.TH - 1) / p.TH : 0;
-            smem = ((size_t)(p.TH / rate + 8) * Wo + (size_t)p.TH * Wo) * 4 + (size_t)p.TH * sizeof(Contrib);
+            smem = ((size_t)(p.TH / rate + 8) * Wo + (size_t)p.TH * Wo) * 4;
             // border-column tables hold kBorderCols entries per side
             // border-column tables hold kBorderCols entries per side (columns outside the interior float4 groups)
             const int NL = 5 * rate - aa_off(rate), NR0 = std::max(NL, rate * (Wo - 2) - aa_off(rate));
             const int n4_lo = (NL + 3) / 4, n4_hi = std::max(n4_lo, NR0 / 4);
-            tiled_ok = tiled_ok && 4 * n4_lo <= kBorderCols && (W - 4 * n4_hi) <= kBorderCols;
+            const int ML = std::min(H, NL), MR0 = std::max(ML, rate * (Ho - 2) - aa_off(rate));
+            tiled_ok = tiled_ok && 4 * n4_lo <= kBorderCols && (W - 4 * n4_hi) <= kBorderCols && ML <= kBorderRows &&
+                       (H - MR0) <= kBorderRows;
         }
         tiled_ok = tiled_ok && p.TH > 0 && planes * p.nbands < (1ll << 31);
     }

@@ -45,7 +45,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <class K>
 inline cudaError_t allow_smem(K kernel, size_t bytes)
 {
-    if (bytes <= 48 * 1024) return cudaSuccess;
+    if (bytes <= 40 * 1024) return cudaSuccess;     // static shared memory counts against the 48 KB default as well
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
