@@ -332,7 +332,7 @@ def run_b200(args):
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "imgs/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": int(2 * xs[0].numel() * 4), "d2h_bytes_per_step": 4,
                 "how": "losses.get_loss(...)(x, y, model) + backward + Adam from pinned host x,y; loss.item() each step"},
-        "gpu_launches": int(launches_per_step * args.steps * 2),
+        "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clock_summary, "roofline": roofline, "roofline_operators": roofline_ops, "cpu_baseline": cpu_baseline,
         "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),

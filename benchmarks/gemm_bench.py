@@ -26,6 +26,7 @@ def bench(fn, reps=10, warmup=3):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     dev = torch.device("cuda:0")
     peak = 1685.6
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -41,6 +42,8 @@ def main():
     print(f"| layer | M | N | K | sei us | sei TFLOP/s | frac of {peak} | cuBLAS us | cuBLAS TFLOP/s |")
     print("|---|---|---|---|---|---|---|---|---|")
     for name, M, N, K in shapes:
+        if only and only not in name:
+            continue
         if M * K * 2 > 8e9 or M * N * 2 > 8e9:
             M = M // 4
             name += " (M/4)"

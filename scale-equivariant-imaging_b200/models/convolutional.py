@@ -60,7 +60,7 @@ class _GemmTN(torch.autograd.Function):
             else:                                                                    # 3-channel edges of the network
                 gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.float().sum(0)
+            gb = torch.sum(gy, 0, dtype=torch.float32)      # one pass, fp32 accumulation, no fp32 copy of gy
         return gx, gw, gb, None, None
 
 
