@@ -180,6 +180,22 @@ int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, l
 int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long long K, int M, int N,
                       long long lda, long long ldb, void* stream);
 
+/* Batched operator product  D_b[M, N] = A[M, K] * X_b[K, N]  (bf16, fp32 accumulation, bf16 result), A shared by
+ * all batch entries and resident in shared memory, X streamed once.  Replaces the rfft2 / fftshift / mask or
+ * zero-pad / irfft2 chains of the reference's IdealDownsample / IdealUpsample (src/models/convolutional.py
+ * :54-92,113-133) on channels-last activations: those chains are fixed linear maps, applied here as two such
+ * products (width then height; two terms because the reference shifts the half-spectrum axis).
+ *   A: [ceil(M / tile_rows) * tile_rows][Kpad] row-major, zero padded; Kpad a multiple of 64;
+ *      tile_rows = sei_bgemm_tile_rows(M, Kpad).
+ *   batch entry bt = bo * b_inner + bi starts at X + bo*x_bo + bi*x_bi and D + bo*d_bo + bi*d_bi;
+ *   row k of X_b = ko * k_inner + ki lives at ko*x_ko + ki*x_ki, row m of D_b = mo * m_inner + mi at mo*d_mo + mi*d_mi;
+ *   the N index is contiguous; N and all strides are multiples of 8 elements. */
+int sei_bgemm_tile_rows(int M, int Kpad);
+int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int K, int N, int Kpad, int tile_rows,
+                   long long batches, int b_inner, long long x_bo, long long x_bi,
+                   int k_inner, long long x_ko, long long x_ki,
+                   long long d_bo, long long d_bi, int m_inner, long long d_mo, long long d_mi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

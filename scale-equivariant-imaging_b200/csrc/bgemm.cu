@@ -1,0 +1,282 @@
+// bgemm.cu -- batched "small dense operator x channels-last activation" product, the restoration CNN's ideal
+// (Fourier-domain) resamplers as matrix products (reference: src/models/convolutional.py IdealDownsample
+// :113-133, IdealUpsample :54-92).
+//
+// rfft2 -> fftshift -> mask / zero-pad -> irfft2 (-> stride) is a fixed linear map of the image.  Because the
+// reference shifts the half-spectrum axis as well and discards its ifftshift, the map is not one separable
+// product but the sum of two:  out = Gr X P^T + Gi X Q^T  (models/resample.py derives the four matrices).
+// On channels-last activations both contractions are the same primitive,
+//
+//     D_b[M, N] = A[M, K] * X_b[K, N]        b = 0 .. batches-1,   N contiguous (channels, or width x channels)
+//
+// with A shared by every batch entry (A = [P; Q] over batch = image rows, then A = [Gr | Gi] over batch = images).
+// The primitive is HBM-bound (K <= 512), so the design is: the A block stays resident in shared memory for the
+// life of a persistent CTA, X streams through a 4-stage cp.async ring in 64 x 64 chunks that runs ahead across
+// work items, the products run on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate; ldmatrix fragments
+// from padded, conflict-free rows), and every warp stages its output tile in shared memory to store full
+// 16-byte vectors.  Row indices of X and D may be split (r = ro * inner + ri, two strides) so that the two-term
+// intermediate [B, 2, H, W', C] is written and read in place.
+#include "sei_common.cuh"
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace sei {
+
+constexpr int kBgThreads = 256;
+constexpr int kBgBN = 64;          // output columns per work item
+constexpr int kBgKC = 64;          // X rows per pipeline chunk
+constexpr int kBgStages = 4;
+constexpr int kBgXPitch = kBgBN + 8;   // bf16 elements; 144 B rows: ldmatrix conflict-free
+
+struct BgemmParams {
+    const __nv_bfloat16* A;      // [m_blocks * MT][Kpad], zero padded
+    const __nv_bfloat16* X;
+    __nv_bfloat16* D;
+    int M, K, N, Kpad;
+    int b_inner, k_inner, m_inner, n_tiles;
+    long long items;             // batches * n_tiles
+    long long x_bo, x_bi, x_ko, x_ki;
+    long long d_bo, d_bi, d_mo, d_mi;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
+{
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// MT: rows of A resident per CTA (blockIdx.y selects the block).  Warp grid WM x WN over the MT x 64 tile.
+template <int MT>
+__global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_constant__ BgemmParams p)
+{
+    constexpr int WM = MT >= 128 ? 8 : MT / 16;       // warps along M
+    constexpr int WN = 8 / WM;                         // warps along N
+    constexpr int TM = MT / WM;                        // warp tile rows (32 for MT = 256, else 16)
+    constexpr int TN = kBgBN / WN;                     // warp tile columns (64, 32, 16, 8)
+    constexpr int MI = TM / 16;
+    constexpr int NI = TN / 8;
+    constexpr int DP = TN + 8;                         // staging pitch (bf16)
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int apitch = p.Kpad + 8;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);                           // [MT][Kpad + 8]
+    __nv_bfloat16* sX = sA + (size_t)MT * apitch;                                              // [stages][64][72]
+    __nv_bfloat16* sD = sX + (size_t)kBgStages * kBgKC * kBgXPitch;                            // [8 warps][TM][DP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int m_block = blockIdx.y;
+    const int kch = p.Kpad / kBgKC;
+
+    // ---- resident A block (zero padded on the host: no bounds checks)
+    {
+        const __nv_bfloat16* gA = p.A + (size_t)m_block * MT * p.Kpad;
+        const int vec_per_row = p.Kpad / 8;
+        for (int i = tid; i < MT * vec_per_row; i += kBgThreads) {
+            const int r = i / vec_per_row, v = i - r * vec_per_row;
+            cp_async16(sA + (size_t)r * apitch + v * 8, gA + (size_t)r * p.Kpad + v * 8, true);
+        }
+        cp_async_commit();
+    }
+
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
+    const long long total_chunks = my_items * kch;
+
+    // one pipeline chunk: 64 rows x 64 columns of X (rows beyond K / columns beyond N are zero-filled)
+    auto issue = [&](long long g) {
+        const long long it = g / kch;
+        const int kc = (int)(g - it * kch);
+        const long long item = first + it * stride;
+        const long long bt = item / p.n_tiles;
+        const int nt = (int)(item - bt * p.n_tiles);
+        const long long bo = bt / p.b_inner, bi = bt - bo * p.b_inner;
+        const __nv_bfloat16* xb = p.X + bo * p.x_bo + bi * p.x_bi;
+        __nv_bfloat16* dst = sX + (size_t)(g % kBgStages) * kBgKC * kBgXPitch;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + j * kBgThreads;          // 0 .. 511
+            const int row = idx >> 3, cv = idx & 7;
+            const int k = kc * kBgKC + row, n = nt * kBgBN + cv * 8;
+            const bool valid = k < p.K && n < p.N;
+            const int ko = valid ? k / p.k_inner : 0, ki = valid ? k - ko * p.k_inner : 0;
+            cp_async16(dst + row * kBgXPitch + cv * 8, xb + ko * p.x_ko + ki * p.x_ki + (valid ? n : 0), valid);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < kBgStages - 1; ++s) {
+        if (s < total_chunks) issue(s);
+        cp_async_commit();
+    }
+
+    float acc[MI][NI][4];
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+        for (int b = 0; b < NI; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+    // lane-dependent fragment addresses
+    const int a_row = wm * TM + (lane & 15), a_kofs = (lane >> 4) * 8;
+    const int b_krow = (lane & 15), b_nofs = wn * TN + (lane >> 4) * 8;
+    __nv_bfloat16* myD = sD + (size_t)warp * TM * DP;
+
+    for (long long g = 0; g < total_chunks; ++g) {
+        cp_async_wait<kBgStages - 2>();
+        __syncthreads();
+        if (g + kBgStages - 1 < total_chunks) issue(g + kBgStages - 1);
+        cp_async_commit();
+
+        const long long it = g / kch;
+        const int kc = (int)(g - it * kch);
+        const __nv_bfloat16* xs = sX + (size_t)(g % kBgStages) * kBgKC * kBgXPitch;
+#pragma unroll
+        for (int ks = 0; ks < kBgKC / 16; ++ks) {
+            uint32_t af[MI][4];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+                ldsm_x4(af[a], sA + (size_t)(a_row + a * 16) * apitch + kc * kBgKC + ks * 16 + a_kofs);
+            if constexpr (NI >= 2) {
+#pragma unroll
+                for (int b = 0; b < NI / 2; ++b) {
+                    uint32_t bf[4];
+                    ldsm_x4_trans(bf, xs + (size_t)(ks * 16 + b_krow) * kBgXPitch + b_nofs + b * 16);
+#pragma unroll
+                    for (int a = 0; a < MI; ++a) {
+                        mma_bf16(acc[a][2 * b], af[a], bf[0], bf[1]);
+                        mma_bf16(acc[a][2 * b + 1], af[a], bf[2], bf[3]);
+                    }
+                }
+            } else {
+                // 8-column warp tile: one n8 block; lanes 16-31 point at the same matrices as lanes 0-15
+                uint32_t bf[4];
+                ldsm_x4_trans(bf, xs + (size_t)(ks * 16 + b_krow) * kBgXPitch + wn * TN);
+#pragma unroll
+                for (int a = 0; a < MI; ++a) mma_bf16(acc[a][0], af[a], bf[0], bf[1]);
+            }
+        }
+
+        if (kc == kch - 1) {
+            // ---- epilogue of this work item: fragments -> per-warp staging tile -> 16-byte global stores
+            const long long item = first + it * stride;
+            const long long bt = item / p.n_tiles;
+            const int nt = (int)(item - bt * p.n_tiles);
+            const long long bo = bt / p.b_inner, bi = bt - bo * p.b_inner;
+            __nv_bfloat16* db = p.D + bo * p.d_bo + bi * p.d_bi;
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < NI; ++b) {
+                    const int r = a * 16 + (lane >> 2), c = b * 8 + (lane & 3) * 2;
+                    *reinterpret_cast<__nv_bfloat162*>(myD + r * DP + c) = __floats2bfloat162_rn(acc[a][b][0], acc[a][b][1]);
+                    *reinterpret_cast<__nv_bfloat162*>(myD + (r + 8) * DP + c) = __floats2bfloat162_rn(acc[a][b][2], acc[a][b][3]);
+                    acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+                }
+            __syncwarp();
+            constexpr int VPR = TN / 8;                    // 16-byte vectors per tile row
+            for (int i = lane; i < TM * VPR; i += 32) {
+                const int r = i / VPR, v = i - r * VPR;
+                const int m = m_block * MT + wm * TM + r, n = nt * kBgBN + wn * TN + v * 8;
+                if (m < p.M && n < p.N) {
+                    const int mo = m / p.m_inner, mi = m - mo * p.m_inner;
+                    *reinterpret_cast<uint4*>(db + mo * p.d_mo + mi * p.d_mi + n) =
+                        *reinterpret_cast<const uint4*>(myD + r * DP + v * 8);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+static size_t bgemm_smem(int MT, int Kpad)
+{
+    const int WMc = MT >= 128 ? 8 : MT / 16, TM = MT / WMc, TN = kBgBN / (8 / WMc);
+    return ((size_t)MT * (Kpad + 8) + (size_t)kBgStages * kBgKC * kBgXPitch + (size_t)8 * TM * (TN + 8)) * 2;
+}
+
+template <int MT>
+static int launch_bgemm(const BgemmParams& p, int m_blocks, int sm_count, cudaStream_t st)
+{
+    const size_t smem = bgemm_smem(MT, p.Kpad);
+    SEI_CUDA(allow_smem(bgemm_kernel<MT>, smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)227 * 1024 / (smem + 1024)));
+    const long long per_block = std::max(1, sm_count * ctas_per_sm / m_blocks);
+    dim3 grid((unsigned)std::min<long long>(p.items, per_block), (unsigned)m_blocks);
+    bgemm_kernel<MT><<<grid, kBgThreads, smem, st>>>(p);
+    return finish_launch("bgemm_kernel");
+}
+
+}  // namespace sei
+
+using namespace sei;
+
+// rows of A resident per CTA for an (M, Kpad) operator: the smallest tile that covers M, shrunk until it fits
+extern "C" int sei_bgemm_tile_rows(int M, int Kpad)
+{
+    DeviceProps dp;
+    if (get_device_props(&dp)) return 0;
+    int mt = 16;
+    while (mt < M && mt < 256) mt *= 2;
+    while (mt > 16 && bgemm_smem(mt, Kpad) + 1024 > (size_t)dp.smem_optin) mt /= 2;
+    return bgemm_smem(mt, Kpad) + 1024 <= (size_t)dp.smem_optin ? mt : 0;
+}
+
+extern "C" int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int K, int N, int Kpad, int tile_rows,
+                              long long batches, int b_inner, long long x_bo, long long x_bi,
+                              int k_inner, long long x_ko, long long x_ki,
+                              long long d_bo, long long d_bi, int m_inner, long long d_mo, long long d_mi, void* stream)
+{
+    SEI_REQUIRE(A && X && D, "null pointer argument");
+    SEI_REQUIRE(M > 0 && K > 0 && N > 0 && batches >= 0, "bad shape M=%d K=%d N=%d", M, K, N);
+    SEI_REQUIRE(N % 8 == 0, "N=%d must be a multiple of 8 (16-byte rows)", N);
+    SEI_REQUIRE(Kpad % kBgKC == 0 && Kpad >= K, "Kpad=%d must be a multiple of %d and >= K=%d", Kpad, kBgKC, K);
+    SEI_REQUIRE(b_inner > 0 && k_inner > 0 && m_inner > 0, "inner sizes must be positive");
+    SEI_REQUIRE(aligned16(A) && aligned16(X) && aligned16(D), "operands must be 16-byte aligned");
+    SEI_REQUIRE(((x_bo | x_bi | x_ko | x_ki | d_bo | d_bi | d_mo | d_mi) & 7) == 0, "strides must be multiples of 8 elements");
+    SEI_REQUIRE(tile_rows == sei_bgemm_tile_rows(M, Kpad) && tile_rows > 0, "tile_rows %d does not match this operator", tile_rows);
+    if (batches == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    BgemmParams p;
+    p.A = static_cast<const __nv_bfloat16*>(A);
+    p.X = static_cast<const __nv_bfloat16*>(X);
+    p.D = static_cast<__nv_bfloat16*>(D);
+    p.M = M; p.K = K; p.N = N; p.Kpad = Kpad;
+    p.b_inner = b_inner; p.k_inner = k_inner; p.m_inner = m_inner;
+    p.n_tiles = (N + kBgBN - 1) / kBgBN;
+    p.items = batches * p.n_tiles;
+    p.x_bo = x_bo; p.x_bi = x_bi; p.x_ko = x_ko; p.x_ki = x_ki;
+    p.d_bo = d_bo; p.d_bi = d_bi; p.d_mo = d_mo; p.d_mi = d_mi;
+    const int m_blocks = (M + tile_rows - 1) / tile_rows;
+    switch (tile_rows) {
+    case 256: return launch_bgemm<256>(p, m_blocks, dp.sm_count, st);
+    case 128: return launch_bgemm<128>(p, m_blocks, dp.sm_count, st);
+    case 64: return launch_bgemm<64>(p, m_blocks, dp.sm_count, st);
+    case 32: return launch_bgemm<32>(p, m_blocks, dp.sm_count, st);
+    default: return launch_bgemm<16>(p, m_blocks, dp.sm_count, st);
+    }
+}

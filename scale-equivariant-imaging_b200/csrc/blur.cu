@@ -31,9 +31,12 @@ struct BlurBandParams {
     float ch[kMaxK];
 };
 
-// Persistent, software-pipelined: each CTA walks bands blockIdx.x, blockIdx.x + gridDim.x, ... and keeps
-// two input stages in shared memory, so the bulk copy of band i+1 is in flight while band i is filtered.
-template <int K, bool NOISE, int NT, int WT>
+// Persistent: each CTA walks bands blockIdx.x, blockIdx.x + gridDim.x, ...
+//   NSTAGE = 2: two input stages, the bulk copy of band i+1 is issued before band i is filtered;
+//   NSTAGE = 1: one input stage, the copy of band i+1 is issued as soon as the vertical pass of band i has consumed
+//               the stage, so it overlaps the horizontal pass; the smaller footprint buys one more CTA per SM.
+//   H16: horizontal pass with 16 outputs per work item (tile_ops.cuh), needs W % 16 == 0.
+template <int K, bool NOISE, int NT, int WT, int NSTAGE, bool H16>
 __global__ void __launch_bounds__(NT) blur_band_kernel(const __grid_constant__ BlurBandParams p)
 {
     constexpr int P = K / 2;
@@ -42,8 +45,8 @@ __global__ void __launch_bounds__(NT) blur_band_kernel(const __grid_constant__ B
 
     const int H = p.H, W = WT ? WT : p.W;
     const size_t stage_floats = (size_t)(p.TH + 2 * P) * W;
-    float* sIn = reinterpret_cast<float*>(smem_raw);      // [2][TH + 2P][W]
-    float* sMid = sIn + 2 * stage_floats;                  // [TH][W]
+    float* sIn = reinterpret_cast<float*>(smem_raw);      // [NSTAGE][TH + 2P][W]
+    float* sMid = sIn + NSTAGE * stage_floats;             // [TH][pitch]
     const uint32_t row_bytes = (uint32_t)W * 4u;
     const long long total = p.total_bands;
 
@@ -68,8 +71,8 @@ __global__ void __launch_bounds__(NT) blur_band_kernel(const __grid_constant__ B
 
     int it = 0;
     for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (threadIdx.x == 0 && w + gridDim.x < total) {
+        const int buf = NSTAGE == 2 ? (it & 1) : 0;
+        if (NSTAGE == 2 && threadIdx.x == 0 && w + gridDim.x < total) {
             fence_proxy_async();              // stage buf^1 was read by generic loads in iteration it-1
             issue(w + gridDim.x, buf ^ 1);
         }
@@ -77,12 +80,19 @@ __global__ void __launch_bounds__(NT) blur_band_kernel(const __grid_constant__ B
         const long long plane = w / p.nbands;
         const int r0 = band * p.TH;
         const int th = min(p.TH, H - r0);
-        mbar_wait(&bar[buf], (it >> 1) & 1);
+        mbar_wait(&bar[buf], NSTAGE == 2 ? ((it >> 1) & 1) : (it & 1));
 
         blur_vpass<K, NT, WT, true>(sIn + buf * stage_floats, sMid, W, th, p.cv);
         __syncthreads();
+        if (NSTAGE == 1 && threadIdx.x == 0 && w + gridDim.x < total) {
+            fence_proxy_async();              // the stage was read by generic loads in the vertical pass
+            issue(w + gridDim.x, 0);
+        }
         const size_t row0 = ((size_t)plane * H + r0) * W;
-        blur_hpass<K, NT, NOISE, WT, true>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
+        if (H16)
+            blur_hpass16<K, NT, NOISE, WT, true>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
+        else
+            blur_hpass<K, NT, NOISE, WT, true>(sMid, W, th, p.ch, p.y + row0, NOISE ? p.noise + row0 : nullptr, p.sigma);
         __syncthreads();
     }
 }
@@ -149,59 +159,66 @@ static int env_int(const char* name, int dflt)
     return s && *s ? atoi(s) : dflt;
 }
 
-template <int K, bool NOISE, int WT>
-static int launch_band_w(const BlurBandParams& p, size_t smem, int ctas_per_sm, int sm_count, cudaStream_t st)
+struct BandConfig {
+    int TH, threads, ctas_per_sm, nstage, h16;
+    size_t smem;
+};
+
+template <int K, bool NOISE, int NT, int WT, int NSTAGE, bool H16>
+static int launch_band_inst(const BlurBandParams& p, const BandConfig& c, int sm_count, cudaStream_t st)
 {
-    constexpr int NT = 256;
-    SEI_CUDA(allow_smem(blur_band_kernel<K, NOISE, NT, WT>, smem));
-    const long long want = (long long)sm_count * ctas_per_sm;
+    SEI_CUDA(allow_smem(blur_band_kernel<K, NOISE, NT, WT, NSTAGE, H16>, c.smem));
+    const long long want = (long long)sm_count * c.ctas_per_sm;
     const unsigned grid = (unsigned)std::min<long long>(p.total_bands, want);
-    blur_band_kernel<K, NOISE, NT, WT><<<grid, NT, smem, st>>>(p);
+    blur_band_kernel<K, NOISE, NT, WT, NSTAGE, H16><<<grid, NT, c.smem, st>>>(p);
     return finish_launch(NOISE ? "blur_band_kernel<noise>" : "blur_band_kernel");
+}
+
+// CTA shapes: (128 threads, one stage, 16-wide horizontal items) or (256 threads, two stages, 4-wide items; any
+// W % 4 == 0).  Measured on B200 (profiles/r01_blur_variants.md, 128x3x256x256): the first is faster whenever the
+// kernel is long or the noise epilogue is on (Gaussian_R2 A+noise 61 vs 70 us, Gaussian_R3 57 vs 63 us), the second
+// for short kernels without noise (Box_R3: 38 vs 44 us).
+template <int K, bool NOISE, int WT>
+static int launch_band_w(const BlurBandParams& p, const BandConfig& c, int sm_count, cudaStream_t st)
+{
+    if (c.h16) return launch_band_inst<K, NOISE, 128, WT, 1, true>(p, c, sm_count, st);
+    return launch_band_inst<K, NOISE, 256, WT, 2, false>(p, c, sm_count, st);
 }
 
 // width-specialised instantiations for the benchmark shapes (256: cfg2/cfg4, 512: cfg5), run-time width otherwise
 template <int K>
-static int launch_band(const BlurBandParams& p, size_t smem, int ctas_per_sm, int sm_count, cudaStream_t st)
+static int launch_band(const BlurBandParams& p, const BandConfig& c, int sm_count, cudaStream_t st)
 {
-    const bool spec = env_int("SEI_BLUR_NOSPEC", 0) == 0;
-    if (spec && p.W == 256)
-        return p.noise ? launch_band_w<K, true, 256>(p, smem, ctas_per_sm, sm_count, st)
-                       : launch_band_w<K, false, 256>(p, smem, ctas_per_sm, sm_count, st);
-    if (spec && p.W == 512)
-        return p.noise ? launch_band_w<K, true, 512>(p, smem, ctas_per_sm, sm_count, st)
-                       : launch_band_w<K, false, 512>(p, smem, ctas_per_sm, sm_count, st);
-    return p.noise ? launch_band_w<K, true, 0>(p, smem, ctas_per_sm, sm_count, st)
-                   : launch_band_w<K, false, 0>(p, smem, ctas_per_sm, sm_count, st);
+    if (p.W == 256)
+        return p.noise ? launch_band_w<K, true, 256>(p, c, sm_count, st) : launch_band_w<K, false, 256>(p, c, sm_count, st);
+    if (p.W == 512)
+        return p.noise ? launch_band_w<K, true, 512>(p, c, sm_count, st) : launch_band_w<K, false, 512>(p, c, sm_count, st);
+    return p.noise ? launch_band_w<K, true, 0>(p, c, sm_count, st) : launch_band_w<K, false, 0>(p, c, sm_count, st);
 }
 
-struct BandConfig {
-    int TH, threads, ctas_per_sm;
-    size_t smem;
-};
-
-// two input stages of (th + 2P) rows + one halo-padded intermediate of th rows (pitch W + 2 * 4 * ceil(P/4))
-static size_t blur_band_smem(int th, int P, int W)
+// NSTAGE input stages of (th + 2P) rows + one halo-padded intermediate of th rows
+static size_t blur_band_smem(int th, int K, int W, int nstage)
 {
-    return ((size_t)(2 * th + 4 * P) * W + (size_t)th * (W + 8 * ((P + 3) / 4))) * 4;
+    return ((size_t)nstage * (th + 2 * (K / 2)) * W + (size_t)th * blur_mid_pitch_host(K, W)) * 4;
 }
 
-// Band height / CTA shape: prefer TH = 32 (halo re-read factor (TH+2P)/TH from L2), two pipelined stages per CTA.
-// Overridable for tuning: SEI_BLUR_TH, SEI_BLUR_THREADS, SEI_BLUR_CTAS.
-BandConfig blur_pick_band_config(int H, int W, int P, int smem_optin)
+// Band height / CTA shape.  Overridable for tuning: SEI_BLUR_TH, SEI_BLUR_H16 (0/1), SEI_BLUR_CTAS.
+BandConfig blur_pick_band_config(int H, int W, int K, bool noise, int smem_optin)
 {
-    BandConfig c = {0, 256, 1, 0};
+    BandConfig c = {0, 256, 1, 2, 0, 0};
     const int per_sm = 227 * 1024;
+    c.h16 = (W % 16 == 0) ? env_int("SEI_BLUR_H16", (K > 7 || noise) ? 1 : 0) : 0;
+    c.threads = c.h16 ? 128 : 256;
+    c.nstage = c.h16 ? 1 : 2;
     int best = 0;
-    for (int th = 8; th <= 16; th += 8)   // TH = 16 with three CTAs per SM measured best on B200 (profiles/r01_blur_tuning.md)
-        if (blur_band_smem(th, P, W) + 1024 <= (size_t)smem_optin) best = th;
+    for (int th = 8; th <= 16; th += 8)   // TH = 16 measured best on B200 (profiles/)
+        if (blur_band_smem(th, K, W, c.nstage) + 1024 <= (size_t)smem_optin) best = th;
     const int forced = env_int("SEI_BLUR_TH", 0);
-    if (forced > 0 && forced % 8 == 0 && blur_band_smem(forced, P, W) + 1024 <= (size_t)smem_optin) best = forced;
+    if (forced > 0 && forced % 8 == 0 && blur_band_smem(forced, K, W, c.nstage) + 1024 <= (size_t)smem_optin) best = forced;
     if (best == 0) return c;
     c.TH = std::min(best, ((H + 7) / 8) * 8);
-    c.smem = blur_band_smem(c.TH, P, W);
-    c.ctas_per_sm = std::max(1, std::min(4, (int)(per_sm / (c.smem + 1024))));
-    c.threads = 256;
+    c.smem = blur_band_smem(c.TH, K, W, c.nstage);
+    c.ctas_per_sm = std::max(1, std::min(c.threads == 128 ? 6 : 4, (int)(per_sm / (c.smem + 1024))));
     const int fc = env_int("SEI_BLUR_CTAS", 0);
     if (fc >= 1 && fc <= c.ctas_per_sm) c.ctas_per_sm = fc;
     return c;
@@ -231,8 +248,8 @@ extern "C" int sei_blur_circular_f32(const float* x, float* y, long long planes,
     const bool sep = kh == kw && (kh % 2 == 1) && factor_separable(kernel_host, kh, kw, v, h);
     const bool ksupported = kh == 5 || kh == 7 || kh == 9 || kh == 13 || kh == 19;
     const int P = kh / 2;
-    BandConfig cfg = {0, 256, 1, 0};
-    if (sep && ksupported && (W % 4 == 0) && W >= 4 * ((P + 3) / 4)) cfg = blur_pick_band_config(H, W, P, dp.smem_optin);
+    BandConfig cfg = {0, 256, 1, 2, 0, 0};
+    if (sep && ksupported && (W % 4 == 0) && W >= 4 * ((P + 3) / 4)) cfg = blur_pick_band_config(H, W, kh, noise != nullptr, dp.smem_optin);
     const int TH = cfg.TH;
     const bool aligned = aligned16(x) && aligned16(y) && (!noise || aligned16(noise));
     const bool tiled_ok = TH > 0 && aligned && planes * ((H + TH - 1) / TH) < (1ll << 31);
@@ -250,11 +267,11 @@ extern "C" int sei_blur_circular_f32(const float* x, float* y, long long planes,
             p.ch[t] = (float)(adjoint ? h[t] : h[kh - 1 - t]);
         }
         switch (kh) {
-        case 5: return launch_band<5>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
-        case 7: return launch_band<7>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
-        case 9: return launch_band<9>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
-        case 13: return launch_band<13>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
-        default: return launch_band<19>(p, cfg.smem, cfg.ctas_per_sm, dp.sm_count, st);
+        case 5: return launch_band<5>(p, cfg, dp.sm_count, st);
+        case 7: return launch_band<7>(p, cfg, dp.sm_count, st);
+        case 9: return launch_band<9>(p, cfg, dp.sm_count, st);
+        case 13: return launch_band<13>(p, cfg, dp.sm_count, st);
+        default: return launch_band<19>(p, cfg, dp.sm_count, st);
         }
     }
 

@@ -194,7 +194,7 @@ static int launch_ei_blur(const EiBlurParams& p, long long planes, size_t smem, 
 
 static int ei_tmp_floats(int th, int P, int S)
 {
-    const int n2 = th + 2 * P, pitch = S + 8 * ((P + 3) / 4);
+    const int n2 = th + 2 * P, pitch = blur_mid_pitch_host(2 * P + 1, S);
     return std::max(n2 * S, th * pitch);
 }
 

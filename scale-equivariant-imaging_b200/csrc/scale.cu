@@ -14,6 +14,7 @@
 // Direct kernel: one thread per output element, for shapes the tiled path does not take.
 #include "tile_ops.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sei {
 
@@ -202,6 +203,11 @@ int scale_pick_band_rows(int S, int smem_optin, size_t* smem_out)
     for (int th = 8; th <= 64; th += 8) {
         const size_t need = ((size_t)scale_src_rows(th) + th) * S * 4 + (size_t)(S + th) * sizeof(AxisTap);
         if (need <= budget) best = th;
+    }
+    if (const char* e = getenv("SEI_SCALE_TH")) {     // tuning override
+        const int f = atoi(e);
+        if (f >= 8 && f % 8 == 0 && ((size_t)scale_src_rows(f) + f) * S * 4 + (size_t)(S + f) * sizeof(AxisTap) <= (size_t)smem_optin)
+            best = f;
     }
     if (best == 0) return 0;
     best = std::min(best, ((S + 7) / 8) * 8);

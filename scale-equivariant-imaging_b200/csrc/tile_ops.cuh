@@ -19,10 +19,18 @@ template <int K> struct BlurGeom {
     static constexpr int LEFT = 4 * LCH;
 };
 
+// Row pitch of the halo-padded intermediate: W + 2*LEFT rounded up to 4 (mod 32) floats, so consecutive rows start
+// one 16-byte bank group apart.  blur_hpass16 relies on it: a quarter-warp reads 4 rows x 2 column blocks with
+// 128-bit loads and touches 8 distinct bank groups (no conflicts).
+__host__ __device__ constexpr int blur_pad_pitch(int n) { return n + ((4 - n % 32) + 32) % 32; }
+
 template <int K, bool PAD> __host__ __device__ constexpr int blur_mid_pitch(int W)
 {
-    return PAD ? W + 2 * BlurGeom<K>::LEFT : W;
+    return PAD ? blur_pad_pitch(W + 2 * BlurGeom<K>::LEFT) : W;
 }
+
+// host-side: pitch of the padded intermediate for a run-time tap count
+inline int blur_mid_pitch_host(int K, int W) { return blur_pad_pitch(W + 8 * ((K / 2 + 3) / 4)); }
 
 // vertical: sMid[o][c] = sum_t cv[t] * sIn[o + t][c],  o in [0, th), rows of sIn in [0, th + K - 1)
 // Register-blocked: each work item owns kRH output rows x 4 columns and streams kRH + K - 1 input
@@ -172,6 +180,81 @@ __device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int W
         const int r0 = item / CW, c0 = item - r0 * CW;
         const int g0 = r0 * W + c0 * 4;
         blur_hpass_item<K, NOISE, PAD>(sMid + r0 * pitch, c0, CW, tap, yrow0 + g0, NOISE ? nrow0 + g0 : nullptr, sigma);
+    }
+}
+
+// horizontal pass, 16 outputs per work item.  One item = (row r, block of 16 columns): 4 + 2*LCH 128-bit shared
+// loads feed 16*K FMAs (2 loads per output vector at K = 13, against 4-5 for the 4-wide item above; the ncu
+// profile of the 4-wide version showed the LSU shared-memory pipe at 71 % and the FMA pipe at 42 %).  Lanes are
+// laid out 4 rows x 8 column blocks per warp (lane = 4 * block + row); with the intermediate's pitch = 4 (mod 32)
+// every quarter-warp load is conflict-free.  Requires W % 16 == 0 and the padded intermediate.
+template <int K, bool NOISE>
+__device__ __forceinline__ void blur_hpass16_item(const float* __restrict__ src, const float (&tap)[K],
+                                                  float* __restrict__ ydst, const float* __restrict__ ndst, float sigma)
+{
+    using G = BlurGeom<K>;
+    constexpr int P = G::P, LCH = G::LCH, LEFT = G::LEFT, NCH = 4 + 2 * LCH;
+    float4 nz[4];
+    if (NOISE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nz[i] = ld_stream4(ndst + 4 * i);
+    }
+    float v[4 * NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+        v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    float out[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) out[o] = 0.f;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o) out[o] = fmaf(tap[t], v[LEFT + o + t - P], out[o]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (NOISE) {
+            out[4 * i + 0] = fmaf(sigma, nz[i].x, out[4 * i + 0]); out[4 * i + 1] = fmaf(sigma, nz[i].y, out[4 * i + 1]);
+            out[4 * i + 2] = fmaf(sigma, nz[i].z, out[4 * i + 2]); out[4 * i + 3] = fmaf(sigma, nz[i].w, out[4 * i + 3]);
+        }
+        st_stream4(ydst + 4 * i, make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
+    }
+}
+
+template <int K, int NT, bool NOISE, int WT, bool TWO>
+__device__ __forceinline__ void blur_hpass16(const float* __restrict__ sMid, int Wrt, int th, const float* __restrict__ ch,
+                                             float* __restrict__ yrow0, const float* __restrict__ nrow0, float sigma)
+{
+    const int W = WT ? WT : Wrt;
+    const int NB = W >> 4;
+    const int pitch = blur_mid_pitch<K, true>(W);
+    float tap[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) asm volatile("mov.f32 %0, %1;" : "=f"(tap[t]) : "f"(ch[t]));
+    const int nitems = ((th + 3) >> 2) * 4 * NB;
+    const bool whole = (th & 3) == 0;      // every item maps to a row of the band: no per-item row check
+    auto run = [&](int item, bool check) {
+        const int j = item & 3, q = item >> 2;
+        const int rg = q / NB, k = q - rg * NB;
+        const int r = 4 * rg + j;
+        if (!check || r < th) {
+            const int g = r * W + 16 * k;
+            blur_hpass16_item<K, NOISE>(sMid + r * pitch + 16 * k, tap, yrow0 + g, NOISE ? nrow0 + g : nullptr, sigma);
+        }
+    };
+    int item = threadIdx.x;
+    if (whole) {
+        if (TWO) {
+            for (; item + NT < nitems; item += 2 * NT) {
+                run(item, false);
+                run(item + NT, false);
+            }
+        }
+        for (; item < nitems; item += NT) run(item, false);
+    } else {
+        for (; item < nitems; item += NT) run(item, true);
     }
 }
 

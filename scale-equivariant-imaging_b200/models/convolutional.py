@@ -9,9 +9,10 @@ unchanged.  What differs is where the arithmetic runs:
     wgrad call the same kernel with the operand roles permuted;
   * activations travel through the network in bf16, channels-last; parameters stay fp32 masters and are
     cast once per optimizer step;
-  * everything else (depthwise 7x7, channel LayerNorm, GELU, the FFT "ideal" resamplers, including the
-    reference's quirks: fftshift applied to the half-spectrum axis, ifftshift results discarded) stays
-    PyTorch library code.
+  * the FFT "ideal" resamplers (including the reference's quirks: fftshift applied to the half-spectrum axis,
+    ifftshift results discarded) are applied as the explicit linear operators they are, by two batched
+    tensor-core products per call (models/resample.py, csrc/bgemm.cu) -- no cuFFT, no layout copies;
+  * depthwise 7x7, channel LayerNorm and GELU stay PyTorch library code.
 """
 from math import ceil
 
@@ -20,6 +21,7 @@ import torch.nn.functional as F
 from torch.nn import Conv2d, GELU, LayerNorm as BaseLayerNorm, Module, ModuleList, Sequential
 
 from sei_b200 import ops
+from . import resample
 
 CL = torch.channels_last
 # activation / GEMM operand dtype.  bf16 is the only dtype the tcgen05 kernel takes; the unit tests set this to
@@ -161,6 +163,8 @@ class IdealUpsample(Module):
         self.rate = rate
 
     def forward(self, x):
+        if resample.supported(x):       # bf16 channels-last on the GPU: two batched tensor-core products (bgemm.cu)
+            return resample.ideal_resample(x, "up", self.rate)
         dtype = x.dtype
         r = self.rate
         s = (x.shape[-2], x.shape[-1])
@@ -198,6 +202,8 @@ class IdealDownsample(Module):
         self.rate = rate
 
     def forward(self, x):
+        if resample.supported(x):
+            return resample.ideal_resample(x, "down", self.rate)
         dtype = x.dtype
         s = (x.shape[-2], x.shape[-1])
         X = torch.fft.fftshift(torch.fft.rfft2(x.float(), dim=(-2, -1)), dim=(-2, -1))

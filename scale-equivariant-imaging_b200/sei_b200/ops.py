@@ -266,6 +266,26 @@ def gemm_bf16_atb(a, b):
     return d
 
 
+def bgemm_tile_rows(M, Kpad):
+    """rows of the operator kept resident per CTA by sei_bgemm_bf16 for an (M, Kpad) operator"""
+    return int(_lib.load().sei_bgemm_tile_rows(int(M), int(Kpad)))
+
+
+def bgemm_bf16(A, x, out, M, K, N, tile_rows, batches, b_inner, x_b, k_inner, x_k, d_b, m_inner, d_m):
+    """out_b[M, N] = A[M, K] @ x_b[K, N] for every batch entry (include/sei_b200.h: sei_bgemm_bf16).
+    A: zero-padded bf16 operator [rows, Kpad]; x_b / d_b: (outer, inner) batch strides; x_k / d_m: (outer, inner)
+    row strides; all in elements."""
+    for t, name in ((A, "A"), (x, "x"), (out, "out")):
+        if not t.is_cuda or t.dtype != torch.bfloat16:
+            raise SeiError(f"bgemm_bf16: {name} must be a CUDA bf16 tensor")
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_bgemm_bf16(_ptr(A), _ptr(x), _ptr(out), int(M), int(K), int(N), int(A.shape[1]),
+                                         int(tile_rows), int(batches), int(b_inner), int(x_b[0]), int(x_b[1]),
+                                         int(k_inner), int(x_k[0]), int(x_k[1]), int(d_b[0]), int(d_b[1]),
+                                         int(m_inner), int(d_m[0]), int(d_m[1]), _stream(x)))
+    return out
+
+
 # ------------------------------------------------------------------------------ autograd
 class _BlurCircular(torch.autograd.Function):
     """y = A x (adjoint=False) or A^T x; backward applies the other one (hand-written transpose)."""

@@ -404,6 +404,27 @@ def gen_model():
          n_params=np.array(sum(p_.numel() for p_ in big.parameters())))
 
 
+def gen_resample():
+    """IdealUpsample / IdealDownsample of the reference's CNN (src/models/convolutional.py:48-133), float64, with the
+    vector-Jacobian product autograd gives for a random output gradient (pins the transposed operators)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_convolutional", os.path.join(REF_SRC, "models", "convolutional.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(2024)
+    out = {}
+    shapes = [(2, 3, 16, 16), (1, 2, 32, 32), (1, 2, 48, 48), (1, 1, 24, 40), (1, 1, 6, 12), (1, 2, 64, 64)]
+    for i, shape in enumerate(shapes):
+        for kind, layer in (("down", mod.IdealDownsample(rate=2)), ("up", mod.IdealUpsample(rate=2))):
+            x = torch.randn(shape, generator=g, dtype=torch.float64, requires_grad=True)
+            y = layer(x)
+            gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+            (gx,) = torch.autograd.grad(y, x, gy)
+            out[f"{kind}{i}_x"], out[f"{kind}{i}_y"] = np_(x), np_(y)
+            out[f"{kind}{i}_gy"], out[f"{kind}{i}_gx"] = np_(gy), np_(gx)
+    save("resample", **out)
+
+
 def gen_step():
     """BASELINE configs[0]: deblurring Gaussian_R2, method=proposed, one training step's loss + gradients on
     synthetic 48x48 RGB crops, batch 8, on the CPU in fp32, with the reference's own ConvolutionalModel (small

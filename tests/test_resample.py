@@ -1,0 +1,120 @@
+"""The CNN's ideal (Fourier-domain) resamplers as explicit operators (models/resample.py, csrc/bgemm.cu) against
+fixtures produced by running the reference's IdealUpsample / IdealDownsample (tests/golden/make_golden.py
+gen_resample, float64): outputs and the autograd vector-Jacobian products.
+  CPU:  the four operator matrices reproduce the reference to 1e-12 (forward and transposed).
+  GPU:  the batched tensor-core product against fp32 matmul of the same bf16 operands (accumulation order only:
+        8e-3 covers the bf16 rounding of the result), and the resamplers on bf16 channels-last activations against
+        the float64 fixtures within the bf16 tolerance 2e-2 (max |a-b| / max |b|)."""
+import numpy as np
+import pytest
+import torch
+
+from util import rel_err
+
+N_CASES = 6
+
+
+@pytest.mark.parametrize("kind", ["down", "up"])
+def test_resample_operators_match_reference(golden, kind):
+    from models import resample
+    g = golden("resample")
+    for i in range(N_CASES):
+        x, y = torch.from_numpy(g[f"{kind}{i}_x"]), g[f"{kind}{i}_y"]
+        got = resample.apply_dense(kind, x, 2)
+        assert rel_err(got.numpy(), y) < 1e-12, (kind, i)
+        Gr, Gi, P, Q = resample.operator(kind, x.shape[-2], x.shape[-1], 2)
+        gy = torch.from_numpy(g[f"{kind}{i}_gy"])
+        gx = Gr.t() @ gy @ P + Gi.t() @ gy @ Q
+        assert rel_err(gx.numpy(), g[f"{kind}{i}_gx"]) < 1e-12, (kind, i)
+
+
+def test_mirror_fft_path_matches_reference(golden):
+    """the library (torch.fft) formulation kept for channel counts that are not a multiple of 8"""
+    import models.convolutional as mc
+    g = golden("resample")
+    for i in range(N_CASES):
+        for kind, layer in (("down", mc.IdealDownsample(2)), ("up", mc.IdealUpsample(2))):
+            x = torch.from_numpy(g[f"{kind}{i}_x"]).float()
+            assert rel_err(layer(x).numpy(), g[f"{kind}{i}_y"]) < 2e-5, (kind, i)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K,N,batches", [(256, 256, 128, 37), (128, 512, 200, 3), (512, 128, 64, 9), (48, 24, 8, 50),
+                                           (16, 32, 1032, 2), (100, 70, 72, 5), (32, 64, 64, 300)])
+def test_bgemm_matches_matmul(dev, M, K, N, batches):
+    from sei_b200 import ops, launch_count
+    torch.manual_seed(M + K + N)
+    A = torch.randn(M, K, device=dev) / K ** 0.5
+    x = torch.randn(batches, K, N, device=dev).bfloat16()
+    kpad = -(-K // 64) * 64
+    tile = ops.bgemm_tile_rows(M, kpad)
+    assert tile in (16, 32, 64, 128, 256)
+    Ap = torch.zeros(-(-M // tile) * tile, kpad, device=dev, dtype=torch.bfloat16)
+    Ap[:M, :K] = A.bfloat16()
+    out = torch.full((batches, M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    n0 = launch_count()
+    ops.bgemm_bf16(Ap, x, out, M, K, N, tile, batches, 1, (K * N, 0), K, (0, N), (M * N, 0), M, (0, N))
+    assert launch_count() == n0 + 1
+    ref = Ap[:M, :K].float() @ x.float()
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < 8e-3
+
+
+@pytest.mark.gpu
+def test_bgemm_split_rows(dev):
+    """split batch / row addressing: the two-term intermediate [B, 2, H, W', C] written and read in place"""
+    from sei_b200 import ops
+    torch.manual_seed(5)
+    B, H, W, Wo, C = 3, 20, 24, 12, 16
+    A1 = torch.randn(2 * Wo, W, device=dev) / W ** 0.5
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    kpad = 64
+    tile = ops.bgemm_tile_rows(2 * Wo, kpad)
+    Ap = torch.zeros(-(-2 * Wo // tile) * tile, kpad, device=dev, dtype=torch.bfloat16)
+    Ap[:2 * Wo, :W] = A1.bfloat16()
+    y = torch.zeros(B, 2, H, Wo, C, device=dev, dtype=torch.bfloat16)
+    ops.bgemm_bf16(Ap, x, y, 2 * Wo, W, C, tile, B * H, H, (H * W * C, W * C), W, (0, C),
+                   (2 * H * Wo * C, Wo * C), Wo, (H * Wo * C, C))
+    ref = torch.einsum("mw,bhwc->bhmc", Ap[:2 * Wo, :W].float(), x.float())        # m = (t, w')
+    ref = ref.view(B, H, 2, Wo, C).permute(0, 2, 1, 3, 4)
+    assert rel_err(y.float().cpu().numpy(), ref.cpu().numpy()) < 8e-3
+    # read it back with split K rows: gx[b, h, w, c] = sum_{t, w'} A1[(t, w'), w] y[b, t, h, w', c]
+    A1T = A1.t().contiguous()
+    kpad2 = 64
+    tile2 = ops.bgemm_tile_rows(W, kpad2)
+    Ap2 = torch.zeros(-(-W // tile2) * tile2, kpad2, device=dev, dtype=torch.bfloat16)
+    Ap2[:W, :2 * Wo] = A1T.bfloat16()
+    gx = torch.zeros(B, H, W, C, device=dev, dtype=torch.bfloat16)
+    ops.bgemm_bf16(Ap2, y, gx, W, 2 * Wo, C, tile2, B * H, H, (2 * H * Wo * C, Wo * C), Wo, (H * Wo * C, C),
+                   (H * W * C, W * C), W, (0, C))
+    ref2 = torch.einsum("wm,bhmc->bhwc", Ap2[:W, :2 * Wo].float(), y.float().permute(0, 2, 1, 3, 4).reshape(B, H, 2 * Wo, C))
+    assert rel_err(gx.float().cpu().numpy(), ref2.cpu().numpy()) < 8e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["down", "up"])
+def test_ideal_resample_gpu_matches_reference(golden, dev, kind):
+    from models import resample
+    from sei_b200 import launch_count
+    g = golden("resample")
+    for i in range(N_CASES):
+        x64, y64 = g[f"{kind}{i}_x"], g[f"{kind}{i}_y"]
+        gy64, gx64 = g[f"{kind}{i}_gy"], g[f"{kind}{i}_gx"]
+        nc = x64.shape[1]
+        idx = [c % nc for c in range(8)]                       # 8 channels (the op needs C % 8 == 0): fixture channels repeated
+        x = torch.from_numpy(x64[:, idx]).to(dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        assert resample.supported(x)
+        n0 = launch_count()
+        y = resample.ideal_resample(x, kind, 2)
+        assert launch_count() == n0 + 2
+        assert rel_err(y.detach().float().cpu().numpy(), y64[:, idx]) < 2e-2, (kind, i)
+        gy = torch.from_numpy(gy64[:, idx]).to(dev).bfloat16()
+        (gx,) = torch.autograd.grad(y, x, gy)
+        assert launch_count() == n0 + 4
+        assert rel_err(gx.float().cpu().numpy(), gx64[:, idx]) < 2e-2, (kind, i)
