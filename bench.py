@@ -156,7 +156,7 @@ def run_b200(args):
     else:
         model = ToyModel(rate=1).to(dev)
     n_params = sum(p.numel() for p in model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=True, fused=True)
     params = [p for p in model.parameters()]
     torch.manual_seed(1 + rank)                # per-rank data and draws
 

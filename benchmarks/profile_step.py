@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--cnn-hidden", type=int, default=32)
     ap.add_argument("--cnn-scales", type=int, default=5)
     ap.add_argument("--rows", type=int, default=45)
+    ap.add_argument("--copies", action="store_true", help="attribute copy / cat / add kernels to source lines")
     args = ap.parse_args()
     import losses
     import models
@@ -42,6 +43,16 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
+    if args.copies:
+        # attribute the layout / dtype copies to the Python lines that issue them
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+            step()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.key_averages(group_by_stack_n=8) if e.key in ("aten::copy_", "aten::cat", "aten::add", "aten::add_", "aten::fill_", "aten::zero_")]
+        for e in sorted(evs, key=lambda e: -e.self_device_time_total)[: args.rows]:
+            frames = [f for f in e.stack if "site-packages" not in f][:4]
+            print(f"{e.self_device_time_total / 1e3:8.2f} ms  x{e.count:<4d} {e.key:12s} " + " <- ".join(f.strip()[-70:] for f in frames))
+        return
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()

@@ -196,6 +196,20 @@ int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int K, int N, i
                    int k_inner, long long x_ko, long long x_ki,
                    long long d_bo, long long d_bi, int m_inner, long long d_mo, long long d_mi, void* stream);
 
+/* Channel LayerNorm of the reference's CNN (src/models/convolutional.py:21-30: swapaxes, nn.LayerNorm(C, eps), swapaxes)
+ * on channels-last bf16 activations viewed as rows [T = B*H*W, C] (C % 8 == 0): statistics and arithmetic in fp32.
+ * forward: y, and mean / rstd per row (saved for the backward).  backward: dx (bf16) and dgamma / dbeta (fp32, fixed
+ * summation order); workspace of sei_ln_cl_backward_workspace_bytes(C) bytes (-1: channel count unsupported). */
+int sei_ln_cl_forward_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                           long long T, int C, float eps, void* stream);
+long long sei_ln_cl_backward_workspace_bytes(int C);
+int sei_ln_cl_backward_bf16(const void* gy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                            void* dx, float* dgamma, float* dbeta, void* workspace, long long T, int C, void* stream);
+
+/* out[c] (fp32) = sum over the T rows of x[T, C] (bf16, C % 8 == 0), fixed summation order: the bias gradient of the
+ * reference's pointwise convolutions (autograd of nn.Conv2d bias).  workspace: sei_ln_cl_backward_workspace_bytes(C). */
+int sei_colsum_bf16(const void* x, float* out, void* workspace, long long T, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

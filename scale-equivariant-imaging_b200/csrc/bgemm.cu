@@ -11,7 +11,7 @@
 //
 // with A shared by every batch entry (A = [P; Q] over batch = image rows, then A = [Gr | Gi] over batch = images).
 // The primitive is HBM-bound (K <= 512), so the design is: the A block stays resident in shared memory for the
-// life of a persistent CTA, X streams through a 4-stage cp.async ring in 64 x 64 chunks that runs ahead across
+// life of a persistent CTA, X streams through a cp.async ring of KC x BN chunks that runs ahead across
 // work items, the products run on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate; ldmatrix fragments
 // from padded, conflict-free rows), and every warp stages its output tile in shared memory to store full
 // 16-byte vectors.  Row indices of X and D may be split (r = ro * inner + ri, two strides) so that the two-term
@@ -22,11 +22,16 @@
 
 namespace sei {
 
-constexpr int kBgThreads = 256;
-constexpr int kBgBN = 64;          // output columns per work item
-constexpr int kBgKC = 64;          // X rows per pipeline chunk
-constexpr int kBgStages = 4;
-constexpr int kBgXPitch = kBgBN + 8;   // bf16 elements; 144 B rows: ldmatrix conflict-free
+// Tile shapes per resident-row count MT: threads, output columns BN per work item, X rows KC per pipeline chunk and
+// ring depth.  Small operators get wide work items so that every warp still owns a 16 x 64 tile per chunk (the first
+// version used 64 columns for all of them and spent its time in the per-chunk barrier); the two large ones run 16
+// warps so that one CTA per SM (the A block fills most of shared memory) still hides the ldmatrix -> mma latency.
+template <int MT> struct BgCfg;
+template <> struct BgCfg<256> { static constexpr int NW = 16, WM = 8, BN = 64, KC = 64, ST = 4; };
+template <> struct BgCfg<128> { static constexpr int NW = 16, WM = 8, BN = 64, KC = 64, ST = 4; };
+template <> struct BgCfg<64> { static constexpr int NW = 8, WM = 4, BN = 128, KC = 64, ST = 4; };
+template <> struct BgCfg<32> { static constexpr int NW = 8, WM = 2, BN = 256, KC = 32, ST = 4; };
+template <> struct BgCfg<16> { static constexpr int NW = 8, WM = 1, BN = 512, KC = 32, ST = 3; };
 
 struct BgemmParams {
     const __nv_bfloat16* A;      // [m_blocks * MT][Kpad], zero padded
@@ -64,34 +69,37 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// MT: rows of A resident per CTA (blockIdx.y selects the block).  Warp grid WM x WN over the MT x 64 tile.
+// MT: rows of A resident per CTA (blockIdx.y selects the block).  Warp grid WM x WN over the MT x BN tile.
 template <int MT>
-__global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_constant__ BgemmParams p)
+__global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __grid_constant__ BgemmParams p)
 {
-    constexpr int WM = MT >= 128 ? 8 : MT / 16;       // warps along M
-    constexpr int WN = 8 / WM;                         // warps along N
+    using Cfg = BgCfg<MT>;
+    constexpr int NT = Cfg::NW * 32, BN = Cfg::BN, KC = Cfg::KC, ST = Cfg::ST;
+    constexpr int WM = Cfg::WM, WN = Cfg::NW / WM;
     constexpr int TM = MT / WM;                        // warp tile rows (32 for MT = 256, else 16)
-    constexpr int TN = kBgBN / WN;                     // warp tile columns (64, 32, 16, 8)
-    constexpr int MI = TM / 16;
-    constexpr int NI = TN / 8;
+    constexpr int TN = BN / WN;                        // warp tile columns (32 or 64)
+    constexpr int MI = TM / 16, NI = TN / 8;
+    constexpr int XP = BN + 8;                         // X stage pitch (bf16): rows 16 B apart mod 128 B, ldmatrix conflict-free
     constexpr int DP = TN + 8;                         // staging pitch (bf16)
+    constexpr int VEC = KC * BN / 8;                   // 16-byte vectors per chunk
+    static_assert(VEC % NT == 0 && NI % 2 == 0, "tile shape");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int apitch = p.Kpad + 8;
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);                           // [MT][Kpad + 8]
-    __nv_bfloat16* sX = sA + (size_t)MT * apitch;                                              // [stages][64][72]
-    __nv_bfloat16* sD = sX + (size_t)kBgStages * kBgKC * kBgXPitch;                            // [8 warps][TM][DP]
+    __nv_bfloat16* sX = sA + (size_t)MT * apitch;                                              // [ST][KC][XP]
+    __nv_bfloat16* sD = sX + (size_t)ST * KC * XP;                                             // [warps][TM][DP]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
     const int m_block = blockIdx.y;
-    const int kch = p.Kpad / kBgKC;
+    const int kch = (p.K + KC - 1) / KC;
 
     // ---- resident A block (zero padded on the host: no bounds checks)
     {
         const __nv_bfloat16* gA = p.A + (size_t)m_block * MT * p.Kpad;
         const int vec_per_row = p.Kpad / 8;
-        for (int i = tid; i < MT * vec_per_row; i += kBgThreads) {
+        for (int i = tid; i < MT * vec_per_row; i += NT) {
             const int r = i / vec_per_row, v = i - r * vec_per_row;
             cp_async16(sA + (size_t)r * apitch + v * 8, gA + (size_t)r * p.Kpad + v * 8, true);
         }
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
     const long long my_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
     const long long total_chunks = my_items * kch;
 
-    // one pipeline chunk: 64 rows x 64 columns of X (rows beyond K / columns beyond N are zero-filled)
+    // one pipeline chunk: KC rows x BN columns of X (rows beyond K / columns beyond N are zero-filled)
     auto issue = [&](long long g) {
         const long long it = g / kch;
         const int kc = (int)(g - it * kch);
@@ -111,20 +119,20 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
         const int nt = (int)(item - bt * p.n_tiles);
         const long long bo = bt / p.b_inner, bi = bt - bo * p.b_inner;
         const __nv_bfloat16* xb = p.X + bo * p.x_bo + bi * p.x_bi;
-        __nv_bfloat16* dst = sX + (size_t)(g % kBgStages) * kBgKC * kBgXPitch;
+        __nv_bfloat16* dst = sX + (size_t)(g % ST) * KC * XP;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = tid + j * kBgThreads;          // 0 .. 511
-            const int row = idx >> 3, cv = idx & 7;
-            const int k = kc * kBgKC + row, n = nt * kBgBN + cv * 8;
+        for (int j = 0; j < VEC / NT; ++j) {
+            const int idx = tid + j * NT;
+            const int row = idx / (BN / 8), cv = idx % (BN / 8);
+            const int k = kc * KC + row, n = nt * BN + cv * 8;
             const bool valid = k < p.K && n < p.N;
             const int ko = valid ? k / p.k_inner : 0, ki = valid ? k - ko * p.k_inner : 0;
-            cp_async16(dst + row * kBgXPitch + cv * 8, xb + ko * p.x_ko + ki * p.x_ki + (valid ? n : 0), valid);
+            cp_async16(dst + row * XP + cv * 8, xb + ko * p.x_ko + ki * p.x_ki + (valid ? n : 0), valid);
         }
     };
 
 #pragma unroll
-    for (int s = 0; s < kBgStages - 1; ++s) {
+    for (int s = 0; s < ST - 1; ++s) {
         if (s < total_chunks) issue(s);
         cp_async_commit();
     }
@@ -143,37 +151,29 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
     __nv_bfloat16* myD = sD + (size_t)warp * TM * DP;
 
     for (long long g = 0; g < total_chunks; ++g) {
-        cp_async_wait<kBgStages - 2>();
+        cp_async_wait<ST - 2>();
         __syncthreads();
-        if (g + kBgStages - 1 < total_chunks) issue(g + kBgStages - 1);
+        if (g + ST - 1 < total_chunks) issue(g + ST - 1);
         cp_async_commit();
 
         const long long it = g / kch;
         const int kc = (int)(g - it * kch);
-        const __nv_bfloat16* xs = sX + (size_t)(g % kBgStages) * kBgKC * kBgXPitch;
+        const __nv_bfloat16* xs = sX + (size_t)(g % ST) * KC * XP;
 #pragma unroll
-        for (int ks = 0; ks < kBgKC / 16; ++ks) {
+        for (int ks = 0; ks < KC / 16; ++ks) {
             uint32_t af[MI][4];
 #pragma unroll
             for (int a = 0; a < MI; ++a)
-                ldsm_x4(af[a], sA + (size_t)(a_row + a * 16) * apitch + kc * kBgKC + ks * 16 + a_kofs);
-            if constexpr (NI >= 2) {
+                ldsm_x4(af[a], sA + (size_t)(a_row + a * 16) * apitch + kc * KC + ks * 16 + a_kofs);
 #pragma unroll
-                for (int b = 0; b < NI / 2; ++b) {
-                    uint32_t bf[4];
-                    ldsm_x4_trans(bf, xs + (size_t)(ks * 16 + b_krow) * kBgXPitch + b_nofs + b * 16);
-#pragma unroll
-                    for (int a = 0; a < MI; ++a) {
-                        mma_bf16(acc[a][2 * b], af[a], bf[0], bf[1]);
-                        mma_bf16(acc[a][2 * b + 1], af[a], bf[2], bf[3]);
-                    }
-                }
-            } else {
-                // 8-column warp tile: one n8 block; lanes 16-31 point at the same matrices as lanes 0-15
+            for (int b = 0; b < NI / 2; ++b) {
                 uint32_t bf[4];
-                ldsm_x4_trans(bf, xs + (size_t)(ks * 16 + b_krow) * kBgXPitch + wn * TN);
+                ldsm_x4_trans(bf, xs + (size_t)(ks * 16 + b_krow) * XP + b_nofs + b * 16);
 #pragma unroll
-                for (int a = 0; a < MI; ++a) mma_bf16(acc[a][0], af[a], bf[0], bf[1]);
+                for (int a = 0; a < MI; ++a) {
+                    mma_bf16(acc[a][2 * b], af[a], bf[0], bf[1]);
+                    mma_bf16(acc[a][2 * b + 1], af[a], bf[2], bf[3]);
+                }
             }
         }
 
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
             constexpr int VPR = TN / 8;                    // 16-byte vectors per tile row
             for (int i = lane; i < TM * VPR; i += 32) {
                 const int r = i / VPR, v = i - r * VPR;
-                const int m = m_block * MT + wm * TM + r, n = nt * kBgBN + wn * TN + v * 8;
+                const int m = m_block * MT + wm * TM + r, n = nt * BN + wn * TN + v * 8;
                 if (m < p.M && n < p.N) {
                     const int mo = m / p.m_inner, mi = m - mo * p.m_inner;
                     *reinterpret_cast<uint4*>(db + mo * p.d_mo + mi * p.d_mi + n) =
@@ -210,21 +210,37 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
     cp_async_wait<0>();
 }
 
+template <int MT> static size_t bgemm_smem_t(int Kpad)
+{
+    using Cfg = BgCfg<MT>;
+    constexpr int TM = MT / Cfg::WM, TN = Cfg::BN / (Cfg::NW / Cfg::WM);
+    return ((size_t)MT * (Kpad + 8) + (size_t)Cfg::ST * Cfg::KC * (Cfg::BN + 8) + (size_t)Cfg::NW * TM * (TN + 8)) * 2;
+}
+
 static size_t bgemm_smem(int MT, int Kpad)
 {
-    const int WMc = MT >= 128 ? 8 : MT / 16, TM = MT / WMc, TN = kBgBN / (8 / WMc);
-    return ((size_t)MT * (Kpad + 8) + (size_t)kBgStages * kBgKC * kBgXPitch + (size_t)8 * TM * (TN + 8)) * 2;
+    switch (MT) {
+    case 256: return bgemm_smem_t<256>(Kpad);
+    case 128: return bgemm_smem_t<128>(Kpad);
+    case 64: return bgemm_smem_t<64>(Kpad);
+    case 32: return bgemm_smem_t<32>(Kpad);
+    default: return bgemm_smem_t<16>(Kpad);
+    }
 }
 
 template <int MT>
-static int launch_bgemm(const BgemmParams& p, int m_blocks, int sm_count, cudaStream_t st)
+static int launch_bgemm(BgemmParams p, int m_blocks, int sm_count, cudaStream_t st)
 {
-    const size_t smem = bgemm_smem(MT, p.Kpad);
+    using Cfg = BgCfg<MT>;
+    const size_t smem = bgemm_smem_t<MT>(p.Kpad);
     SEI_CUDA(allow_smem(bgemm_kernel<MT>, smem));
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)227 * 1024 / (smem + 1024)));
+    p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
+    p.items *= p.n_tiles;                                   // caller passes items = batches
+    const int by_threads = 2048 / (Cfg::NW * 32);
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min(4, by_threads), (size_t)227 * 1024 / (smem + 1024)));
     const long long per_block = std::max(1, sm_count * ctas_per_sm / m_blocks);
     dim3 grid((unsigned)std::min<long long>(p.items, per_block), (unsigned)m_blocks);
-    bgemm_kernel<MT><<<grid, kBgThreads, smem, st>>>(p);
+    bgemm_kernel<MT><<<grid, Cfg::NW * 32, smem, st>>>(p);
     return finish_launch("bgemm_kernel");
 }
 
@@ -251,7 +267,7 @@ extern "C" int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int 
     SEI_REQUIRE(A && X && D, "null pointer argument");
     SEI_REQUIRE(M > 0 && K > 0 && N > 0 && batches >= 0, "bad shape M=%d K=%d N=%d", M, K, N);
     SEI_REQUIRE(N % 8 == 0, "N=%d must be a multiple of 8 (16-byte rows)", N);
-    SEI_REQUIRE(Kpad % kBgKC == 0 && Kpad >= K, "Kpad=%d must be a multiple of %d and >= K=%d", Kpad, kBgKC, K);
+    SEI_REQUIRE(Kpad % 64 == 0 && Kpad >= K, "Kpad=%d must be a multiple of 64 and >= K=%d", Kpad, K);
     SEI_REQUIRE(b_inner > 0 && k_inner > 0 && m_inner > 0, "inner sizes must be positive");
     SEI_REQUIRE(aligned16(A) && aligned16(X) && aligned16(D), "operands must be 16-byte aligned");
     SEI_REQUIRE(((x_bo | x_bi | x_ko | x_ki | d_bo | d_bi | d_mo | d_mi) & 7) == 0, "strides must be multiples of 8 elements");
@@ -267,8 +283,8 @@ extern "C" int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int 
     p.D = static_cast<__nv_bfloat16*>(D);
     p.M = M; p.K = K; p.N = N; p.Kpad = Kpad;
     p.b_inner = b_inner; p.k_inner = k_inner; p.m_inner = m_inner;
-    p.n_tiles = (N + kBgBN - 1) / kBgBN;
-    p.items = batches * p.n_tiles;
+    p.n_tiles = 0;
+    p.items = batches;           // multiplied by the column tiles of the chosen shape in launch_bgemm
     p.x_bo = x_bo; p.x_bi = x_bi; p.x_ko = x_ko; p.x_ki = x_ki;
     p.d_bo = d_bo; p.d_bi = d_bi; p.d_mo = d_mo; p.d_mi = d_mi;
     const int m_blocks = (M + tile_rows - 1) / tile_rows;

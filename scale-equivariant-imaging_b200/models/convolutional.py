@@ -59,10 +59,13 @@ class _GemmTN(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             if gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0:
                 gw = _gemm_atb(gy, x)                                                # wgrad: gy[T,N]^T @ x[T,K], in place
-            else:                                                                    # 3-channel edges of the network
+            elif x.shape[1] % 8 == 0:                         # 3-channel output edge: pad gy's columns, not transposes
+                gw = _gemm_atb(_pad_k(gy), x)[: gy.shape[1]]
+            else:
                 gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = torch.sum(gy, 0, dtype=torch.float32)      # one pass, fp32 accumulation, no fp32 copy of gy
+            # one pass, fp32 accumulation, fixed order (csrc/cnn_elem.cu); library reduction for odd channel counts
+            gb = ops.colsum_bf16(gy) if ops.ln_cl_supported(gy) else torch.sum(gy, 0, dtype=torch.float32)
         return gx, gw, gb, None, None
 
 
@@ -132,9 +135,33 @@ class LayerNorm(Module):
 
     def forward(self, x):
         xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)                   # channels last: a view
+        rows = xl.reshape(-1, xl.shape[-1])
+        if ops.ln_cl_supported(rows):                                             # hand-written kernels (csrc/cnn_elem.cu)
+            out = ops.layer_norm_cl(rows, self.ln.weight, self.ln.bias, self.ln.eps).view(xl.shape)
+            return out.permute(0, 3, 1, 2)
         out = F.layer_norm(xl, self.ln.normalized_shape, self.ln.weight.to(xl.dtype), self.ln.bias.to(xl.dtype),
                            self.ln.eps)
         return out.permute(0, 3, 1, 2)
+
+
+class _DepthwiseConv7(torch.autograd.Function):
+    """depthwise 7x7, padding 3 (reference ConvBlock.conv1 :36-38) through the library convolution.  The input
+    gradient is the same convolution with the taps flipped; asking the library for it that way uses its fast
+    channels-last FORWARD kernel (the profile showed its depthwise dgrad kernel 5x slower than its forward)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return F.conv2d(x, w, b, padding=3, groups=x.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        C = x.shape[1]
+        gx = F.conv2d(g, w.flip(2, 3), None, padding=3, groups=C) if ctx.needs_input_grad[0] else None
+        _, gw, gb = torch.ops.aten.convolution_backward(g, x, w, [C], [1, 1], [3, 3], [1, 1], False, [0, 0], C,
+                                                        [False, True, True])
+        return gx, gw, gb
 
 
 class ConvBlock(Module):
@@ -147,7 +174,7 @@ class ConvBlock(Module):
         self.conv3 = _conv(4 * dim, dim, 1)
 
     def forward(self, x):
-        x1 = F.conv2d(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype), padding=3, groups=x.shape[1])
+        x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
         x1 = self.gelu(x1)

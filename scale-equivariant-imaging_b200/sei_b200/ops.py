@@ -286,6 +286,61 @@ def bgemm_bf16(A, x, out, M, K, N, tile_rows, batches, b_inner, x_b, k_inner, x_
     return out
 
 
+def ln_cl_supported(x_rows):
+    """rows [T, C] of a channels-last activation that sei_ln_cl_* take: CUDA, bf16, contiguous, C % 8 == 0 and a
+    channel count the parameter-gradient kernel can tile"""
+    return (x_rows.is_cuda and x_rows.dtype == torch.bfloat16 and x_rows.dim() == 2 and x_rows.is_contiguous()
+            and x_rows.shape[1] % 8 == 0 and _lib.load().sei_ln_cl_backward_workspace_bytes(int(x_rows.shape[1])) >= 0)
+
+
+class _LayerNormCL(torch.autograd.Function):
+    """y = LayerNorm_C(x) on rows [T, C] (bf16), fp32 affine parameters; backward by the hand-written kernels"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        T, Cc = x.shape
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty(T, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.load().sei_ln_cl_forward_bf16(_ptr(x), _ptr(g32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), T, Cc,
+                                                     float(eps), _stream(x)))
+        ctx.save_for_backward(x, mean, rstd, g32)
+        ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, g32 = ctx.saved_tensors
+        T, Cc = x.shape
+        gy = gy.contiguous()
+        lib = _lib.load()
+        dx = torch.empty_like(x)
+        dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.sei_ln_cl_backward_bf16(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(dx), _ptr(dg),
+                                              _ptr(db), _ptr(ws), T, Cc, _stream(x)))
+        return dx, dg.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
+
+
+def colsum_bf16(x_rows):
+    """fp32 column sums of a bf16 [T, C] matrix (sei_colsum_bf16); rows must satisfy ln_cl_supported"""
+    T, Cc = x_rows.shape
+    lib = _lib.load()
+    out = torch.empty(Cc, dtype=torch.float32, device=x_rows.device)
+    ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=x_rows.device)
+    with torch.cuda.device(x_rows.device):
+        check(lib.sei_colsum_bf16(_ptr(x_rows), _ptr(out), _ptr(ws), T, Cc, _stream(x_rows)))
+    return out
+
+
+def layer_norm_cl(x_rows, gamma, beta, eps):
+    return _LayerNormCL.apply(x_rows, gamma, beta, eps)
+
+
 # ------------------------------------------------------------------------------ autograd
 class _BlurCircular(torch.autograd.Function):
     """y = A x (adjoint=False) or A^T x; backward applies the other one (hand-written transpose)."""

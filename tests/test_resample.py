@@ -118,3 +118,40 @@ def test_ideal_resample_gpu_matches_reference(golden, dev, kind):
         (gx,) = torch.autograd.grad(y, x, gy)
         assert launch_count() == n0 + 4
         assert rel_err(gx.float().cpu().numpy(), gx64[:, idx]) < 2e-2, (kind, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,C", [(1000, 32), (4096 + 3, 128), (777, 512), (300, 2048), (65, 8192), (50, 8), (129, 64), (40, 256)])
+def test_layer_norm_cl_matches_torch(dev, T, C):
+    """hand-written channel LayerNorm (csrc/cnn_elem.cu) vs torch.nn.functional.layer_norm in fp32 on the same bf16
+    input: forward within bf16 rounding of the result (6e-3), dx likewise, dgamma / dbeta 2e-3 (fp32 sums)."""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(T + C)
+    x = (torch.randn(T, C, device=dev) * 1.7 + 0.3).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(C, device=dev)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, device=dev)).requires_grad_(True)
+    gy = torch.randn(T, C, device=dev).bfloat16()
+    assert ops.ln_cl_supported(x)
+    xa = x.clone().requires_grad_(True)
+    y = ops.layer_norm_cl(xa, gamma, beta, 1e-6)
+    y.backward(gy)
+    xr = x.float().requires_grad_(True)
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), g2, b2, 1e-6)
+    yr.backward(gy.float())
+    assert rel_err(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) < 6e-3
+    assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.cpu().numpy()) < 6e-3
+    assert rel_err(gamma.grad.cpu().numpy(), g2.grad.cpu().numpy()) < 2e-3
+    assert rel_err(beta.grad.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,C", [(5000, 32), (333, 128), (2049, 512), (77, 8192), (10, 8)])
+def test_colsum_matches_torch(dev, T, C):
+    from sei_b200 import ops
+    torch.manual_seed(T)
+    x = torch.randn(T, C, device=dev).bfloat16()
+    got = ops.colsum_bf16(x)
+    ref = x.double().sum(0)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
