@@ -210,6 +210,18 @@ int sei_ln_cl_backward_bf16(const void* gy, const void* x, const float* mean, co
  * reference's pointwise convolutions (autograd of nn.Conv2d bias).  workspace: sei_ln_cl_backward_workspace_bytes(C). */
 int sei_colsum_bf16(const void* x, float* out, void* workspace, long long T, int C, void* stream);
 
+/* 3x3 convolution, stride 1, zero "same" padding, with 1..4 output channels, on a channels-last bf16 input
+ * [B, H, W, Cin] (Cin a multiple of 8, <= 64): the reference's UNet.out_conv (src/models/convolutional.py:176,
+ * Conv2d(hidden, in_channels, kernel_size=3, padding="same")).  w: [Cout, Cin, 3, 3] fp32, bias: [Cout] fp32 or NULL.
+ * forward: y [B, H, W, 4] bf16 (channels >= Cout are zero).  backward: gy [B, H, W, 4] bf16 -> gx [B, H, W, Cin] bf16
+ * (skipped when gx == NULL; Cin in {8, 16, 32, 64}), gw [Cout, Cin, 3, 3] and gb [Cout] fp32 in a fixed summation
+ * order; workspace of sei_conv3x3_small_workspace_bytes(Cin, Cout) bytes. */
+long long sei_conv3x3_small_workspace_bytes(int Cin, int Cout);
+int sei_conv3x3_small_forward_bf16(const void* x, const float* w, const float* bias, void* y,
+                                   int B, int H, int W, int Cin, int Cout, void* stream);
+int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, const float* w, void* gx, float* gw, float* gb,
+                                    void* workspace, int B, int H, int W, int Cin, int Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

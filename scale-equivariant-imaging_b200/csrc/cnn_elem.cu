@@ -436,3 +436,311 @@ extern "C" int sei_colsum_bf16(const void* x, float* out, void* workspace, long 
                                                       colsum_slots(C, threads), C, C);
     return finish_launch("colsum_final_kernel");
 }
+
+// ---------------------------------------------------------------- 3x3 convolution with a few output channels
+// The network's last layer (reference UNet.out_conv, src/models/convolutional.py:176: Conv2d(hidden, in_channels = 3,
+// kernel_size=3, padding="same")) maps `hidden` channels to 3.  As a GEMM it has N = 3 and needs a 9x unfolded copy
+// of its input; here it is a direct CUDA-core kernel on the channels-last input (1.8 GFMA at batch 32: not
+// tensor-core work), and so are its input and weight gradients.  Outputs carry 4 channels per pixel (8-byte
+// pixels; channel 3 is zero when Cout = 3).
+namespace sei {
+
+constexpr int kC3MaxCin = 64, kC3MaxCout = 4;
+
+struct Conv3Params {
+    const __nv_bfloat16* x;      // [B, H, W, Cin]
+    const __nv_bfloat16* gy;     // [B, H, W, 4]
+    const float* w;              // [Cout, Cin, 3, 3]
+    const float* bias;           // [Cout] or null
+    __nv_bfloat16* y;            // forward: [B, H, W, 4]; dgrad: [B, H, W, Cin]
+    float* partial;
+    int B, H, W, Cin, Cout;
+    long long T;
+};
+
+// shared-memory copy of the taps as ws[tap][co][ci]
+__device__ __forceinline__ void conv3_load_taps(const Conv3Params& p, float* ws)
+{
+    for (int i = threadIdx.x; i < 9 * p.Cout * p.Cin; i += blockDim.x) {
+        const int ci = i % p.Cin, co = (i / p.Cin) % p.Cout, tap = i / (p.Cin * p.Cout);
+        ws[i] = __ldg(p.w + ((size_t)co * p.Cin + ci) * 9 + tap);
+    }
+    __syncthreads();
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3_small_fwd_kernel(const __grid_constant__ Conv3Params p)
+{
+    extern __shared__ __align__(16) float ws[];
+    conv3_load_taps(p, ws);
+    const int H = p.H, W = p.W, Cin = p.Cin, nvec = Cin >> 3;
+    float b0[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) b0[co] = p.bias ? __ldg(p.bias + co) : 0.f;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < p.T; t += (long long)gridDim.x * blockDim.x) {
+        const int w0 = (int)(t % W);
+        const long long r = t / W;
+        const int h0 = (int)(r % H);
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = b0[co];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hy = h0 + ky - 1;
+            if (hy < 0 || hy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int wx = w0 + kx - 1;
+                if (wx < 0 || wx >= W) continue;
+                const uint4* xp = reinterpret_cast<const uint4*>(p.x + (t + (long long)(ky - 1) * W + (kx - 1)) * Cin);
+                const float* wt = ws + (ky * 3 + kx) * COUT * Cin;
+                for (int v = 0; v < nvec; ++v) {
+                    float f[8];
+                    unpack8(__ldg(xp + v), f);
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wt + co * Cin + 8 * v);
+                        const float4 wb = *reinterpret_cast<const float4*>(wt + co * Cin + 8 * v + 4);
+                        acc[co] = fmaf(f[0], wa.x, acc[co]); acc[co] = fmaf(f[1], wa.y, acc[co]);
+                        acc[co] = fmaf(f[2], wa.z, acc[co]); acc[co] = fmaf(f[3], wa.w, acc[co]);
+                        acc[co] = fmaf(f[4], wb.x, acc[co]); acc[co] = fmaf(f[5], wb.y, acc[co]);
+                        acc[co] = fmaf(f[6], wb.z, acc[co]); acc[co] = fmaf(f[7], wb.w, acc[co]);
+                    }
+                }
+            }
+        }
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) o[co] = acc[co];
+        uint2 packed;
+        *reinterpret_cast<__nv_bfloat162*>(&packed.x) = __floats2bfloat162_rn(o[0], o[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&packed.y) = __floats2bfloat162_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(p.y + t * 4) = packed;
+    }
+}
+
+// input gradient: gx[p][ci] = sum_{ky,kx,co} w[co][ci][ky][kx] * gy[p - (ky-1, kx-1)][co].  NV = Cin / 8.
+template <int COUT, int NV>
+__global__ void __launch_bounds__(256) conv3_small_dgrad_kernel(const __grid_constant__ Conv3Params p)
+{
+    extern __shared__ __align__(16) float ws[];
+    conv3_load_taps(p, ws);
+    constexpr int Cin = NV * 8;
+    const int H = p.H, W = p.W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < p.T; t += (long long)gridDim.x * blockDim.x) {
+        const int w0 = (int)(t % W);
+        const long long r = t / W;
+        const int h0 = (int)(r % H);
+        float acc[Cin];
+#pragma unroll
+        for (int c = 0; c < Cin; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hy = h0 - ky + 1;
+            if (hy < 0 || hy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int wx = w0 - kx + 1;
+                if (wx < 0 || wx >= W) continue;
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.gy + (t - (long long)(ky - 1) * W - (kx - 1)) * 4));
+                const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                const float g[4] = {g01.x, g01.y, g23.x, g23.y};
+                const float* wt = ws + (ky * 3 + kx) * COUT * Cin;
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+                    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wt + co * Cin + 4 * c4);
+                        acc[4 * c4 + 0] = fmaf(g[co], wv.x, acc[4 * c4 + 0]); acc[4 * c4 + 1] = fmaf(g[co], wv.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(g[co], wv.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(g[co], wv.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+        uint4* o = reinterpret_cast<uint4*>(p.y + t * Cin);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = acc[8 * v + j];
+            o[v] = pack8(f);
+        }
+    }
+}
+
+// weight / bias gradient partials.  A CTA holds NG pixel groups of GS = 9 * Cin/8 threads; thread (tap, v) of a
+// group accumulates gW[co][8v .. 8v+7][tap] over the group's pixels, the centre-tap / v = 0 thread also gb[co].
+// partial[cta][co][ci][tap] (PyTorch weight layout), then [Cout] bias sums; combined by colsum_final_kernel.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3_small_wgrad_kernel(const __grid_constant__ Conv3Params p)
+{
+    extern __shared__ __align__(16) float red[];           // [NG][GS][COUT * 8 + COUT]
+    const int H = p.H, W = p.W, Cin = p.Cin, nvec = Cin >> 3;
+    const int GS = 9 * nvec, NG = blockDim.x / GS;
+    const int g = threadIdx.x / GS, lt = threadIdx.x - g * GS;
+    const int tap = lt / nvec, v = lt - tap * nvec;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    float acc[COUT][8], gb[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        gb[co] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[co][j] = 0.f;
+    }
+    if (g < NG) {
+        for (long long t = (long long)blockIdx.x * NG + g; t < p.T; t += (long long)gridDim.x * NG) {
+            const int w0 = (int)(t % W);
+            const long long r = t / W;
+            const int h0 = (int)(r % H);
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.gy + t * 4));
+            const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            const float gv[4] = {g01.x, g01.y, g23.x, g23.y};
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) gb[co] += gv[co];
+            const int hy = h0 + ky - 1, wx = w0 + kx - 1;
+            if (hy < 0 || hy >= H || wx < 0 || wx >= W) continue;
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + (t + (long long)(ky - 1) * W + (kx - 1)) * Cin) + v), f);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[co][j] = fmaf(gv[co], f[j], acc[co][j]);
+        }
+    }
+    constexpr int PER = COUT * 8 + COUT;
+    if (g < NG) {
+        float* mine = red + ((size_t)g * GS + lt) * PER;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine[co * 8 + j] = acc[co][j];
+            mine[COUT * 8 + co] = gb[co];
+        }
+    }
+    __syncthreads();
+    const int nW = COUT * Cin * 9;
+    float* out = p.partial + (size_t)blockIdx.x * (nW + COUT);
+    for (int i = threadIdx.x; i < nW + COUT; i += blockDim.x) {
+        float s = 0.f;
+        if (i < nW) {
+            const int tp = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+            const int l = tp * nvec + (ci >> 3);
+            for (int k = 0; k < NG; ++k) s += red[((size_t)k * GS + l) * PER + co * 8 + (ci & 7)];
+        } else {
+            const int co = i - nW;
+            const int l = 4 * nvec;                        // centre tap, vector 0
+            for (int k = 0; k < NG; ++k) s += red[((size_t)k * GS + l) * PER + COUT * 8 + co];
+        }
+        out[i] = s;
+    }
+}
+
+static int conv3_wgrad_ctas(int sm_count) { return sm_count * 4; }
+
+}  // namespace sei
+
+extern "C" long long sei_conv3x3_small_workspace_bytes(int Cin, int Cout)
+{
+    DeviceProps dp;
+    if (get_device_props(&dp)) return -1;
+    return (long long)conv3_wgrad_ctas(dp.sm_count) * ((long long)Cout * Cin * 9 + Cout) * (long long)sizeof(float);
+}
+
+static int conv3_check(int B, int H, int W, int Cin, int Cout)
+{
+    SEI_REQUIRE(B >= 0 && H > 0 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
+    SEI_REQUIRE(Cin >= 8 && Cin % 8 == 0 && Cin <= kC3MaxCin, "Cin=%d unsupported (multiple of 8, <= %d)", Cin, kC3MaxCin);
+    SEI_REQUIRE(Cout >= 1 && Cout <= kC3MaxCout, "Cout=%d unsupported (1..%d)", Cout, kC3MaxCout);
+    return 0;
+}
+
+extern "C" int sei_conv3x3_small_forward_bf16(const void* x, const float* w, const float* bias, void* y,
+                                              int B, int H, int W, int Cin, int Cout, void* stream)
+{
+    SEI_REQUIRE(x && w && y, "null pointer argument");
+    int rc = conv3_check(B, H, W, Cin, Cout);
+    if (rc) return rc;
+    SEI_REQUIRE(aligned16(x) && aligned16(y), "operands must be 16-byte aligned");
+    if (B == 0) return 0;
+    DeviceProps dp;
+    rc = get_device_props(&dp);
+    if (rc) return rc;
+    Conv3Params p = {};
+    p.x = static_cast<const __nv_bfloat16*>(x); p.w = w; p.bias = bias; p.y = static_cast<__nv_bfloat16*>(y);
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.T = (long long)B * H * W;
+    const size_t smem = (size_t)9 * Cout * Cin * sizeof(float);
+    const unsigned grid = (unsigned)std::min<long long>((p.T + 255) / 256, (long long)dp.sm_count * 16);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (Cout) {
+    case 1: conv3_small_fwd_kernel<1><<<grid, 256, smem, st>>>(p); break;
+    case 2: conv3_small_fwd_kernel<2><<<grid, 256, smem, st>>>(p); break;
+    case 3: conv3_small_fwd_kernel<3><<<grid, 256, smem, st>>>(p); break;
+    default: conv3_small_fwd_kernel<4><<<grid, 256, smem, st>>>(p); break;
+    }
+    return finish_launch("conv3_small_fwd_kernel");
+}
+
+template <int COUT>
+static int conv3_launch_dgrad(const Conv3Params& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (p.Cin) {
+    case 8: conv3_small_dgrad_kernel<COUT, 1><<<grid, 256, smem, st>>>(p); break;
+    case 16: conv3_small_dgrad_kernel<COUT, 2><<<grid, 256, smem, st>>>(p); break;
+    case 32: conv3_small_dgrad_kernel<COUT, 4><<<grid, 256, smem, st>>>(p); break;
+    case 64: conv3_small_dgrad_kernel<COUT, 8><<<grid, 256, smem, st>>>(p); break;
+    default: sei::set_error("conv3x3 input gradient: Cin=%d unsupported (8, 16, 32, 64)", p.Cin); return SEI_EINVAL;
+    }
+    return finish_launch("conv3_small_dgrad_kernel");
+}
+
+// gx may be NULL (input gradient not needed).  gw: [Cout, Cin, 3, 3] fp32, gb: [Cout] fp32 (fixed summation order).
+extern "C" int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, const float* w, void* gx, float* gw,
+                                               float* gb, void* workspace, int B, int H, int W, int Cin, int Cout,
+                                               void* stream)
+{
+    SEI_REQUIRE(gy && x && w && gw && gb && workspace, "null pointer argument");
+    int rc = conv3_check(B, H, W, Cin, Cout);
+    if (rc) return rc;
+    SEI_REQUIRE(aligned16(x) && aligned16(gy) && (!gx || aligned16(gx)) && aligned16(workspace), "operands must be 16-byte aligned");
+    DeviceProps dp;
+    rc = get_device_props(&dp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nW = Cout * Cin * 9;
+    if (B == 0) {
+        SEI_CUDA(cudaMemsetAsync(gw, 0, (size_t)nW * 4, st));
+        SEI_CUDA(cudaMemsetAsync(gb, 0, (size_t)Cout * 4, st));
+        return 0;
+    }
+    Conv3Params p = {};
+    p.x = static_cast<const __nv_bfloat16*>(x); p.gy = static_cast<const __nv_bfloat16*>(gy); p.w = w;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.T = (long long)B * H * W;
+    if (gx) {
+        p.y = static_cast<__nv_bfloat16*>(gx);
+        const size_t smem = (size_t)9 * Cout * Cin * sizeof(float);
+        const unsigned grid = (unsigned)std::min<long long>((p.T + 255) / 256, (long long)dp.sm_count * 16);
+        switch (Cout) {
+        case 1: rc = conv3_launch_dgrad<1>(p, grid, smem, st); break;
+        case 2: rc = conv3_launch_dgrad<2>(p, grid, smem, st); break;
+        case 3: rc = conv3_launch_dgrad<3>(p, grid, smem, st); break;
+        default: rc = conv3_launch_dgrad<4>(p, grid, smem, st); break;
+        }
+        if (rc) return rc;
+    }
+    p.partial = static_cast<float*>(workspace);
+    const int GS = 9 * (Cin / 8), NG = std::max(1, 256 / GS), threads = NG * GS;
+    const int ctas = conv3_wgrad_ctas(dp.sm_count);
+    const size_t smem = (size_t)threads * (Cout * 8 + Cout) * sizeof(float);
+    switch (Cout) {
+    case 1: SEI_CUDA(allow_smem(conv3_small_wgrad_kernel<1>, smem)); conv3_small_wgrad_kernel<1><<<ctas, threads, smem, st>>>(p); break;
+    case 2: SEI_CUDA(allow_smem(conv3_small_wgrad_kernel<2>, smem)); conv3_small_wgrad_kernel<2><<<ctas, threads, smem, st>>>(p); break;
+    case 3: SEI_CUDA(allow_smem(conv3_small_wgrad_kernel<3>, smem)); conv3_small_wgrad_kernel<3><<<ctas, threads, smem, st>>>(p); break;
+    default: SEI_CUDA(allow_smem(conv3_small_wgrad_kernel<4>, smem)); conv3_small_wgrad_kernel<4><<<ctas, threads, smem, st>>>(p); break;
+    }
+    rc = finish_launch("conv3_small_wgrad_kernel");
+    if (rc) return rc;
+    colsum_final_kernel<<<(nW + Cout + 31) / 32, 256, 0, st>>>(p.partial, gw, gb, ctas, nW + Cout, nW);
+    return finish_launch("colsum_final_kernel");
+}

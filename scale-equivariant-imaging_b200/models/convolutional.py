@@ -104,6 +104,10 @@ class _GemmConv2d(Conv2d):
     def forward(self, x):
         B, C, H, W = x.shape
         xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)      # (B, H, W, C) view
+        if self.kernel_size == (3, 3) and ops.conv3x3_small_supported(xl, self.out_channels):
+            # the network's output layer (hidden -> 3 channels): direct kernel, no unfolded copy (csrc/cnn_elem.cu)
+            out = ops.conv3x3_small(xl, self.weight, self.bias)
+            return out[..., : self.out_channels].permute(0, 3, 1, 2)
         if self.kernel_size == (3, 3):
             xl = _unfold3x3(xl)
         x2 = xl.reshape(B * H * W, xl.shape[-1])

@@ -337,6 +337,50 @@ def colsum_bf16(x_rows):
     return out
 
 
+def conv3x3_small_supported(x_bhwc, out_channels):
+    return (x_bhwc.is_cuda and x_bhwc.dtype == torch.bfloat16 and x_bhwc.dim() == 4 and x_bhwc.is_contiguous()
+            and x_bhwc.shape[3] in (8, 16, 32, 64) and 1 <= out_channels <= 4)
+
+
+class _Conv3x3Small(torch.autograd.Function):
+    """x [B, H, W, Cin] bf16 (channels last) -> y [B, H, W, 4] bf16; weight [Cout, Cin, 3, 3], bias [Cout] fp32"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty((B, H, W, 4), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.load().sei_conv3x3_small_forward_bf16(_ptr(x), _ptr(w32), _ptr(b32), _ptr(y), B, H, W, Cin, Cout,
+                                                             _stream(x)))
+        ctx.save_for_backward(x, w32)
+        ctx.has_bias = bias is not None
+        ctx.dtypes = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w32 = ctx.saved_tensors
+        B, H, W, Cin = x.shape
+        Cout = w32.shape[0]
+        gy = gy.contiguous()
+        lib = _lib.load()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w32)
+        gb = torch.empty(Cout, dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(lib.sei_conv3x3_small_workspace_bytes(Cin, Cout)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.sei_conv3x3_small_backward_bf16(_ptr(gy), _ptr(x), _ptr(w32), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(ws),
+                                                      B, H, W, Cin, Cout, _stream(x)))
+        return gx, gw.to(ctx.dtypes[0]), (gb.to(ctx.dtypes[1]) if ctx.has_bias else None)
+
+
+def conv3x3_small(x_bhwc, weight, bias):
+    return _Conv3x3Small.apply(x_bhwc, weight, bias)
+
+
 def layer_norm_cl(x_rows, gamma, beta, eps):
     return _LayerNormCL.apply(x_rows, gamma, beta, eps)
 

@@ -155,3 +155,32 @@ def test_colsum_matches_torch(dev, T, C):
     got = ops.colsum_bf16(x)
     ref = x.double().sum(0)
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,Cin,Cout,need_gx", [(2, 17, 23, 32, 3, True), (1, 8, 8, 8, 3, True), (3, 16, 16, 64, 4, True),
+                                                     (2, 9, 33, 16, 1, False)])
+def test_conv3x3_small_matches_torch(dev, B, H, W, Cin, Cout, need_gx):
+    """direct 3x3 / few-output-channel convolution (the network's out_conv) vs F.conv2d in fp32 on the same bf16 input:
+    forward within bf16 rounding of the result, gradients 6e-3 / 2e-3."""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(B * H + Cin)
+    x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin ** 0.5)).requires_grad_(True)
+    b = (0.1 * torch.randn(Cout, device=dev)).requires_grad_(True)
+    gy = torch.randn(B, H, W, Cout, device=dev).bfloat16()
+    assert ops.conv3x3_small_supported(x, Cout)
+    xa = x.clone().requires_grad_(need_gx)
+    y = ops.conv3x3_small(xa, w, b)
+    assert y.shape == (B, H, W, 4) and (Cout == 4 or float(y[..., Cout:].abs().max()) == 0.0)
+    y[..., :Cout].backward(gy)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    w2, b2 = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, w2, b2, padding=1)
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    assert rel_err(y[..., :Cout].detach().float().cpu().numpy(), yr.detach().permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
+    if need_gx:
+        assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
+    assert rel_err(w.grad.cpu().numpy(), w2.grad.cpu().numpy()) < 2e-3
+    assert rel_err(b.grad.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-3
