@@ -101,7 +101,10 @@ class _GemmConv2d(Conv2d):
                 self._wt_cache = _pad_k(self._w_cache.t())
         return self._wt_cache
 
-    def forward(self, x):
+    def forward_nobias(self, x):
+        return self.forward(x, use_bias=False)
+
+    def forward(self, x, use_bias=True):
         B, C, H, W = x.shape
         xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)      # (B, H, W, C) view
         if self.kernel_size == (3, 3) and ops.conv3x3_small_supported(xl, self.out_channels):
@@ -115,7 +118,7 @@ class _GemmConv2d(Conv2d):
         if x2.shape[1] != w_bf16.shape[1]:
             x2 = F.pad(x2, (0, w_bf16.shape[1] - x2.shape[1]))
         w2p = w2 if w2.shape[1] == w_bf16.shape[1] else F.pad(w2, (0, w_bf16.shape[1] - w2.shape[1]))
-        out = _GemmTN.apply(x2, w2p, self.bias, w_bf16, self._weight_matrix_t)
+        out = _GemmTN.apply(x2, w2p, self.bias if use_bias else None, w_bf16, self._weight_matrix_t)
         return out.view(B, H, W, -1).permute(0, 3, 1, 2)                        # logical NCHW, channels-last memory
 
 
@@ -257,7 +260,20 @@ class Downsample(Module):
         self.ideal_downsample = IdealDownsample(rate=self.rate)
 
     def forward(self, x):
-        return self.ideal_downsample(self.conv(self.ln(x)))
+        x = self.ln(x)
+        if resample.supported(x) and self.conv.kernel_size == (1, 1):
+            # The pointwise convolution (channels) and the ideal resampler (space) are linear maps on different axes,
+            # so they commute: resample the C-channel tensor first, then convolve a quarter of the pixels (4x fewer
+            # resampler bytes and GEMM flops than conv -> resample).  The bias is a constant image per channel; the
+            # resampler maps it to bias[c] * R(1), added afterwards.
+            H, W = x.shape[-2], x.shape[-1]
+            out = self.conv.forward_nobias(self.ideal_downsample(x))
+            if self.conv.bias is not None:
+                pat = resample.constant_response("down", H, W, self.rate, x.device)                 # (Ho, Wo)
+                bias_img = (pat[:, :, None] * self.conv.bias[None, None, :]).to(out.dtype)          # (Ho, Wo, C_out)
+                out = out + bias_img.permute(2, 0, 1)[None]
+            return out
+        return self.ideal_downsample(self.conv(x))
 
 
 class UNet(Module):

@@ -13,7 +13,7 @@ half spectrum R = Rr + i Ri -> real through the real-linear c2r transform (Ir, I
 
 Gi does not vanish because the kept frequency band [hc, H - hc) of the shifted spectrum is not symmetric.  The four
 matrices are obtained by pushing identity matrices through torch.fft in float64, i.e. they ARE the reference's
-operator (tests/test_host_logic.py::test_resample_operators_match_fft: 1e-12).
+operator (tests/test_resample.py::test_resample_operators_match_reference: 1e-12 against fixtures from the reference).
 
 On the GPU the two contractions run as batched tensor-core products on channels-last bf16 activations
 (csrc/bgemm.cu, sei_bgemm_bf16): width first over batch = (image, row) with A = [P; Q], then height over
@@ -152,6 +152,20 @@ class _IdealResample(torch.autograd.Function):
     def backward(ctx, g):
         gl = g.permute(0, 2, 3, 1).contiguous()
         return _backward_cl(gl, ctx.pk, *ctx.hw).permute(0, 3, 1, 2), None, None
+
+
+_CONST = {}
+
+
+def constant_response(kind, H, W, rate, device):
+    """the operator applied to the all-ones image, (Ho, Wo) fp32: what a per-channel constant (a bias) turns into.
+    It is NOT constant: the reference's fftshift without the matching ifftshift moves DC to a high frequency."""
+    key = (kind, H, W, rate, str(device))
+    if key not in _CONST:
+        Gr, Gi, P, Q = operator(kind, H, W, rate)
+        pat = torch.outer(Gr.sum(1), P.sum(1)) + torch.outer(Gi.sum(1), Q.sum(1))
+        _CONST[key] = pat.to(device=device, dtype=torch.float32)
+    return _CONST[key]
 
 
 def supported(x):
