@@ -222,6 +222,16 @@ int sei_conv3x3_small_forward_bf16(const void* x, const float* w, const float* b
 int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, const float* w, void* gx, float* gw, float* gb,
                                     void* workspace, int B, int H, int W, int Cin, int Cout, void* stream);
 
+/* Depthwise 7x7 convolution, padding 3, on channels-last bf16 activations [B, H, W, C] (C % 8 == 0): the reference's
+ * ConvBlock.conv1 (src/models/convolutional.py:36-38, Conv2d(dim, dim, 7, padding=3, groups=dim)).
+ * sei_dwconv7_cl_bf16: y = conv(x) (+ bias); wt = taps as [49][C] fp32 (tap-major).  Called with the taps flipped and
+ * bias == NULL it is the input gradient.  sei_dwconv7_wgrad_cl_bf16: gw [C, 7, 7] and gb [C] fp32, fixed summation
+ * order; workspace of sei_dwconv7_workspace_bytes(C) bytes (-1: channel count unsupported). */
+long long sei_dwconv7_workspace_bytes(int C);
+int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, void* stream);
+int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* gw, float* gb, void* workspace,
+                              int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -744,3 +744,261 @@ extern "C" int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, co
     colsum_final_kernel<<<(nW + Cout + 31) / 32, 256, 0, st>>>(p.partial, gw, gb, ctas, nW + Cout, nW);
     return finish_launch("colsum_final_kernel");
 }
+
+// ---------------------------------------------------------------- depthwise 7x7 convolution, channels-last bf16
+// Reference ConvBlock.conv1 (src/models/convolutional.py:36-38): Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim).
+// 49 fp32 FMAs per output element and nothing to contract over: CUDA-core work whose floor is the FMA rate (3.3 GFMA
+// per call at batch 32), not HBM.  A thread owns 4 channels x 8 consecutive output columns of one row and slides a
+// 14-column window over each of the 7 input rows: 224 FMAs per 14 eight-byte loads and 7 tap vectors; the inputs are
+// read straight from global memory (the CTA's footprint stays in L1).  The input gradient is the same kernel with the
+// taps flipped (the host passes them that way); taps come as wt[49][C] fp32.
+namespace sei {
+
+constexpr int kDwRW = 8;         // output columns per work item
+constexpr int kDwRH = 8;         // consecutive rows per work item
+
+struct DwParams {
+    const __nv_bfloat16* x;      // [B, H, W, C]
+    const __nv_bfloat16* gy;     // wgrad only
+    const float* wt;             // [49][C]
+    const float* bias;           // [C] or null
+    __nv_bfloat16* y;
+    float* partial;
+    int B, H, W, C, wstrips, hgroups;
+    long long items;
+};
+
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4])
+{
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+
+__global__ void __launch_bounds__(128) dwconv7_kernel(const __grid_constant__ DwParams p)
+{
+    const int H = p.H, W = p.W, C = p.C, cqn = C >> 2;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < p.items; it += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(it % cqn);
+        long long r = it / cqn;
+        const int ws = (int)(r % p.wstrips);
+        r /= p.wstrips;
+        const int hg = (int)(r % p.hgroups);
+        const long long b = r / p.hgroups;
+        const int w0 = ws * kDwRW, c0 = cq * 4;
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        }
+        // consecutive output rows by the same thread: the 7 input rows of row h are 6 of the rows of row h - 1, so
+        // the CTA's working set stays in L1 (the first version took one row per thread and re-read every input row
+        // from L2 seven times)
+        const int hend = min(H, (hg + 1) * kDwRH);
+#pragma unroll 1
+        for (int h = hg * kDwRH; h < hend; ++h) {
+            float acc[kDwRW][4];
+#pragma unroll
+            for (int j = 0; j < kDwRW; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[j][c] = bv[c];
+#pragma unroll 1
+            for (int ky = 0; ky < 7; ++ky) {
+                const int hy = h + ky - 3;
+                if (hy < 0 || hy >= H) continue;
+                const __nv_bfloat16* row = p.x + ((b * H + hy) * (long long)W) * C + c0;
+                float win[kDwRW + 6][4];
+#pragma unroll
+                for (int j = 0; j < kDwRW + 6; ++j) {
+                    const int wx = w0 + j - 3;
+                    uint2 raw = make_uint2(0u, 0u);
+                    if (wx >= 0 && wx < W) raw = __ldg(reinterpret_cast<const uint2*>(row + (long long)wx * C));
+                    unpack4(raw, win[j]);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.wt + (size_t)(ky * 7 + kx) * C + c0));
+#pragma unroll
+                    for (int j = 0; j < kDwRW; ++j) {
+                        acc[j][0] = fmaf(t.x, win[j + kx][0], acc[j][0]); acc[j][1] = fmaf(t.y, win[j + kx][1], acc[j][1]);
+                        acc[j][2] = fmaf(t.z, win[j + kx][2], acc[j][2]); acc[j][3] = fmaf(t.w, win[j + kx][3], acc[j][3]);
+                    }
+                }
+            }
+            __nv_bfloat16* orow = p.y + ((b * H + h) * (long long)W) * C + c0;
+#pragma unroll
+            for (int j = 0; j < kDwRW; ++j) {
+                if (w0 + j < W) {
+                    uint2 o;
+                    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(acc[j][0], acc[j][1]);
+                    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(acc[j][2], acc[j][3]);
+                    *reinterpret_cast<uint2*>(orow + (long long)(w0 + j) * C) = o;
+                }
+            }
+        }
+    }
+}
+
+// weight / bias gradient partials.  blockIdx.y selects a block of CQB channel quads; a CTA holds NG groups of
+// CQB * 7 threads; thread (cq, ky) of a group walks down kDwRH rows of an 8-column strip: per row one 14-column
+// window of x[h + ky - 3] and 8 values of gy[h] feed 224 FMAs into gW[c][ky][0..6] for its 4 channels (28 sums; the
+// ky = 3 thread also keeps the 4 bias sums).  partial[cta.x][c * 49 + ky * 7 + kx], then [C] bias sums.
+__global__ void __launch_bounds__(224) dwconv7_wgrad_kernel(const __grid_constant__ DwParams p, int CQB, int NG)
+{
+    extern __shared__ __align__(16) float red[];           // [NG][CQB * 7][32]
+    const int H = p.H, W = p.W, C = p.C;
+    const int GS = CQB * 7;
+    const int g = threadIdx.x / GS, lt = threadIdx.x - g * GS;
+    const int ky = lt / CQB, cql = lt - ky * CQB;
+    const int cq = blockIdx.y * CQB + cql, c0 = cq * 4;
+    float acc[7][4], gb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+    if (g < NG) {
+        for (long long s = (long long)blockIdx.x * NG + g; s < p.items; s += (long long)gridDim.x * NG) {
+            const int ws = (int)(s % p.wstrips);
+            const long long r = s / p.wstrips;
+            const int hg = (int)(r % p.hgroups);
+            const long long b = r / p.hgroups;
+            const int w0 = ws * kDwRW;
+            const int hend = min(H, (hg + 1) * kDwRH);
+#pragma unroll 1
+            for (int h = hg * kDwRH; h < hend; ++h) {
+                const int hy = h + ky - 3;
+                if (hy < 0 || hy >= H) {
+                    if (ky != 3) continue;
+                }
+                const __nv_bfloat16* grow = p.gy + ((b * H + h) * (long long)W) * C + c0;
+                float gv[kDwRW][4];
+#pragma unroll
+                for (int j = 0; j < kDwRW; ++j) {
+                    uint2 raw = make_uint2(0u, 0u);
+                    if (w0 + j < W) raw = __ldg(reinterpret_cast<const uint2*>(grow + (long long)(w0 + j) * C));
+                    unpack4(raw, gv[j]);
+                }
+                if (ky == 3) {
+#pragma unroll
+                    for (int j = 0; j < kDwRW; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) gb[c] += gv[j][c];
+                }
+                const __nv_bfloat16* xrow = p.x + ((b * H + hy) * (long long)W) * C + c0;
+                float win[kDwRW + 6][4];
+#pragma unroll
+                for (int j = 0; j < kDwRW + 6; ++j) {
+                    const int wx = w0 + j - 3;
+                    uint2 raw = make_uint2(0u, 0u);
+                    if (wx >= 0 && wx < W) raw = __ldg(reinterpret_cast<const uint2*>(xrow + (long long)wx * C));
+                    unpack4(raw, win[j]);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                    for (int j = 0; j < kDwRW; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[kx][c] = fmaf(gv[j][c], win[j + kx][c], acc[kx][c]);
+            }
+        }
+        float* mine = red + ((size_t)g * GS + lt) * 32;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mine[kx * 4 + c] = acc[kx][c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mine[28 + c] = gb[c];
+    }
+    __syncthreads();
+    // this CTA's slice of the partial row: channels [blockIdx.y * CQB * 4, +CQB * 4)
+    float* out = p.partial + (size_t)blockIdx.x * ((size_t)C * 50);
+    const int nch = CQB * 4;
+    for (int i = threadIdx.x; i < nch * 50; i += blockDim.x) {
+        const int cl = i / 50, e = i - cl * 50;           // e < 49: tap ky * 7 + kx; e == 49: bias
+        const int cqi = cl >> 2, cc = cl & 3;
+        const int c = blockIdx.y * nch + cl;
+        float s = 0.f;
+        if (e < 49) {
+            const int kyy = e / 7, kxx = e - kyy * 7;
+            for (int k = 0; k < NG; ++k) s += red[((size_t)k * GS + kyy * CQB + cqi) * 32 + kxx * 4 + cc];
+            out[(size_t)c * 49 + e] = s;
+        } else {
+            for (int k = 0; k < NG; ++k) s += red[((size_t)k * GS + 3 * CQB + cqi) * 32 + 28 + cc];
+            out[(size_t)C * 49 + c] = s;
+        }
+    }
+}
+
+static void dw_wgrad_shape(int C, int sm_count, int* CQB, int* NG, int* gx, int* gy)
+{
+    const int cqn = C / 4;
+    *CQB = cqn >= 32 ? 32 : cqn;                 // cqn in {2, 4, 8, 16} for small C: a divisor of 32
+    *NG = 224 / (*CQB * 7);
+    *gy = cqn / *CQB;
+    *gx = std::max(1, sm_count * 4 / *gy);
+}
+
+}  // namespace sei
+
+extern "C" long long sei_dwconv7_workspace_bytes(int C)
+{
+    DeviceProps dp;
+    if (get_device_props(&dp) || C < 8 || C % 8) return -1;
+    const int cqn = C / 4;
+    if (!(cqn % 32 == 0 || 32 % cqn == 0)) return -1;
+    int CQB, NG, gx, gy;
+    dw_wgrad_shape(C, dp.sm_count, &CQB, &NG, &gx, &gy);
+    return (long long)gx * C * 50 * (long long)sizeof(float);
+}
+
+// y = depthwise7x7(x) (+ bias); wt: taps as [49][C] fp32 (flipped by the caller for the input gradient)
+extern "C" int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C,
+                                   void* stream)
+{
+    SEI_REQUIRE(x && wt && y, "null pointer argument");
+    SEI_REQUIRE(B >= 0 && H > 0 && W > 0 && C >= 8 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+    SEI_REQUIRE(aligned16(x) && aligned16(y) && aligned16(wt) && (!bias || aligned16(bias)), "operands must be 16-byte aligned");
+    if (B == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    DwParams p = {};
+    p.x = static_cast<const __nv_bfloat16*>(x); p.wt = wt; p.bias = bias; p.y = static_cast<__nv_bfloat16*>(y);
+    p.B = B; p.H = H; p.W = W; p.C = C; p.wstrips = (W + kDwRW - 1) / kDwRW; p.hgroups = (H + kDwRH - 1) / kDwRH;
+    p.items = (long long)B * p.hgroups * p.wstrips * (C / 4);
+    const unsigned grid = (unsigned)std::min<long long>((p.items + 127) / 128, (long long)dp.sm_count * 64);
+    dwconv7_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return finish_launch("dwconv7_kernel");
+}
+
+// gw: [C, 7, 7] fp32 (PyTorch depthwise weight layout [C, 1, 7, 7]), gb: [C] fp32; fixed summation order
+extern "C" int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* gw, float* gb, void* workspace,
+                                         int B, int H, int W, int C, void* stream)
+{
+    SEI_REQUIRE(gy && x && gw && gb && workspace, "null pointer argument");
+    SEI_REQUIRE(B >= 0 && H > 0 && W > 0 && C >= 8 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+    SEI_REQUIRE(sei_dwconv7_workspace_bytes(C) > 0, "channel count %d unsupported by the depthwise weight-gradient kernel", C);
+    SEI_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(workspace), "operands must be 16-byte aligned");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (B == 0) {
+        SEI_CUDA(cudaMemsetAsync(gw, 0, (size_t)C * 49 * 4, st));
+        SEI_CUDA(cudaMemsetAsync(gb, 0, (size_t)C * 4, st));
+        return 0;
+    }
+    DwParams p = {};
+    p.x = static_cast<const __nv_bfloat16*>(x); p.gy = static_cast<const __nv_bfloat16*>(gy);
+    p.partial = static_cast<float*>(workspace);
+    p.B = B; p.H = H; p.W = W; p.C = C; p.wstrips = (W + kDwRW - 1) / kDwRW; p.hgroups = (H + kDwRH - 1) / kDwRH;
+    p.items = (long long)B * p.hgroups * p.wstrips;
+    int CQB, NG, gx, gyb;
+    dw_wgrad_shape(C, dp.sm_count, &CQB, &NG, &gx, &gyb);
+    const size_t smem = (size_t)NG * CQB * 7 * 32 * sizeof(float);
+    dwconv7_wgrad_kernel<<<dim3(gx, gyb), NG * CQB * 7, smem, st>>>(p, CQB, NG);
+    rc = finish_launch("dwconv7_wgrad_kernel");
+    if (rc) return rc;
+    colsum_final_kernel<<<(C * 50 + 31) / 32, 256, 0, st>>>(p.partial, gw, gb, gx, C * 50, C * 49);
+    return finish_launch("colsum_final_kernel");
+}

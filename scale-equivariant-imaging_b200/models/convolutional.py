@@ -181,7 +181,11 @@ class ConvBlock(Module):
         self.conv3 = _conv(4 * dim, dim, 1)
 
     def forward(self, x):
-        x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
+        xl = x.permute(0, 2, 3, 1)
+        if ops.dwconv7_supported(xl):                     # hand-written channels-last kernels (csrc/cnn_elem.cu)
+            x1 = ops.dwconv7(xl, self.conv1.weight, self.conv1.bias).permute(0, 3, 1, 2)
+        else:
+            x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
         x1 = self.gelu(x1)

@@ -43,6 +43,9 @@ SIGNATURES = {
     "sei_conv3x3_small_workspace_bytes": (C.c_longlong, [_i, _i]),
     "sei_conv3x3_small_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sei_conv3x3_small_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sei_dwconv7_workspace_bytes": (C.c_longlong, [_i]),
+    "sei_dwconv7_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sei_dwconv7_wgrad_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sei_bgemm_tile_rows": (C.c_int, [_i, _i]),
     "sei_bgemm_bf16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _ll, _ll, _i, _ll, _ll, _ll, _ll, _i, _ll, _ll,
                                  _vp]),

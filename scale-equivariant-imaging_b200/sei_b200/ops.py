@@ -381,6 +381,54 @@ def conv3x3_small(x_bhwc, weight, bias):
     return _Conv3x3Small.apply(x_bhwc, weight, bias)
 
 
+def dwconv7_supported(x_bhwc):
+    return (x_bhwc.is_cuda and x_bhwc.dtype == torch.bfloat16 and x_bhwc.dim() == 4 and x_bhwc.is_contiguous()
+            and x_bhwc.shape[3] % 8 == 0 and _lib.load().sei_dwconv7_workspace_bytes(int(x_bhwc.shape[3])) > 0)
+
+
+def _dwconv7_raw(x, wt, bias):
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_dwconv7_cl_bf16(_ptr(x), _ptr(wt), _ptr(bias), _ptr(y), B, H, W, Cc, _stream(x)))
+    return y
+
+
+class _DwConv7(torch.autograd.Function):
+    """x [B, H, W, C] bf16 (channels last), weight [C, 1, 7, 7], bias [C] (fp32 parameters)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        Cc = x.shape[3]
+        w32 = weight.detach().float().reshape(Cc, 49)
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        ctx.save_for_backward(x, w32)
+        ctx.has_bias = bias is not None
+        ctx.dtypes = (weight.dtype, None if bias is None else bias.dtype)
+        ctx.wshape = weight.shape
+        return _dwconv7_raw(x, w32.t().contiguous(), b32)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w32 = ctx.saved_tensors
+        B, H, W, Cc = x.shape
+        gy = gy.contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = _dwconv7_raw(gy, w32.flip(1).t().contiguous(), None)      # the same convolution with the taps flipped
+        lib = _lib.load()
+        gw = torch.empty((Cc, 49), dtype=torch.float32, device=x.device)
+        gb = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(lib.sei_dwconv7_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.sei_dwconv7_wgrad_cl_bf16(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(ws), B, H, W, Cc, _stream(x)))
+        return gx, gw.view(ctx.wshape).to(ctx.dtypes[0]), (gb.to(ctx.dtypes[1]) if ctx.has_bias else None)
+
+
+def dwconv7(x_bhwc, weight, bias):
+    return _DwConv7.apply(x_bhwc, weight, bias)
+
+
 def layer_norm_cl(x_rows, gamma, beta, eps):
     return _LayerNormCL.apply(x_rows, gamma, beta, eps)
 

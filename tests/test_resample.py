@@ -184,3 +184,28 @@ def test_conv3x3_small_matches_torch(dev, B, H, W, Cin, Cout, need_gx):
         assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
     assert rel_err(w.grad.cpu().numpy(), w2.grad.cpu().numpy()) < 2e-3
     assert rel_err(b.grad.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8), (1, 5, 9, 256), (2, 33, 8, 16)])
+def test_dwconv7_matches_torch(dev, B, H, W, C):
+    """depthwise 7x7 (ConvBlock.conv1) vs F.conv2d(groups=C) in fp32 on the same bf16 input"""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(B + H + C)
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(C, 1, 7, 7, device=dev) / 7).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device=dev)).requires_grad_(True)
+    gy = torch.randn(B, H, W, C, device=dev).bfloat16()
+    assert ops.dwconv7_supported(x)
+    xa = x.clone().requires_grad_(True)
+    y = ops.dwconv7(xa, w, b)
+    y.backward(gy)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    w2, b2 = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, w2, b2, padding=3, groups=C)
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    assert rel_err(y.detach().float().cpu().numpy(), yr.detach().permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
+    assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
+    assert rel_err(w.grad.cpu().numpy(), w2.grad.cpu().numpy()) < 2e-3
+    assert rel_err(b.grad.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-3
