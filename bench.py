@@ -71,8 +71,10 @@ def model_args(hidden, scales):
 def network_description(args):
     if args.network == "cnn":
         return (f"reference ConvolutionalModel (hidden {args.cnn_hidden}, {args.cnn_scales} scales, 1 block per scale; "
-                "random init), bf16 activations, every 1x1/3x3 convolution on the tcgen05 GEMM (fp32 accumulation); "
-                "depthwise 7x7, LayerNorm, GELU and FFT resamplers are PyTorch library ops")
+                "random init), bf16 channels-last activations; pointwise / input 3x3 convolutions on the tcgen05 GEMM "
+                "(fp32 accumulation), ideal resamplers as batched mma.sync operator products, depthwise 7x7, channel "
+                "LayerNorm, output 3x3 convolution and bias / gamma / beta reductions as hand-written kernels; "
+                "GELU, residual adds and Adam are PyTorch library ops")
     return ("4-parameter pointwise stand-in (tests/toy_model.py): isolates the operator + loss-assembly path; "
             "the restoration CNN is not in this line")
 

@@ -232,6 +232,10 @@ int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* bias, void*
 int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* gw, float* gb, void* workspace,
                               int B, int H, int W, int C, void* stream);
 
+/* Exact (erf-form) GELU of the reference's ConvBlock (src/models/convolutional.py:41, nn.GELU()) on n bf16 elements
+ * (n % 8 == 0): out = gelu(x) when gy == NULL, else out = gy * gelu'(x) (the backward of the same layer). */
+int sei_gelu_bf16(const void* x, const void* gy, void* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

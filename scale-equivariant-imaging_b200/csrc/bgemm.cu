@@ -26,12 +26,20 @@ namespace sei {
 // ring depth.  Small operators get wide work items so that every warp still owns a 16 x 64 tile per chunk (the first
 // version used 64 columns for all of them and spent its time in the per-chunk barrier); the two large ones run 16
 // warps so that one CTA per SM (the A block fills most of shared memory) still hides the ldmatrix -> mma latency.
-template <int MT> struct BgCfg;
-template <> struct BgCfg<256> { static constexpr int NW = 16, WM = 8, BN = 64, KC = 64, ST = 4; };
-template <> struct BgCfg<128> { static constexpr int NW = 16, WM = 8, BN = 64, KC = 64, ST = 4; };
-template <> struct BgCfg<64> { static constexpr int NW = 8, WM = 4, BN = 128, KC = 64, ST = 4; };
-template <> struct BgCfg<32> { static constexpr int NW = 8, WM = 2, BN = 256, KC = 32, ST = 4; };
-template <> struct BgCfg<16> { static constexpr int NW = 8, WM = 1, BN = 512, KC = 32, ST = 3; };
+template <int MT, bool WIDE> struct BgCfg;
+template <> struct BgCfg<256, false> { static constexpr int NW = 8, WM = 8, BN = 64, KC = 64, ST = 4; };   // 32 x 64 warp tiles
+template <> struct BgCfg<128, false> { static constexpr int NW = 8, WM = 8, BN = 64, KC = 64, ST = 4; };   // 16 x 64
+template <> struct BgCfg<64, false> { static constexpr int NW = 8, WM = 4, BN = 128, KC = 64, ST = 4; };
+template <> struct BgCfg<32, false> { static constexpr int NW = 8, WM = 2, BN = 256, KC = 32, ST = 4; };
+template <> struct BgCfg<16, false> { static constexpr int NW = 8, WM = 1, BN = 512, KC = 32, ST = 3; };
+// WIDE (N >= 2 x the narrow BN): 64 x 64 warp tiles, 4 + 4 ldmatrix per 32 mma instead of 2 + 4 per 16 -- the A and X
+// fragments are re-read from shared memory by every warp that shares them, and that traffic, not the tensor pipe,
+// bounded the 32 x 64 version (ncu: profiles/)
+template <> struct BgCfg<256, true> { static constexpr int NW = 8, WM = 4, BN = 128, KC = 32, ST = 4; };
+template <> struct BgCfg<128, true> { static constexpr int NW = 8, WM = 2, BN = 256, KC = 32, ST = 3; };
+template <> struct BgCfg<64, true> : BgCfg<64, false> {};
+template <> struct BgCfg<32, true> : BgCfg<32, false> {};
+template <> struct BgCfg<16, true> : BgCfg<16, false> {};
 
 struct BgemmParams {
     const __nv_bfloat16* A;      // [m_blocks * MT][Kpad], zero padded
@@ -70,10 +78,10 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 // MT: rows of A resident per CTA (blockIdx.y selects the block).  Warp grid WM x WN over the MT x BN tile.
-template <int MT>
-__global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __grid_constant__ BgemmParams p)
+template <int MT, bool WIDE>
+__global__ void __launch_bounds__(BgCfg<MT, WIDE>::NW * 32, 1) bgemm_kernel(const __grid_constant__ BgemmParams p)
 {
-    using Cfg = BgCfg<MT>;
+    using Cfg = BgCfg<MT, WIDE>;
     constexpr int NT = Cfg::NW * 32, BN = Cfg::BN, KC = Cfg::KC, ST = Cfg::ST;
     constexpr int WM = Cfg::WM, WN = Cfg::NW / WM;
     constexpr int TM = MT / WM;                        // warp tile rows (32 for MT = 256, else 16)
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __gr
     const int apitch = p.Kpad + 8;
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);                           // [MT][Kpad + 8]
     __nv_bfloat16* sX = sA + (size_t)MT * apitch;                                              // [ST][KC][XP]
-    __nv_bfloat16* sD = sX + (size_t)ST * KC * XP;                                             // [warps][TM][DP]
+    __nv_bfloat16* sD = sX + (size_t)ST * KC * XP;                                             // [warps][16][DP]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __gr
     // lane-dependent fragment addresses
     const int a_row = wm * TM + (lane & 15), a_kofs = (lane >> 4) * 8;
     const int b_krow = (lane & 15), b_nofs = wn * TN + (lane >> 4) * 8;
-    __nv_bfloat16* myD = sD + (size_t)warp * TM * DP;
+    __nv_bfloat16* myD = sD + (size_t)warp * 16 * DP;
 
     for (long long g = 0; g < total_chunks; ++g) {
         cp_async_wait<ST - 2>();
@@ -184,25 +192,26 @@ __global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __gr
             const int nt = (int)(item - bt * p.n_tiles);
             const long long bo = bt / p.b_inner, bi = bt - bo * p.b_inner;
             __nv_bfloat16* db = p.D + bo * p.d_bo + bi * p.d_bi;
-            __syncwarp();
+            constexpr int VPR = TN / 8;                    // 16-byte vectors per tile row
 #pragma unroll
-            for (int a = 0; a < MI; ++a)
+            for (int a = 0; a < MI; ++a) {                 // 16 rows at a time through the per-warp staging tile
+                __syncwarp();
 #pragma unroll
                 for (int b = 0; b < NI; ++b) {
-                    const int r = a * 16 + (lane >> 2), c = b * 8 + (lane & 3) * 2;
+                    const int r = lane >> 2, c = b * 8 + (lane & 3) * 2;
                     *reinterpret_cast<__nv_bfloat162*>(myD + r * DP + c) = __floats2bfloat162_rn(acc[a][b][0], acc[a][b][1]);
                     *reinterpret_cast<__nv_bfloat162*>(myD + (r + 8) * DP + c) = __floats2bfloat162_rn(acc[a][b][2], acc[a][b][3]);
                     acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
                 }
-            __syncwarp();
-            constexpr int VPR = TN / 8;                    // 16-byte vectors per tile row
-            for (int i = lane; i < TM * VPR; i += 32) {
-                const int r = i / VPR, v = i - r * VPR;
-                const int m = m_block * MT + wm * TM + r, n = nt * BN + wn * TN + v * 8;
-                if (m < p.M && n < p.N) {
-                    const int mo = m / p.m_inner, mi = m - mo * p.m_inner;
-                    *reinterpret_cast<uint4*>(db + mo * p.d_mo + mi * p.d_mi + n) =
-                        *reinterpret_cast<const uint4*>(myD + r * DP + v * 8);
+                __syncwarp();
+                for (int i = lane; i < 16 * VPR; i += 32) {
+                    const int r = i / VPR, v = i - r * VPR;
+                    const int m = m_block * MT + wm * TM + a * 16 + r, n = nt * BN + wn * TN + v * 8;
+                    if (m < p.M && n < p.N) {
+                        const int mo = m / p.m_inner, mi = m - mo * p.m_inner;
+                        *reinterpret_cast<uint4*>(db + mo * p.d_mo + mi * p.d_mi + n) =
+                            *reinterpret_cast<const uint4*>(myD + r * DP + v * 8);
+                    }
                 }
             }
         }
@@ -210,38 +219,46 @@ __global__ void __launch_bounds__(BgCfg<MT>::NW * 32, 1) bgemm_kernel(const __gr
     cp_async_wait<0>();
 }
 
-template <int MT> static size_t bgemm_smem_t(int Kpad)
+template <int MT, bool WIDE> static size_t bgemm_smem_t(int Kpad)
 {
-    using Cfg = BgCfg<MT>;
-    constexpr int TM = MT / Cfg::WM, TN = Cfg::BN / (Cfg::NW / Cfg::WM);
-    return ((size_t)MT * (Kpad + 8) + (size_t)Cfg::ST * Cfg::KC * (Cfg::BN + 8) + (size_t)Cfg::NW * TM * (TN + 8)) * 2;
+    using Cfg = BgCfg<MT, WIDE>;
+    constexpr int TN = Cfg::BN / (Cfg::NW / Cfg::WM);
+    return ((size_t)MT * (Kpad + 8) + (size_t)Cfg::ST * Cfg::KC * (Cfg::BN + 8) + (size_t)Cfg::NW * 16 * (TN + 8)) * 2;
 }
 
+// the resident-row count is chosen with the larger (WIDE) footprint so that both variants of a tile size fit
 static size_t bgemm_smem(int MT, int Kpad)
 {
     switch (MT) {
-    case 256: return bgemm_smem_t<256>(Kpad);
-    case 128: return bgemm_smem_t<128>(Kpad);
-    case 64: return bgemm_smem_t<64>(Kpad);
-    case 32: return bgemm_smem_t<32>(Kpad);
-    default: return bgemm_smem_t<16>(Kpad);
+    case 256: return std::max(bgemm_smem_t<256, false>(Kpad), bgemm_smem_t<256, true>(Kpad));
+    case 128: return std::max(bgemm_smem_t<128, false>(Kpad), bgemm_smem_t<128, true>(Kpad));
+    case 64: return bgemm_smem_t<64, false>(Kpad);
+    case 32: return bgemm_smem_t<32, false>(Kpad);
+    default: return bgemm_smem_t<16, false>(Kpad);
     }
 }
 
-template <int MT>
-static int launch_bgemm(BgemmParams p, int m_blocks, int sm_count, cudaStream_t st)
+template <int MT, bool WIDE>
+static int launch_bgemm_cfg(BgemmParams p, int m_blocks, int sm_count, cudaStream_t st)
 {
-    using Cfg = BgCfg<MT>;
-    const size_t smem = bgemm_smem_t<MT>(p.Kpad);
-    SEI_CUDA(allow_smem(bgemm_kernel<MT>, smem));
+    using Cfg = BgCfg<MT, WIDE>;
+    const size_t smem = bgemm_smem_t<MT, WIDE>(p.Kpad);
+    SEI_CUDA(allow_smem(bgemm_kernel<MT, WIDE>, smem));
     p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
     p.items *= p.n_tiles;                                   // caller passes items = batches
     const int by_threads = 2048 / (Cfg::NW * 32);
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min(4, by_threads), (size_t)227 * 1024 / (smem + 1024)));
     const long long per_block = std::max(1, sm_count * ctas_per_sm / m_blocks);
     dim3 grid((unsigned)std::min<long long>(p.items, per_block), (unsigned)m_blocks);
-    bgemm_kernel<MT><<<grid, Cfg::NW * 32, smem, st>>>(p);
+    bgemm_kernel<MT, WIDE><<<grid, Cfg::NW * 32, smem, st>>>(p);
     return finish_launch("bgemm_kernel");
+}
+
+template <int MT>
+static int launch_bgemm(const BgemmParams& p, int m_blocks, int sm_count, cudaStream_t st)
+{
+    if ((MT == 256 && p.N >= 128) || (MT == 128 && p.N >= 128)) return launch_bgemm_cfg<MT, true>(p, m_blocks, sm_count, st);
+    return launch_bgemm_cfg<MT, false>(p, m_blocks, sm_count, st);
 }
 
 }  // namespace sei

@@ -1002,3 +1002,103 @@ extern "C" int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* g
     colsum_final_kernel<<<(C * 50 + 31) / 32, 256, 0, st>>>(p.partial, gw, gb, gx, C * 50, C * 49);
     return finish_launch("colsum_final_kernel");
 }
+
+// ---------------------------------------------------------------- GELU (exact, erf form), bf16 elementwise
+// Reference ConvBlock.gelu = nn.GELU() (src/models/convolutional.py:41): 0.5 x (1 + erf(x / sqrt 2)).  The library
+// kernel is bound by erff's instruction count (it ran at half the HBM rate); erf is evaluated here with the
+// Abramowitz-Stegun 7.1.26 rational form (|error| < 1.5e-7, far below bf16 resolution): one MUFU.RCP, one MUFU.EX2 and
+// a degree-5 polynomial.  The backward kernel shares the exponential: gelu'(x) = Phi(x) + x phi(x).
+namespace sei {
+
+__device__ __forceinline__ void gelu_parts(float x, float& Phi, float& phi)
+{
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float e = __expf(-z * z);                                  // exp(-x^2 / 2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = fmaf(-poly * t, e, 1.0f);                  // erf(|x| / sqrt 2)
+    Phi = 0.5f * (1.0f + copysignf(erf_abs, x));
+    phi = 0.39894228040143268f * e;
+}
+
+// four independent 16-byte loads per thread before any arithmetic: one load in flight per thread left the kernel
+// at half the HBM rate (latency-bound)
+constexpr int kGeluUnroll = 4;
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec)
+{
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += step * kGeluUnroll) {
+        uint4 raw[kGeluUnroll];
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u)
+            if (i0 + u * step < nvec) raw[u] = __ldcs(x + i0 + u * step);
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u) {
+            if (i0 + u * step >= nvec) break;
+            float f[8];
+            unpack8(raw[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float Phi, phi;
+                gelu_parts(f[j], Phi, phi);
+                f[j] *= Phi;
+            }
+            __stcs(y + i0 + u * step, pack8(f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                       uint4* __restrict__ gx, long long nvec)
+{
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += step * kGeluUnroll) {
+        uint4 rx[kGeluUnroll], rg[kGeluUnroll];
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u)
+            if (i0 + u * step < nvec) {
+                rx[u] = __ldcs(x + i0 + u * step);
+                rg[u] = __ldcs(gy + i0 + u * step);
+            }
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u) {
+            if (i0 + u * step >= nvec) break;
+            float f[8], g[8];
+            unpack8(rx[u], f);
+            unpack8(rg[u], g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float Phi, phi;
+                gelu_parts(f[j], Phi, phi);
+                g[j] *= fmaf(f[j], phi, Phi);
+            }
+            __stcs(gx + i0 + u * step, pack8(g));
+        }
+    }
+}
+
+}  // namespace sei
+
+// y = gelu(x) (gy == NULL) or gx = gy * gelu'(x); n bf16 elements, n % 8 == 0, 16-byte aligned
+extern "C" int sei_gelu_bf16(const void* x, const void* gy, void* out, long long n, void* stream)
+{
+    SEI_REQUIRE(x && out, "null pointer argument");
+    SEI_REQUIRE(n >= 0 && n % 8 == 0, "element count %lld must be a multiple of 8", n);
+    SEI_REQUIRE(aligned16(x) && aligned16(out) && (!gy || aligned16(gy)), "operands must be 16-byte aligned");
+    if (n == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const long long nvec = n / 8;
+    const unsigned grid = (unsigned)std::min<long long>((nvec + 255) / 256, (long long)dp.sm_count * 16);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gy)
+        gelu_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(gy), static_cast<uint4*>(out), nvec);
+    else
+        gelu_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), nvec);
+    return finish_launch(gy ? "gelu_bwd_kernel" : "gelu_fwd_kernel");
+}

@@ -188,7 +188,7 @@ class ConvBlock(Module):
             x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
-        x1 = self.gelu(x1)
+        x1 = ops.gelu(x1) if ops.gelu_supported(x1) else self.gelu(x1)
         x1 = self.conv3(x1)
         return x + x1
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sei_dwconv7_workspace_bytes": (C.c_longlong, [_i]),
     "sei_dwconv7_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sei_dwconv7_wgrad_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sei_gelu_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
     "sei_bgemm_tile_rows": (C.c_int, [_i, _i]),
     "sei_bgemm_bf16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _ll, _ll, _i, _ll, _ll, _ll, _ll, _i, _ll, _ll,
                                  _vp]),

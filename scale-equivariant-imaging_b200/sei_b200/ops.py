@@ -429,6 +429,36 @@ def dwconv7(x_bhwc, weight, bias):
     return _DwConv7.apply(x_bhwc, weight, bias)
 
 
+def gelu_supported(x):
+    """dense (any permutation of a contiguous block) CUDA bf16 tensor with a multiple of 8 elements"""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.numel() % 8 == 0
+            and (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)))
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.empty_like(x)                 # preserves x's (dense) strides: element order in memory is the same
+        with torch.cuda.device(x.device):
+            check(_lib.load().sei_gelu_bf16(_ptr(x), None, _ptr(y), x.numel(), _stream(x)))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        if gy.stride() != x.stride():
+            gy = torch.empty_like(x).copy_(gy)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(_lib.load().sei_gelu_bf16(_ptr(x), _ptr(gy), _ptr(gx), x.numel(), _stream(x)))
+        return gx
+
+
+def gelu(x):
+    return _Gelu.apply(x)
+
+
 def layer_norm_cl(x_rows, gamma, beta, eps):
     return _LayerNormCL.apply(x_rows, gamma, beta, eps)
 

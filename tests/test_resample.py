@@ -209,3 +209,29 @@ def test_dwconv7_matches_torch(dev, B, H, W, C):
     assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).cpu().numpy()) < 6e-3
     assert rel_err(w.grad.cpu().numpy(), w2.grad.cpu().numpy()) < 2e-3
     assert rel_err(b.grad.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+def test_gelu_matches_torch(dev):
+    """erf-form GELU with the A&S 7.1.26 erf (|err| < 1.5e-7) vs torch's exact GELU in fp32 on the same bf16 input"""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(3)
+    x = torch.cat([torch.randn(4096 * 8, device=dev) * 3, torch.linspace(-12, 12, 4096, device=dev)]).bfloat16()
+    gy = torch.randn_like(x)
+    xa = x.clone().requires_grad_(True)
+    y = ops.gelu(xa)
+    y.backward(gy)
+    xr = x.float().requires_grad_(True)
+    yr = F.gelu(xr)
+    yr.backward(gy.float())
+    # element-wise: one bf16 rounding of the exact value (2^-8 relative) plus the erf approximation's 1.5e-7 * |x|
+    assert bool(torch.all((y.detach().float() - yr.detach()).abs() <= 2.0 ** -8 * yr.detach().abs() + 2e-6))
+    assert rel_err(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) < 4e-3
+    assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.cpu().numpy()) < 6e-3
+    # channels-last dense layout goes through unchanged
+    x4 = torch.randn(2, 16, 5, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    assert ops.gelu_supported(x4)
+    y4 = ops.gelu(x4)
+    assert y4.stride() == x4.stride()
+    assert rel_err(y4.float().cpu().numpy(), F.gelu(x4.float()).cpu().numpy()) < 4e-3
