@@ -509,6 +509,212 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------- CTA-pair kernel (cta_group::2)
+// A 128 x 256 tile per SM reads (128 + 256) x 16 bf16 = 12 KB of shared memory per UMMA, 192 B per tensor-core clock
+// against the 128 B/clk an SM's shared memory delivers: the single-CTA kernel above tops out near 70 % of the tensor
+// peak (measured: 1.20 of 1.69 PFLOP/s).  Here two CTAs of a cluster (one TPC) share a 256 x 256 tile: each stages
+// its own 128 rows of A and HALF of B (128 of the 256 columns), the leader CTA issues one tcgen05.mma.cta_group::2
+// (M = 256) that reads both halves in place, and each CTA's TMEM receives its 128 rows of the accumulator.  Shared
+// memory traffic per CTA drops to 8 KB per UMMA = 128 B/clk.
+//   * both CTAs run a TMA producer; every load signals the LEADER's full barrier (peer bit cleared), which expects
+//     the bytes of both CTAs;
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster arrives on the empty / accumulator-full barriers of BOTH CTAs;
+//   * the epilogue threads of both CTAs arrive on the leader's accumulator-empty barrier (256 arrivals).
+// TN operands (K contiguous), bf16 output through the TMA-store epilogue, no split-K: the forward and input-gradient
+// GEMMs of the deep layers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask),
+                   "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all earlier MMAs of this thread completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
+{
+    constexpr int BM = kGemmBM, BK = kGemmBK, BN = 256, BNH = 128;      // per CTA: 128 rows of A, 128 columns of B
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;               // two accumulator stages of 256 fp32 columns
+    constexpr uint32_t SLAB_BYTES = 32 * 128;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;
+    const int nk = (p.K + BK - 1) / BK;
+    const long long total = (long long)tiles_m * tiles_n;
+    const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 256);           // the epilogue threads of both CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of both CTAs initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own rows of A, own half of B; completion on the leader's barrier =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long w = cluster_id; w < total; w += n_clusters) {
+                const int m0 = (int)(w % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(w / tiles_m) * BN + (int)rank * BNH;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
+                    tma_load_2d_2sm(a_dst, &map_a, kb * BK, m0, &full_bar[s]);
+                    tma_load_2d_2sm(a_dst + A_BYTES, &map_b, kb * BK, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, false);
+            uint32_t it = 0, tcount = 0;
+            for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
+                const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+                if (tcount >= 2) mbar_wait(&tmem_empty_bar[acc], (acc_use - 1) & 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[s]);              // frees this stage in both CTAs
+                }
+                umma_commit_2sm(&tmem_full_bar[acc]);            // accumulator complete: both epilogues
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows of the accumulator =====
+        const int q = warp & 3;
+        uint32_t tcount = 0, chunk_count = 0;
+        unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * 2 * SLAB_BYTES;
+        for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
+            const int m0 = (int)(w % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(w / tiles_m) * BN;
+            const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            mbar_wait(&tmem_full_bar[acc], acc_use & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 64) {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
+                tmem_ld_wait();
+                unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+                const int col0 = n0 + c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int cc = 8 * j + e;
+                        v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
+                        if (p.bias && col0 + cc < p.N) v[e] += __ldg(p.bias + col0 + cc);
+                    }
+                    uint4 pk;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
+                                   t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                    *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
+                    tma_store_2d(&map_d, slab, col0, m0 + q * 32);
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_leader(&tmem_empty_bar[acc]);       // this thread is done reading the accumulator stage
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // the peer's shared memory / barriers stay valid until both are done
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -648,6 +854,20 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
         p.kb_per_split = (nk + want - 1) / want;
         p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
         if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+    }
+    // CTA-pair kernel for the large bf16-output TN products (forward / input gradient of the deep layers)
+    const char* no2 = getenv("SEI_GEMM_NO_2CTA");
+    if (bn == 256 && p.tma_store && p.splits == 1 && M >= 256 && N >= 256 && dp.sm_count >= 2 && !(no2 && *no2 == '1')) {
+        constexpr int ST2 = 5;
+        CUtensorMap mb2;
+        rc = make_map_bf16(&mb2, B, N, K, ldb, 128);
+        if (rc) return rc;
+        constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
+        const long long ctiles = ((M + 255) / 256) * (long long)((N + 255) / 256);
+        const unsigned grid = 2u * (unsigned)std::min<long long>(ctiles, dp.sm_count / 2);
+        SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2>, smem2));
+        gemm_bf16_tn_2cta_kernel<ST2><<<grid, kGemmThreads, smem2, st>>>(ma, mb2, md, p);
+        return finish_launch("gemm_bf16_tn_2cta_kernel");
     }
     switch (bn) {
     case 32: return launch_gemm<32, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);

@@ -29,13 +29,31 @@ def test_gemm_matches_fp32_reference(dev, M, N, K, out_dtype):
     ref = a.float() @ b.float().t() + bias
     for tile_n in (0, 32, 64, 128, 256):
         d = ops.gemm_bf16_tn(a, b, bias, out_dtype=out_dtype, tile_n=tile_n)
-        assert last_kernel() == "gemm_bf16_tn_kernel"
+        assert last_kernel() in ("gemm_bf16_tn_kernel", "gemm_bf16_tn_2cta_kernel")
         assert d.dtype == out_dtype and d.shape == (M, N)
         err = (d.float() - ref).abs().max() / ref.abs().max()
         tol = 2e-5 if out_dtype == torch.float32 else 6e-3
         assert float(err) < tol, (tile_n, float(err))
     d0 = ops.gemm_bf16_tn(a, b, None, out_dtype=torch.float32)
     assert float((d0 - (ref - bias)).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (300, 264, 72), (8192, 2048, 1024), (4100, 8192, 520),
+                                   (257, 256, 8)])
+def test_gemm_cta_pair_kernel(dev, M, N, K):
+    """large bf16-output products run on the cta_group::2 kernel (two CTAs share a 256 x 256 tile); ragged edges are
+    clipped by the tensor maps"""
+    from sei_b200 import ops, last_kernel
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref = a.float() @ b.float().t() + bias
+    d = ops.gemm_bf16_tn(a, b, bias, out_dtype=torch.bfloat16)
+    assert last_kernel() == "gemm_bf16_tn_2cta_kernel"
+    assert float((d.float() - ref).abs().max() / ref.abs().max()) < 6e-3
+    d2 = ops.gemm_bf16_tn(a, b, bias, out_dtype=torch.bfloat16)          # persistent barriers / TMEM reused correctly
+    assert torch.equal(d, d2)
 
 
 def test_gemm_strided_operands(dev):
