@@ -27,88 +27,161 @@ struct ScaleParams {
     const float* center;
     int C, S, TH, nbands, SRC_MAX;
     float two_over_S;
+    long long total_bands;
 };
 
-template <int ST>
+// de-interleaved column layout of the vertical-pass result: even columns first, odd columns HALF floats later
+// (HALF = S/2 + 16: the two halves start 16 banks apart).  At rate 0.5 the horizontal gather of 32 neighbouring
+// outputs reads every second column -- a 2-way bank conflict in a plain row (ncu: 3.6 M conflicts on 4.4 M shared
+// loads, the shared-memory pipe at 74 %) and consecutive words here.
+__host__ __device__ constexpr int scale_tmp_half(int S) { return S / 2 + 16; }
+__host__ __device__ constexpr int scale_tmp_pitch(int S) { return 2 * scale_tmp_half(S); }
+__device__ __forceinline__ int scale_tmp_pos(int c, int S) { return (c >> 1) + (c & 1) * scale_tmp_half(S); }
+
+// Persistent, double-buffered: a CTA walks bands blockIdx.x, blockIdx.x + gridDim.x, ...  While band i is resampled,
+// warp 0 has already computed the row taps of band i+1, derived its source-row range with warp shuffles and issued
+// the bulk copy into the other staging buffer, and the remaining warps have written its column taps; the first
+// version loaded, waited and computed strictly in sequence (17 % of its stall samples sat in the mbarrier wait).
+template <int ST, int THT>
 __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __grid_constant__ ScaleParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    __shared__ int s_lo, s_hi;
+    __shared__ uint64_t bar[2];
+    __shared__ int s_lo[2], s_n[2], s_img[2];
 
     const int S = ST ? ST : p.S;
-    const int band = blockIdx.x % p.nbands;
-    const long long plane = blockIdx.x / p.nbands;
-    const int b = (int)(plane / p.C);
-    const int r0 = band * p.TH;
-    const int th = min(p.TH, S - r0);
-
-    float* sSrc = reinterpret_cast<float*>(smem_raw);                    // [SRC_MAX][S]
-    float* sTmp = sSrc + (size_t)p.SRC_MAX * S;                           // [TH][S]
-    AxisTap* colT = reinterpret_cast<AxisTap*>(sTmp + (size_t)p.TH * S);  // [S]
-    AxisTap* rowT = colT + S;                                             // [TH]
-
-    const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
-    const float cx = __ldg(p.center + 2 * b), cy = __ldg(p.center + 2 * b + 1);
-    const float* xplane = p.x + (size_t)plane * S * S;
+    const int TH = THT ? THT : p.TH;
+    const int TP = scale_tmp_pitch(S);
+    float* sSrc = reinterpret_cast<float*>(smem_raw);                         // [2][SRC_MAX][S]
+    float* sTmp = sSrc + (size_t)2 * p.SRC_MAX * S;                            // [TH][TP]
+    AxisTap* colT = reinterpret_cast<AxisTap*>(sTmp + (size_t)TH * TP);      // [2][S]   (idx = de-interleaved position)
+    AxisTap* rowT = colT + 2 * S;                                              // [2][TH]  (idx relative to the staged rows)
+    const long long total = p.total_bands;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
-        s_lo = S;
-        s_hi = -1;
     }
     __syncthreads();
-    if (threadIdx.x < th) {
-        AxisTap t;
-        scale_axis_tap(r0 + threadIdx.x, S, p.two_over_S, inv_rate, cy, t);
-        rowT[threadIdx.x] = t;
-        const int lo = min(min(t.idx[0], t.idx[1]), min(t.idx[2], t.idx[3]));
-        const int hi = max(max(t.idx[0], t.idx[1]), max(t.idx[2], t.idx[3]));
-        atomicMin(&s_lo, lo);
-        atomicMax(&s_hi, hi);
-    }
-    __syncthreads();
-    const int lo = s_lo, nsrc = s_hi - s_lo + 1;
-    const bool staged = nsrc <= p.SRC_MAX;
-    if (staged && threadIdx.x == 0) {
-        const uint32_t row_bytes = (uint32_t)S * 4u;
-        mbar_arrive_expect_tx(&bar, (uint32_t)nsrc * row_bytes);
-        bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sSrc), reinterpret_cast<const unsigned char*>(xplane),
-                                S, row_bytes, lo, nsrc, &bar);
-    }
-    for (int j = threadIdx.x; j < S; j += kScaleThreads) {
-        AxisTap t;
-        scale_axis_tap(j, S, p.two_over_S, inv_rate, cx, t);
-        colT[j] = t;
-    }
-    if (staged) mbar_wait(&bar, 0);
 
-    // ---- vertical pass: sTmp[r][c] = sum_a wy[r][a] * src[iy[r][a]][c]
-    if (staged) {
-        if (threadIdx.x < th) {
+    // every CTA owns a contiguous range of bands, so consecutive bands mostly belong to the same image and share
+    // their column taps (a tap costs ~120 instructions -- reflections need integer divisions -- against ~10 per
+    // output of the passes themselves): colT[slot] is recomputed only when the image changes
+    const long long w_begin = total * blockIdx.x / gridDim.x, w_end = total * (blockIdx.x + 1) / gridDim.x;
+    int cur_img = -1, cur_slot = 1;
+
+    // taps of band w into buffer `buf`; warp 0: row taps, source range, bulk copy.  Requires sSrc[buf] to be free.
+    auto prepare = [&](long long w, int buf) {
+        const int band = (int)(w % p.nbands);
+        const long long plane = w / p.nbands;
+        const int b = (int)(plane / p.C);
+        const int r0 = band * TH, th = min(TH, S - r0);
+        const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
+        if (warp == 0) {
+            const float cy = __ldg(p.center + 2 * b + 1);
+            AxisTap t;
+            int lo = S, hi = -1;
+            if (lane < th) {
+                scale_axis_tap(r0 + lane, S, p.two_over_S, inv_rate, cy, t);
+                lo = min(min(t.idx[0], t.idx[1]), min(t.idx[2], t.idx[3]));
+                hi = max(max(t.idx[0], t.idx[1]), max(t.idx[2], t.idx[3]));
+            }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) rowT[threadIdx.x].idx[a] -= lo;
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            const int nsrc = hi - lo + 1;
+            const bool staged = nsrc <= p.SRC_MAX;
+            if (lane < th) {
+                if (staged) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) t.idx[a] -= lo;
+                }
+                rowT[buf * TH + lane] = t;
+            }
+            if (lane == 0) {
+                s_lo[buf] = lo;
+                s_n[buf] = staged ? nsrc : 0;
+                if (staged) {
+                    const uint32_t row_bytes = (uint32_t)S * 4u;
+                    fence_proxy_async();          // the buffer was read by generic loads two bands ago
+                    mbar_arrive_expect_tx(&bar[buf], (uint32_t)nsrc * row_bytes);
+                    bulk_load_rows_circular(reinterpret_cast<unsigned char*>(sSrc + (size_t)buf * p.SRC_MAX * S),
+                                            reinterpret_cast<const unsigned char*>(p.x + (size_t)plane * S * S), S, row_bytes,
+                                            lo, nsrc, &bar[buf]);
+                }
+            }
         }
-        __syncthreads();
-        scale_vpass<kScaleThreads, ST>(sSrc, sTmp, S, th, rowT);
-    } else {
-        __syncthreads();
-        scale_vpass<kScaleThreads, ST>(xplane, sTmp, S, th, rowT);
-    }
-    __syncthreads();
+        if (b != cur_img) {                // uniform across the CTA
+            cur_img = b;
+            cur_slot ^= 1;
+            if (warp != 0) {
+                const float cx = __ldg(p.center + 2 * b);
+                for (int j = threadIdx.x - 32; j < S; j += kScaleThreads - 32) {
+                    AxisTap t;
+                    scale_axis_tap(j, S, p.two_over_S, inv_rate, cx, t);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) t.idx[a] = scale_tmp_pos(t.idx[a], S);
+                    colT[cur_slot * S + j] = t;
+                }
+            }
+        }
+        if (threadIdx.x == 0) s_img[buf] = cur_slot;
+    };
 
-    // ---- horizontal pass: out[r][j] = sum_b wx[j][b] * sTmp[r][ix[j][b]]
-    float* oplane = p.out + (size_t)plane * S * S;
-    const int ngrp = max(1, kScaleThreads / S);
-    const int grp = threadIdx.x / S;
-    if (grp < ngrp) {
-        for (int j = threadIdx.x - grp * S; j < S; j += kScaleThreads) {
-            const AxisTap t = colT[j];
-#pragma unroll 4
-            for (int r = grp; r < th; r += ngrp)
-                __stcs(oplane + (size_t)(r0 + r) * S + j, scale_hgather(sTmp + r * S, t));
+    if (w_begin < w_end) prepare(w_begin, 0);
+    uint32_t phases = 0u;                  // bit b: parity of buffer b's barrier (a phase completes only for staged bands)
+    int it = 0;
+    for (long long w = w_begin; w < w_end; ++w, ++it) {
+        const int buf = it & 1;
+        if (w + 1 < w_end) prepare(w + 1, buf ^ 1);
+        __syncthreads();                                        // taps of this band (written one iteration ago) visible
+        const int band = (int)(w % p.nbands);
+        const long long plane = w / p.nbands;
+        const int r0 = band * TH, th = min(TH, S - r0);
+        const bool staged = s_n[buf] > 0;
+        const AxisTap* rT = rowT + buf * TH;
+        const float* src = staged ? sSrc + (size_t)buf * p.SRC_MAX * S : p.x + (size_t)plane * S * S;
+        if (staged) {
+            mbar_wait(&bar[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
         }
+
+        // ---- vertical pass: sTmp[r][pos(c)] = sum_a wy[r][a] * src[iy[r][a]][c]
+        const int CW = S >> 2;
+        for (int item = threadIdx.x; item < th * CW; item += kScaleThreads) {
+            const int r = item / CW, c4 = item - r * CW;
+            const AxisTap t = rT[r];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t.idx[a] * S + 4 * c4);
+                acc.x = fmaf(t.w[a], v.x, acc.x); acc.y = fmaf(t.w[a], v.y, acc.y);
+                acc.z = fmaf(t.w[a], v.z, acc.z); acc.w = fmaf(t.w[a], v.w, acc.w);
+            }
+            float* d = sTmp + (size_t)r * TP + 2 * c4;
+            *reinterpret_cast<float2*>(d) = make_float2(acc.x, acc.z);                               // columns 4c4, 4c4+2
+            *reinterpret_cast<float2*>(d + scale_tmp_half(S)) = make_float2(acc.y, acc.w);           // columns 4c4+1, 4c4+3
+        }
+        __syncthreads();
+
+        // ---- horizontal pass: out[r][j] = sum_b wx[j][b] * sTmp[r][pos(ix[j][b])]
+        float* oplane = p.out + (size_t)plane * S * S + (size_t)r0 * S;
+        const AxisTap* cT = colT + s_img[buf] * S;
+        for (int j = threadIdx.x; j < S; j += kScaleThreads) {
+            const AxisTap t = cT[j];
+            if (THT && th == THT) {            // full band: fully unrolled, every address is base + immediate
+#pragma unroll
+                for (int r = 0; r < (THT ? THT : 1); ++r) __stcs(oplane + (size_t)r * S + j, scale_hgather(sTmp + (size_t)r * TP, t));
+            } else {
+#pragma unroll 4
+                for (int r = 0; r < th; ++r) __stcs(oplane + (size_t)r * S + j, scale_hgather(sTmp + (size_t)r * TP, t));
+            }
+        }
+        __syncthreads();                                        // sTmp and the staging buffer are free again
     }
 }
 
@@ -196,22 +269,26 @@ __global__ void scale_params_kernel(const float* u_rate, const float* u_center, 
 // staging rows for a band of th output rows at the smallest rate the reference samples (0.5)
 static int scale_src_rows(int th) { return 2 * th + 6; }
 
+static size_t scale_band_smem(int th, int S)
+{
+    return ((size_t)2 * scale_src_rows(th) * S + (size_t)th * scale_tmp_pitch(S)) * 4 + (size_t)(2 * S + 2 * th) * sizeof(AxisTap);
+}
+
+// band height: 16 rows (two staging buffers of 38 rows + taps = 111 KB at S = 256: two CTAs per SM); SEI_SCALE_TH overrides
 int scale_pick_band_rows(int S, int smem_optin, size_t* smem_out)
 {
-    const size_t budget = std::min((size_t)smem_optin, (size_t)110 * 1024);
+    const size_t budget = std::min((size_t)smem_optin, (size_t)112 * 1024);
     int best = 0;
-    for (int th = 8; th <= 64; th += 8) {
-        const size_t need = ((size_t)scale_src_rows(th) + th) * S * 4 + (size_t)(S + th) * sizeof(AxisTap);
-        if (need <= budget) best = th;
-    }
+    for (int th = 8; th <= 16; th += 8)
+        if (scale_band_smem(th, S) <= budget) best = th;
+    if (best == 0 && scale_band_smem(8, S) <= (size_t)smem_optin) best = 8;
     if (const char* e = getenv("SEI_SCALE_TH")) {     // tuning override
         const int f = atoi(e);
-        if (f >= 8 && f % 8 == 0 && ((size_t)scale_src_rows(f) + f) * S * 4 + (size_t)(S + f) * sizeof(AxisTap) <= (size_t)smem_optin)
-            best = f;
+        if (f >= 8 && f % 8 == 0 && f <= 32 && scale_band_smem(f, S) <= (size_t)smem_optin) best = f;
     }
     if (best == 0) return 0;
     best = std::min(best, ((S + 7) / 8) * 8);
-    *smem_out = ((size_t)scale_src_rows(best) + best) * S * 4 + (size_t)(S + best) * sizeof(AxisTap);
+    *smem_out = scale_band_smem(best, S);
     return best;
 }
 
@@ -241,16 +318,18 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
         p.x = x; p.out = out; p.rate = rate; p.center = center;
         p.C = C; p.S = S; p.TH = TH; p.nbands = (S + TH - 1) / TH; p.SRC_MAX = scale_src_rows(TH);
         p.two_over_S = two_over_S;
-        const unsigned grid = (unsigned)(planes * p.nbands);
-        if (S == 256) {
-            SEI_CUDA(allow_smem(scale_band_kernel<256>, smem));
-            scale_band_kernel<256><<<grid, kScaleThreads, smem, st>>>(p);
-        } else if (S == 512) {
-            SEI_CUDA(allow_smem(scale_band_kernel<512>, smem));
-            scale_band_kernel<512><<<grid, kScaleThreads, smem, st>>>(p);
+        p.total_bands = planes * p.nbands;
+        const int ctas_per_sm = std::max(1, std::min(2, (int)((size_t)227 * 1024 / (smem + 1024))));
+        const unsigned grid = (unsigned)std::min<long long>(p.total_bands, (long long)dp.sm_count * ctas_per_sm);
+        if (S == 256 && TH == 16) {
+            SEI_CUDA(allow_smem(scale_band_kernel<256, 16>, smem));
+            scale_band_kernel<256, 16><<<grid, kScaleThreads, smem, st>>>(p);
+        } else if (S == 512 && TH == 8) {
+            SEI_CUDA(allow_smem(scale_band_kernel<512, 8>, smem));
+            scale_band_kernel<512, 8><<<grid, kScaleThreads, smem, st>>>(p);
         } else {
-            SEI_CUDA(allow_smem(scale_band_kernel<0>, smem));
-            scale_band_kernel<0><<<grid, kScaleThreads, smem, st>>>(p);
+            SEI_CUDA(allow_smem(scale_band_kernel<0, 0>, smem));
+            scale_band_kernel<0, 0><<<grid, kScaleThreads, smem, st>>>(p);
         }
         return finish_launch("scale_band_kernel");
     }
