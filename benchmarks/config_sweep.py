@@ -22,7 +22,7 @@ CONFIGS = [
     # name, task, kernel, sr, method, transforms, measurement size, batch per GPU
     ("cfg2 deblur Gaussian_R2 proposed 256 b32", "deblurring", "Gaussian_R2", None, "proposed", "Scaling_Transforms", 256, 32),
     ("cfg3 SR x2 proposed 256 b8/GPU", "sr", None, 2, "proposed", "Scaling_Transforms", 256, 8),
-    ("cfg4 SR x4 proposed 256 b8", "sr", None, 4, "proposed", "Scaling_Transforms", 256, 8),
+    ("cfg4 SR x4 proposed 256 b2", "sr", None, 4, "proposed", "Scaling_Transforms", 256, 2),
     ("cfg4 deblur Box_R3 proposed 256 b32", "deblurring", "Box_R3", None, "proposed", "Scaling_Transforms", 256, 32),
     ("cfg5 supervised 512 b16", "deblurring", "Gaussian_R2", None, "supervised", "Scaling_Transforms", 512, 16),
     ("cfg5 css 512 b16", "deblurring", "Gaussian_R2", None, "css", "Scaling_Transforms", 512, 16),
@@ -59,7 +59,7 @@ def run(cfg, args, dev, rank, world):
         model = models.get_model(margs, physics=phys, device=dev).to(dev)
     else:
         model = ToyModel(rate=rate).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)
     reducer = parallel.GradAllReducer(model.parameters())
     torch.manual_seed(1 + rank)
     x = torch.rand(batch, 3, size * rate, size * rate, device=dev)

@@ -261,6 +261,11 @@ static int launch_bgemm(const BgemmParams& p, int m_blocks, int sm_count, cudaSt
     return launch_bgemm_cfg<MT, false>(p, m_blocks, sm_count, st);
 }
 
+int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int N, int Kpad, int rows_a,
+                        long long batches, int b_inner, long long x_bo, long long x_bi,
+                        int k_inner, long long x_ko, long long x_ki,
+                        long long d_bo, long long d_bi, int m_inner, long long d_mo, long long d_mi, cudaStream_t st);
+
 }  // namespace sei
 
 using namespace sei;
@@ -294,6 +299,13 @@ extern "C" int sei_bgemm_bf16(const void* A, const void* X, void* D, int M, int 
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
+    // tcgen05 / TMEM / TMA kernel (gemm.cu) for the shapes its tensor maps can express; mma.sync kernel otherwise
+    {
+        const int rows_a = ((M + tile_rows - 1) / tile_rows) * tile_rows;
+        rc = bgemm_tc_try_launch(A, X, D, M, K, N, Kpad, rows_a, batches, b_inner, x_bo, x_bi, k_inner, x_ko, x_ki,
+                                 d_bo, d_bi, m_inner, d_mo, d_mi, st);
+        if (rc != 1) return rc;
+    }
     BgemmParams p;
     p.A = static_cast<const __nv_bfloat16*>(A);
     p.X = static_cast<const __nv_bfloat16*>(X);

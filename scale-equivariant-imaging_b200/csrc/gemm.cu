@@ -715,6 +715,202 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
 }
 
+// ---------------------------------------------------------------- batched operator product on tcgen05
+// D_b[M, N] = A[M, K] * X_b[K, N]  (csrc/bgemm.cu; the CNN's ideal resamplers).  The operator A (M <= 256 rows per
+// CTA, M * K <= 64 K elements) is loaded ONCE per persistent CTA into shared memory as K-major SWIZZLE_128B tiles and
+// is the UMMA "A" operand; X_b is the "B" operand read in place as an MN-major tile (its rows are the contraction
+// index, its columns contiguous), streamed through a TMA ring; the accumulators (one 128-row block per 128 rows of A,
+// double-buffered) live in TMEM and leave through the swizzled-slab / TMA-store epilogue.  Batch entries and the
+// split row indices of X and D (r = ro * inner + ri) are dimensions of 5-D tensor maps, so the two-term resampler
+// intermediate [B, 2, H, W', C] is read and written in place.  HBM-bound by construction: a 256 x 128 x 256 item is
+// 1 k tensor-core clocks for 128 KB of traffic.
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+                   "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+// instruction descriptor: A K-major, B MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_kmn(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct BgemmTcParams {
+    int M, K, N;                 // logical sizes
+    int mb, kb;                  // 128-row blocks of A per CTA (1 or 2), 64-column k-blocks
+    int n_tiles, b_inner;
+    int k_inner, m_inner;        // split sizes of the X rows / D rows
+    long long items;             // batches * n_tiles
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ BgemmTcParams p)
+{
+    constexpr int BK = kGemmBK;
+    constexpr uint32_t A_TILE = 128 * BK * 2, X_STAGE = BN * BK * 2, SLAB_BYTES = 32 * 128;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2], a_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* sA = smem_raw + (((raw + 1023u) & ~1023u) - raw);           // [mb][kb] tiles of 128 x 64, K-major SW128
+    unsigned char* sX = sA + (size_t)p.mb * p.kb * A_TILE;                      // [STAGES][BN/64] boxes of 64 k x 64 n
+    unsigned char* slabs0 = sX + (size_t)STAGES * X_STAGE;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_row0 = blockIdx.y * p.mb * 128;
+    const uint32_t tmem_cols = 2u * (uint32_t)p.mb * BN;                        // 128 .. 512: a power of two
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_d);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 128);
+        }
+        mbar_init(&a_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    // decode of the k-th 64-row block of X / a 32-row group of D into split coordinates
+    const int kbox_i = min(64, p.k_inner);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident operator
+            mbar_arrive_expect_tx(&a_bar, (uint32_t)(p.mb * p.kb) * A_TILE);
+            for (int mb = 0; mb < p.mb; ++mb)
+                for (int kb = 0; kb < p.kb; ++kb)
+                    tma_load_2d(sA + (size_t)(mb * p.kb + kb) * A_TILE, &map_a, kb * BK, m_row0 + mb * 128, &a_bar);
+            uint32_t it = 0;
+            for (long long w = blockIdx.x; w < p.items; w += gridDim.x) {
+                const long long bt = w / p.n_tiles;
+                const int n0 = (int)(w - bt * p.n_tiles) * BN;
+                const int bo = (int)(bt / p.b_inner), bi = (int)(bt - (long long)bo * p.b_inner);
+                for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&full_bar[s], X_STAGE);
+                    const int k0 = kb * BK;
+                    const int ko = k0 / p.k_inner, ki = k0 - ko * p.k_inner;
+#pragma unroll
+                    for (int nb = 0; nb < BN / 64; ++nb)
+                        tma_load_5d(sX + (size_t)s * X_STAGE + nb * (BK * 128), &map_x, n0 + 64 * nb, ki, ko, bi, bo, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_kmn(128, BN);
+            mbar_wait(&a_bar, 0);
+            tc_fence_after();
+            uint32_t it = 0, tcount = 0;
+            for (long long w = blockIdx.x; w < p.items; w += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+                if (tcount >= 2) mbar_wait(&tmem_empty_bar[acc], (acc_use - 1) & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t dx = umma_smem_desc_mn_sw128(smem_u32(sX + (size_t)s * X_STAGE), BK * 128);
+                    for (int mb = 0; mb < p.mb; ++mb) {
+                        const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + (size_t)(mb * p.kb + kb) * A_TILE));
+                        const uint32_t tmem_d = tmem_base + (acc * (uint32_t)p.mb + (uint32_t)mb) * BN;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), dx + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        uint32_t tcount = 0, chunk_count = 0;
+        unsigned char* slabs = slabs0 + (size_t)(warp - 2) * 2 * SLAB_BYTES;
+        const int mbox_i = min(32, p.m_inner);
+        for (long long w = blockIdx.x; w < p.items; w += gridDim.x, ++tcount) {
+            const long long bt = w / p.n_tiles;
+            const int n0 = (int)(w - bt * p.n_tiles) * BN;
+            const int bo = (int)(bt / p.b_inner), bi = (int)(bt - (long long)bo * p.b_inner);
+            const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            mbar_wait(&tmem_full_bar[acc], acc_use & 1);
+            tc_fence_after();
+            for (int mb = 0; mb < p.mb; ++mb) {
+                const int m0 = m_row0 + mb * 128 + q * 32;                      // first of this warp's 32 rows
+                const int mo = m0 / p.m_inner, mi = m0 - mo * p.m_inner;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    uint32_t r0[32], r1[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * (uint32_t)p.mb + (uint32_t)mb) * BN + (uint32_t)c;
+                    tmem_ld_32x32(taddr, r0);
+                    tmem_ld_32x32(taddr + 32, r1);
+                    tmem_ld_wait();
+                    unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int cc = 8 * j + e;
+                            v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
+                        }
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
+                                       t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && n0 + c < p.N && m0 < p.M) {
+                        tma_store_5d(&map_d, slab, n0 + c, mi, mo, bi, bo);
+                        bulk_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (lane == 0) bulk_wait_all();
+        (void)mbox_i;
+    }
+    (void)kbox_i;
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -805,6 +1001,81 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
         gemm_bf16_tn_kernel<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, md, p);
     }
     return finish_launch("gemm_bf16_tn_kernel");
+}
+
+// 5-D bf16 tensor map {n, ri, ro, bi, bo}: element (n, r = ro * r_inner + ri, batch = bo * b_inner + bi) of a tensor whose
+// rows / batch entries are split with two strides each; box = 64 n x box_ri x box_ro x 1 x 1, SWIZZLE_128B.
+static int make_map_bf16_5d(CUtensorMap* map, const void* base, long long n, int r_inner, long long r_outer, int b_inner,
+                            long long b_outer, long long s_ri, long long s_ro, long long s_bi, long long s_bo,
+                            int box_ri, int box_ro)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    SEI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[5] = {(cuuint64_t)n, (cuuint64_t)r_inner, (cuuint64_t)r_outer, (cuuint64_t)b_inner, (cuuint64_t)b_outer};
+    // unused dimensions (size 1) still need a valid (non-zero, 16-byte multiple) stride
+    auto st = [](long long v) { return (cuuint64_t)(v > 0 ? v : 8) * 2; };
+    cuuint64_t strides[4] = {st(s_ri), st(s_ro), st(s_bi), st(s_bo)};
+    cuuint32_t box[5] = {64u, (cuuint32_t)box_ri, (cuuint32_t)box_ro, 1u, 1u};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SEI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (5-D) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static bool pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Returns 1 if the tcgen05 kernel does not take this shape (the caller then uses the mma.sync kernel), 0 on a
+// successful launch, or an error code.
+int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int N, int Kpad, int rows_a,
+                        long long batches, int b_inner, long long x_bo, long long x_bi,
+                        int k_inner, long long x_ko, long long x_ki,
+                        long long d_bo, long long d_bi, int m_inner, long long d_mo, long long d_mi, cudaStream_t st)
+{
+    const char* off = getenv("SEI_BGEMM_NO_TC");
+    if (off && *off == '1') return 1;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    if (dp.cc_major != 10) return 1;
+    // shape rules: see the kernel comment
+    const int mb_total = (M + 127) / 128;
+    const int mb = std::min(2, mb_total);                                   // 128-row blocks per CTA
+    const int kb = Kpad / 64;
+    // (rows of A beyond rows_a are out of the tensor map's bounds: TMA zero-fills them)
+    if ((long long)mb * kb * 16384 > 128 * 1024) return 1;
+    if (N % 8 != 0 || K % 16 != 0 || batches % b_inner != 0) return 1;
+    if (!(k_inner % 64 == 0 || (pow2(k_inner) && k_inner < 64)) || K % k_inner != 0) return 1;
+    if (!(m_inner % 32 == 0 || (pow2(m_inner) && m_inner < 32)) || M % m_inner != 0) return 1;
+    if (M % 32 != 0 && M > 32) return 1;
+    if (x_ki <= 0 || d_mi <= 0) return 1;
+    const int bn = N <= 64 ? 64 : 128;
+    CUtensorMap ma, mx, md;
+    rc = make_map_bf16(&ma, A, rows_a, Kpad, Kpad, 128);
+    if (rc) return rc;
+    const int kbox_i = std::min(64, k_inner), mbox_i = std::min(32, m_inner);
+    rc = make_map_bf16_5d(&mx, X, N, k_inner, K / k_inner, b_inner, batches / b_inner, x_ki, x_ko, x_bi, x_bo, kbox_i, 64 / kbox_i);
+    if (rc) return rc;
+    rc = make_map_bf16_5d(&md, D, N, m_inner, M / m_inner, b_inner, batches / b_inner, d_mi, d_mo, d_bi, d_bo, mbox_i, 32 / mbox_i);
+    if (rc) return rc;
+    BgemmTcParams p;
+    p.M = M; p.K = K; p.N = N; p.mb = mb; p.kb = kb;
+    p.n_tiles = (N + bn - 1) / bn; p.b_inner = b_inner; p.k_inner = k_inner; p.m_inner = m_inner;
+    p.items = batches * p.n_tiles;
+    const int m_blocks = (mb_total + mb - 1) / mb;
+    const unsigned gx = (unsigned)std::min<long long>(p.items, std::max(1, dp.sm_count / m_blocks));
+    constexpr int ST = 3;
+    if (bn == 64) {
+        const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * 64 * 64 * 2 + 4 * 2 * 32 * 128 + 1024;
+        SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST>, smem));
+        bgemm_tc_kernel<64, ST><<<dim3(gx, m_blocks), kGemmThreads, smem, st>>>(ma, mx, md, p);
+    } else {
+        const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * 128 * 64 * 2 + 4 * 2 * 32 * 128 + 1024;
+        SEI_CUDA(allow_smem(bgemm_tc_kernel<128, ST>, smem));
+        bgemm_tc_kernel<128, ST><<<dim3(gx, m_blocks), kGemmThreads, smem, st>>>(ma, mx, md, p);
+    }
+    return finish_launch("bgemm_tc_kernel");
 }
 
 }  // namespace sei

@@ -62,6 +62,8 @@ def test_bgemm_matches_matmul(dev, M, K, N, batches):
     n0 = launch_count()
     ops.bgemm_bf16(Ap, x, out, M, K, N, tile, batches, 1, (K * N, 0), K, (0, N), (M * N, 0), M, (0, N))
     assert launch_count() == n0 + 1
+    from sei_b200 import last_kernel
+    assert last_kernel() in ("bgemm_tc_kernel", "bgemm_kernel")
     ref = Ap[:M, :K].float() @ x.float()
     assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < 8e-3
 
@@ -95,6 +97,28 @@ def test_bgemm_split_rows(dev):
                    (H * W * C, W * C), W, (0, C))
     ref2 = torch.einsum("wm,bhmc->bhwc", Ap2[:W, :2 * Wo].float(), y.float().permute(0, 2, 1, 3, 4).reshape(B, H, 2 * Wo, C))
     assert rel_err(gx.float().cpu().numpy(), ref2.cpu().numpy()) < 8e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,kind", [(3, 16, 32, 16, "down"), (2, 64, 64, 8, "down"), (2, 32, 16, 64, "up"),
+                                          (1, 128, 128, 32, "down"), (1, 64, 64, 128, "up"), (2, 256, 256, 8, "down")])
+def test_ideal_resample_tcgen05_path(dev, B, H, W, C, kind):
+    """power-of-two shapes take the tcgen05 kernel (5-D tensor maps for the split rows): forward and transposed
+    operator against the dense fp32 formulation of the same operator (models/resample.apply_dense)"""
+    from models import resample
+    from sei_b200 import last_kernel
+    torch.manual_seed(H + W + C)
+    x = torch.randn(B, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = resample.ideal_resample(x, kind, 2)
+    assert last_kernel() == "bgemm_tc_kernel"
+    ref_in = x.detach().float().requires_grad_(True)
+    ref = resample.apply_dense(kind, ref_in, 2)
+    assert rel_err(y.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) < 2e-2
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    assert last_kernel() == "bgemm_tc_kernel"
+    (gref,) = torch.autograd.grad(ref, ref_in, gy.float())
+    assert rel_err(gx.float().cpu().numpy(), gref.cpu().numpy()) < 2e-2
 
 
 @pytest.mark.gpu
