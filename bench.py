@@ -72,9 +72,9 @@ def network_description(args):
     if args.network == "cnn":
         return (f"reference ConvolutionalModel (hidden {args.cnn_hidden}, {args.cnn_scales} scales, 1 block per scale; "
                 "random init), bf16 channels-last activations; pointwise / input 3x3 convolutions on the tcgen05 GEMM "
-                "(fp32 accumulation), ideal resamplers as batched mma.sync operator products, depthwise 7x7, channel "
-                "LayerNorm, output 3x3 convolution and bias / gamma / beta reductions as hand-written kernels; "
-                "GELU, residual adds and Adam are PyTorch library ops")
+                "(fp32 accumulation), ideal resamplers as batched tcgen05 operator products, depthwise 7x7, channel "
+                "LayerNorm, GELU, output 3x3 convolution and bias / gamma / beta reductions as hand-written kernels; "
+                "residual adds and Adam are PyTorch library ops")
     return ("4-parameter pointwise stand-in (tests/toy_model.py): isolates the operator + loss-assembly path; "
             "the restoration CNN is not in this line")
 
