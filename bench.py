@@ -74,7 +74,7 @@ def network_description(args):
                 "random init), bf16 channels-last activations; pointwise / input 3x3 convolutions on the tcgen05 GEMM "
                 "(fp32 accumulation), ideal resamplers as batched tcgen05 operator products, depthwise 7x7, channel "
                 "LayerNorm, GELU, output 3x3 convolution and bias / gamma / beta reductions as hand-written kernels; "
-                "residual adds and Adam are PyTorch library ops")
+                "Adam as one streaming kernel per tensor (also refreshes the bf16 weight copies); residual adds are PyTorch library ops")
     return ("4-parameter pointwise stand-in (tests/toy_model.py): isolates the operator + loss-assembly path; "
             "the restoration CNN is not in this line")
 
@@ -158,7 +158,8 @@ def run_b200(args):
     else:
         model = ToyModel(rate=1).to(dev)
     n_params = sum(p.numel() for p in model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=True, fused=True)
+    from sei_b200.optim import Adam as SeiAdam        # torch.optim.Adam's rule as one streaming kernel per tensor
+    opt = SeiAdam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
     params = [p for p in model.parameters()]
     torch.manual_seed(1 + rank)                # per-rank data and draws
 

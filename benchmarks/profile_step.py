@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--cnn-hidden", type=int, default=32)
     ap.add_argument("--cnn-scales", type=int, default=5)
     ap.add_argument("--rows", type=int, default=45)
+    ap.add_argument("--torch-adam", action="store_true")
     ap.add_argument("--copies", action="store_true", help="attribute copy / cat / add kernels to source lines")
     args = ap.parse_args()
     import losses
@@ -30,7 +31,8 @@ def main():
     phys = physics.get_physics(bench.loss_args(), device=dev)
     loss_fn = losses.get_loss(bench.loss_args(), phys)
     model = models.get_model(bench.model_args(args.cnn_hidden, args.cnn_scales), physics=phys, device=dev).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    from sei_b200.optim import Adam as SeiAdam
+    opt = SeiAdam(model.parameters(), lr=1e-4) if not args.torch_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     x = torch.rand(args.batch, 3, 256, 256, device=dev)
     y = phys(x)
 

@@ -236,6 +236,15 @@ int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* gw, float* g
  * (n % 8 == 0): out = gelu(x) when gy == NULL, else out = gy * gelu'(x) (the backward of the same layer). */
 int sei_gelu_bf16(const void* x, const void* gy, void* out, long long n, void* stream);
 
+/* One Adam update (torch.optim.Adam semantics without weight decay / amsgrad; reference demo/train.py:167-186,266) of
+ * n float32 parameters: m, v updated in place, p <- p - lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps), with the
+ * step count t read from device memory (graph-capturable).  lowp_bf16 (optional): bf16 copy of the updated
+ * parameters written in the same pass (the operand the tensor-core GEMMs read). */
+int sei_adam_step_f32(float* p, const float* g, float* m, float* v, void* lowp_bf16, const float* step,
+                      long long n, float lr, float beta1, float beta2, float eps, void* stream);
+/* out[c][r] = in[r][c] for a bf16 [rows, cols] matrix (the (K, N) weight copy of the input-gradient GEMMs). */
+int sei_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from torch.nn import Conv2d, GELU, LayerNorm as BaseLayerNorm, Module, ModuleList, Sequential
 
 from sei_b200 import ops
+from sei_b200.optim import shadow_epoch
 from . import resample
 
 CL = torch.channels_last
@@ -86,19 +87,34 @@ class _GemmConv2d(Conv2d):
             w2 = w.reshape(w.shape[0], w.shape[1])
         else:
             w2 = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)        # (C_out, ky, kx, C_in): matches _unfold3x3
-        key = (w._version, w.data_ptr(), COMPUTE_DTYPE)
+        key = (w._version, w.data_ptr(), COMPUTE_DTYPE, shadow_epoch(w))
         if getattr(self, "_w_key", None) != key:
             with torch.no_grad():
                 self._w_cache = _pad_k(w2.detach().to(COMPUTE_DTYPE))
             self._w_key = key
             self._wt_cache = None
+            # Low-precision shadows for sei_b200.optim.Adam: when the cache has the parameter's own element order
+            # (pointwise convolutions with C_in % 8 == 0) the optimizer kernel rewrites it in the pass that updates
+            # the fp32 master, so no cast runs in the forward pass; otherwise it just invalidates this cache.
+            if w.is_cuda and COMPUTE_DTYPE == torch.bfloat16:
+                if self.kernel_size == (1, 1) and self._w_cache.shape == w2.shape:
+                    w._sei_lowp, w._sei_lowp_t, w._sei_invalidate = self._w_cache, None, None
+                else:
+                    w._sei_lowp, w._sei_lowp_t, w._sei_invalidate = None, None, self._invalidate
         return w2, self._w_cache
 
+    def _invalidate(self):
+        self._w_key = None
+
     def _weight_matrix_t(self):
-        """(K, N) copy of the low-precision weight for dgrad, made once per weight version"""
+        """(K, N) copy of the low-precision weight for dgrad, made once per weight version (and then kept fresh by
+        sei_b200.optim.Adam through the transposed shadow registered on the parameter)"""
         if getattr(self, "_wt_cache", None) is None:
             with torch.no_grad():
                 self._wt_cache = _pad_k(self._w_cache.t())
+            w = self.weight
+            if getattr(w, "_sei_lowp", None) is self._w_cache and self._wt_cache.shape == (self._w_cache.shape[1], self._w_cache.shape[0]):
+                w._sei_lowp_t = (self._w_cache.shape[0], self._w_cache.shape[1], self._wt_cache)
         return self._wt_cache
 
     def forward_nobias(self, x):
