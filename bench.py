@@ -304,7 +304,7 @@ def run_b200(args):
             us = e0.elapsed_time(e1) * 1e3 / reps
             flops = 2.0 * T * dim * 4 * dim
             tf = flops / (us * 1e-6) / 1e12
-            roofline = {"kernel": f"gemm_bf16_tn_kernel (deepest ConvBlock conv2: {T}x{dim} @ ({4 * dim}x{dim})^T)",
+            roofline = {"kernel": f"{sei_b200.last_kernel()} (tcgen05 cta_group::2; deepest ConvBlock conv2: {T}x{dim} @ ({4 * dim}x{dim})^T)",
                         "bound": "tensor", "achieved": round(tf, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": round(tf / peaks["tf_sustained"], 4), "frac_of_burst_peak": round(tf / peaks["tf_burst"], 4),
                         "traffic": None, "peak_source": peaks["src"] + ", sustained cuBLAS bf16 figure",

@@ -245,6 +245,13 @@ int sei_adam_step_f32(float* p, const float* g, float* m, float* v, void* lowp_b
 /* out[c][r] = in[r][c] for a bf16 [rows, cols] matrix (the (K, N) weight copy of the input-gradient GEMMs). */
 int sei_transpose_bf16(const void* in, void* out, int rows, int cols, void* stream);
 
+/* Bias of a pointwise convolution pushed through an ideal resampler (Downsample applies the resampler first):
+ * out[t][c] += pat[t % period] * bias[c] in place on bf16 rows [T, C]; and its gradient
+ * gbias[c] = sum_t gy[t][c] * pat[t % period] (fixed order; workspace as for sei_colsum_bf16). */
+int sei_bias_pattern_add_bf16(void* out, const float* pat, const float* bias, long long T, int C, int period, void* stream);
+int sei_bias_pattern_grad_bf16(const void* gy, const float* pat, float* gbias, void* workspace, long long T, int C, int period,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,11 +206,12 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
 //   MODE 0 (LayerNorm parameter gradients): partial[slot][0][c] = sum gy * xhat, partial[slot][1][c] = sum gy
 //   MODE 1 (bias gradient of a pointwise convolution):  partial[slot][0][c] = sum gy
 // colsum_final_kernel then adds the partial rows (fixed order: deterministic, no atomics).
+//   MODE 2 (bias gradient through a resampler): partial[slot][0][c] = sum gy * rowweight[r % period]  (mean = the table)
 template <int MODE>
 __global__ void __launch_bounds__(kLnThreads) colsum_kernel(const __nv_bfloat16* __restrict__ x,
                                                              const __nv_bfloat16* __restrict__ gy,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             float* __restrict__ partial, long long T, int C)
+                                                             float* __restrict__ partial, long long T, int C, int period = 1)
 {
     constexpr int NQ = MODE == 0 ? 2 : 1;
     __shared__ float red[kLnThreads * 8 * NQ];
@@ -232,8 +233,14 @@ __global__ void __launch_bounds__(kLnThreads) colsum_kernel(const __nv_bfloat16*
 #pragma unroll
             for (int j = 0; j < 8; ++j) dg[j] = fmaf(fg[j], (fx[j] - mu) * rs, dg[j]);
         }
+        if (MODE == 2) {
+            const float wr = __ldg(mean + (r % period));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) db[j] += fg[j];
+            for (int j = 0; j < 8; ++j) db[j] = fmaf(fg[j], wr, db[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) db[j] += fg[j];
+        }
     }
     // in-CTA reduction over the threads that own the same vector (only when a CTA spans several rows: nvec < 256)
     const int per_cta = nvec < kLnThreads ? kLnThreads / nvec : 1;      // row slots per CTA
@@ -1132,4 +1139,76 @@ extern "C" int sei_gelu_bf16(const void* x, const void* gy, void* out, long long
     else
         gelu_fwd_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), nvec);
     return finish_launch(gy ? "gelu_bwd_kernel" : "gelu_fwd_kernel");
+}
+
+
+// ---------------------------------------------------------------- bias behind a resampler
+// Downsample = LayerNorm -> conv1x1 -> ideal resampler; the resampler is applied BEFORE the convolution here (they
+// commute), so the convolution's bias must be pushed through it: the constant image bias[c] becomes
+// bias[c] * R(1)[h, w] with R(1) the resampler's response to the all-ones image (models/resample.constant_response).
+//   out[t][c] += pat[t % period] * bias[c]          (in place, rows = pixels, period = Ho * Wo)
+//   gbias[c]   = sum_t gy[t][c] * pat[t % period]   (colsum_kernel<2>)
+namespace sei {
+
+__global__ void __launch_bounds__(256) bias_pattern_add_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ pat,
+                                                               const float* __restrict__ bias, long long T, int C, int period)
+{
+    const int nvec = C >> 3;
+    const long long total = T * nvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / nvec;
+        const int v = (int)(i - r * nvec);
+        const float wr = __ldg(pat + (r % period));
+        float f[8], b[8];
+        uint4* ptr = reinterpret_cast<uint4*>(out + r * C) + v;
+        unpack8(*ptr, f);
+        load8f(bias + 8 * v, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(wr, b[j], f[j]);
+        *ptr = pack8(f);
+    }
+}
+
+}  // namespace sei
+
+extern "C" int sei_bias_pattern_add_bf16(void* out, const float* pat, const float* bias, long long T, int C, int period,
+                                         void* stream)
+{
+    SEI_REQUIRE(out && pat && bias, "null pointer argument");
+    SEI_REQUIRE(T >= 0 && C >= 8 && C % 8 == 0 && period >= 1, "bad shape T=%lld C=%d period=%d", T, C, period);
+    SEI_REQUIRE(aligned16(out) && aligned16(bias), "operands must be 16-byte aligned");
+    if (T == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const long long total = T * (C / 8);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)dp.sm_count * 16);
+    bias_pattern_add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(out), pat, bias, T, C, period);
+    return finish_launch("bias_pattern_add_kernel");
+}
+
+// gbias[c] = sum_t gy[t][c] * pat[t % period]; workspace as for sei_colsum_bf16
+extern "C" int sei_bias_pattern_grad_bf16(const void* gy, const float* pat, float* gbias, void* workspace, long long T, int C,
+                                          int period, void* stream)
+{
+    SEI_REQUIRE(gy && pat && gbias && workspace, "null pointer argument");
+    SEI_REQUIRE(T >= 0 && C >= 8 && C % 8 == 0 && period >= 1, "bad shape T=%lld C=%d period=%d", T, C, period);
+    SEI_REQUIRE(aligned16(gy) && aligned16(workspace), "operands must be 16-byte aligned");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const long long threads = colsum_threads(C, dp.sm_count);
+    SEI_REQUIRE(threads > 0, "channel count %d unsupported by the column-sum kernel", C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (T == 0) {
+        SEI_CUDA(cudaMemsetAsync(gbias, 0, (size_t)C * 4, st));
+        return 0;
+    }
+    colsum_kernel<2><<<(unsigned)(threads / kLnThreads), kLnThreads, 0, st>>>(
+        nullptr, static_cast<const __nv_bfloat16*>(gy), pat, nullptr, static_cast<float*>(workspace), T, C, period);
+    rc = finish_launch("colsum_kernel<pattern>");
+    if (rc) return rc;
+    colsum_final_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), gbias, gbias,
+                                                      colsum_slots(C, threads), C, C);
+    return finish_launch("colsum_final_kernel");
 }

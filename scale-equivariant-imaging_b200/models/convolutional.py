@@ -289,9 +289,14 @@ class Downsample(Module):
             H, W = x.shape[-2], x.shape[-1]
             out = self.conv.forward_nobias(self.ideal_downsample(x))
             if self.conv.bias is not None:
-                pat = resample.constant_response("down", H, W, self.rate, x.device)                 # (Ho, Wo)
-                bias_img = (pat[:, :, None] * self.conv.bias[None, None, :]).to(out.dtype)          # (Ho, Wo, C_out)
-                out = out + bias_img.permute(2, 0, 1)[None]
+                pat = resample.constant_response("down", H, W, self.rate, x.device)                 # (Ho, Wo) fp32
+                rows = out.permute(0, 2, 3, 1).reshape(-1, out.shape[1])                            # view of the GEMM output
+                if ops.ln_cl_supported(rows):
+                    rows = ops.bias_pattern_add(rows, pat.reshape(-1), self.conv.bias)
+                    out = rows.view(out.shape[0], out.shape[2], out.shape[3], out.shape[1]).permute(0, 3, 1, 2)
+                else:
+                    bias_img = (pat[:, :, None] * self.conv.bias[None, None, :]).to(out.dtype)      # (Ho, Wo, C_out)
+                    out = out + bias_img.permute(2, 0, 1)[None]
             return out
         return self.ideal_downsample(self.conv(x))
 

@@ -49,6 +49,8 @@ SIGNATURES = {
     "sei_gelu_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
     "sei_adam_step_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "sei_transpose_bf16": (C.c_int, [_vp, _vp, _i, _i, _vp]),
+    "sei_bias_pattern_add_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "sei_bias_pattern_grad_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "sei_bgemm_tile_rows": (C.c_int, [_i, _i]),
     "sei_bgemm_bf16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _ll, _ll, _i, _ll, _ll, _ll, _ll, _i, _ll, _ll,
                                  _vp]),

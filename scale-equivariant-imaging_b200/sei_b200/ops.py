@@ -459,6 +459,37 @@ def gelu(x):
     return _Gelu.apply(x)
 
 
+class _BiasPattern(torch.autograd.Function):
+    """rows [T, C] (bf16) + pat[t % period] * bias[c]; the rows are updated in place (they are a fresh GEMM output)"""
+
+    @staticmethod
+    def forward(ctx, rows, pat, bias):
+        T, Cc = rows.shape
+        b32 = bias.detach().float().contiguous()
+        with torch.cuda.device(rows.device):
+            check(_lib.load().sei_bias_pattern_add_bf16(_ptr(rows), _ptr(pat), _ptr(b32), T, Cc, pat.numel(), _stream(rows)))
+        ctx.mark_dirty(rows)
+        ctx.save_for_backward(pat)
+        ctx.bias_dtype = bias.dtype
+        return rows
+
+    @staticmethod
+    def backward(ctx, gy):
+        (pat,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        T, Cc = gy.shape
+        lib = _lib.load()
+        gb = torch.empty(Cc, dtype=torch.float32, device=gy.device)
+        ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=gy.device)
+        with torch.cuda.device(gy.device):
+            check(lib.sei_bias_pattern_grad_bf16(_ptr(gy), _ptr(pat), _ptr(gb), _ptr(ws), T, Cc, pat.numel(), _stream(gy)))
+        return gy, None, gb.to(ctx.bias_dtype)
+
+
+def bias_pattern_add(rows, pat, bias):
+    return _BiasPattern.apply(rows, pat, bias)
+
+
 def layer_norm_cl(x_rows, gamma, beta, eps):
     return _LayerNormCL.apply(x_rows, gamma, beta, eps)
 

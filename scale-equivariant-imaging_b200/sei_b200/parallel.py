@@ -63,7 +63,9 @@ class GradAllReducer:
     all-reduce (ReduceOp.AVG): no flatten / unflatten copies and no separate division kernel.  Gradients that were
     re-created elsewhere (e.g. `zero_grad(set_to_none=True)`) fall back to the copying path."""
 
-    def __init__(self, params, max_elems=64 * 2 ** 20, group=None):
+    def __init__(self, params, max_elems=2 ** 40, group=None):
+        # one bucket by default: nothing overlaps the reduction (it runs between backward and the optimizer step), so a
+        # single large all-reduce gets the best NVLink bandwidth; pass a smaller max_elems to split it
         self.params = [p for p in params if p.requires_grad]
         self.buckets = make_buckets(self.params, max_elems)
         self.group = group
