@@ -144,28 +144,32 @@ __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __gr
         const int r0 = band * TH, th = min(TH, S - r0);
         const bool staged = s_n[buf] > 0;
         const AxisTap* rT = rowT + buf * TH;
-        const float* src = staged ? sSrc + (size_t)buf * p.SRC_MAX * S : p.x + (size_t)plane * S * S;
         if (staged) {
             mbar_wait(&bar[buf], (phases >> buf) & 1u);
             phases ^= 1u << buf;
         }
 
         // ---- vertical pass: sTmp[r][pos(c)] = sum_a wy[r][a] * src[iy[r][a]][c]
+        // (two instantiations so that the staged path compiles to shared loads and the other to read-only global loads)
         const int CW = S >> 2;
-        for (int item = threadIdx.x; item < th * CW; item += kScaleThreads) {
-            const int r = item / CW, c4 = item - r * CW;
-            const AxisTap t = rT[r];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto vpass = [&](const float* __restrict__ src, auto ld) {
+            for (int item = threadIdx.x; item < th * CW; item += kScaleThreads) {
+                const int r = item / CW, c4 = item - r * CW;
+                const AxisTap t = rT[r];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t.idx[a] * S + 4 * c4);
-                acc.x = fmaf(t.w[a], v.x, acc.x); acc.y = fmaf(t.w[a], v.y, acc.y);
-                acc.z = fmaf(t.w[a], v.z, acc.z); acc.w = fmaf(t.w[a], v.w, acc.w);
+                for (int a = 0; a < 4; ++a) {
+                    const float4 v = ld(reinterpret_cast<const float4*>(src + (size_t)t.idx[a] * S + 4 * c4));
+                    acc.x = fmaf(t.w[a], v.x, acc.x); acc.y = fmaf(t.w[a], v.y, acc.y);
+                    acc.z = fmaf(t.w[a], v.z, acc.z); acc.w = fmaf(t.w[a], v.w, acc.w);
+                }
+                float* d = sTmp + (size_t)r * TP + 2 * c4;
+                *reinterpret_cast<float2*>(d) = make_float2(acc.x, acc.z);                               // columns 4c4, 4c4+2
+                *reinterpret_cast<float2*>(d + scale_tmp_half(S)) = make_float2(acc.y, acc.w);           // columns 4c4+1, 4c4+3
             }
-            float* d = sTmp + (size_t)r * TP + 2 * c4;
-            *reinterpret_cast<float2*>(d) = make_float2(acc.x, acc.z);                               // columns 4c4, 4c4+2
-            *reinterpret_cast<float2*>(d + scale_tmp_half(S)) = make_float2(acc.y, acc.w);           // columns 4c4+1, 4c4+3
-        }
+        };
+        if (staged) vpass(sSrc + (size_t)buf * p.SRC_MAX * S, [](const float4* q) { return *q; });
+        else vpass(p.x + (size_t)plane * S * S, [](const float4* q) { return __ldg(q); });
         __syncthreads();
 
         // ---- horizontal pass: out[r][j] = sum_b wx[j][b] * sTmp[r][pos(ix[j][b])]
@@ -267,7 +271,14 @@ __global__ void scale_params_kernel(const float* u_rate, const float* u_center, 
 }
 
 // staging rows for a band of th output rows at the smallest rate the reference samples (0.5)
-static int scale_src_rows(int th) { return 2 * th + 6; }
+
+// SEI_SCALE_NOSTAGE=1 (experiment): no staging buffers, the vertical pass reads its taps through L1
+static bool scale_nostage()
+{
+    const char* e = getenv("SEI_SCALE_NOSTAGE");
+    return e && *e == '1';
+}
+static int scale_src_rows(int th) { return scale_nostage() ? 0 : 2 * th + 6; }
 
 static size_t scale_band_smem(int th, int S)
 {
@@ -319,7 +330,7 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
         p.C = C; p.S = S; p.TH = TH; p.nbands = (S + TH - 1) / TH; p.SRC_MAX = scale_src_rows(TH);
         p.two_over_S = two_over_S;
         p.total_bands = planes * p.nbands;
-        const int ctas_per_sm = std::max(1, std::min(2, (int)((size_t)227 * 1024 / (smem + 1024))));
+        const int ctas_per_sm = std::max(1, std::min(scale_nostage() ? 3 : 2, (int)((size_t)227 * 1024 / (smem + 1024))));
         const unsigned grid = (unsigned)std::min<long long>(p.total_bands, (long long)dp.sm_count * ctas_per_sm);
         if (S == 256 && TH == 16) {
             SEI_CUDA(allow_smem(scale_band_kernel<256, 16>, smem));
