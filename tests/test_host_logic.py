@@ -51,6 +51,11 @@ def test_sass_is_blackwell_native():
     assert "sm_100a" in out
     assert out.count("UBLKCP") >= 8
     assert "SYNCS.ARRIVE.TRANS64" in out
+    # tcgen05 / TMEM / TMA in the GEMMs: single-CTA UMMA, the CTA-pair kernel (cta_group::2 MMA, multicast commit, 2-CTA
+    # TMA loads, cluster barrier) and the batched operator product (5-D tensor maps in both directions)
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG.2D", "UTMASTG.2D", "UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST",
+                     "UTMALDG.2D.2CTA", "UCGABAR_ARV", "UTMALDG.5D", "UTMASTG.5D"):
+        assert mnemonic in out, mnemonic
 
 
 def test_argument_validation_needs_no_device():
