@@ -148,40 +148,83 @@ __global__ void __launch_bounds__(kDownThreads) down_band_kernel(const __grid_co
         __syncthreads();
     }
 
-    // ---- vertical pass: y[i][j] = sum_t w[t] * sTmp[R*i - OFF + t - in_lo][j]   (rows are warp-uniform)
+    // ---- vertical pass: y[i][j] = sum_t w[t] * sTmp[R*i - OFF + t - in_lo][j]
+    // Register-blocked: a work item owns 4 consecutive output rows x 4 columns and streams the 3R + T intermediate rows
+    // they share once (14 shared loads per 4 output vectors at R = 2 instead of 32; the per-row version was bound by
+    // the shared-memory pipe).  Groups that contain one of the image's four border rows, or a ragged tail, take the
+    // per-row path with the border weight tables.
     float* yplane = p.y + (size_t)plane * Ho * Wo;
     const float* nplane = p.noise ? p.noise + (size_t)plane * Ho * Wo : nullptr;
-    for (int item = threadIdx.x; item < th * CW; item += NT) {
-        const int r = item / CW, j4 = item - r * CW;
-        const int i = i0 + r;
-        const int g = i * Wo + 4 * j4;
-        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nplane) nz = ld_stream4(nplane + g);
-        const int k = border_slot(i, Ho);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < 0) {
+    const int ngrp = (th + 3) >> 2;
+    for (int item = threadIdx.x; item < ngrp * CW; item += NT) {
+        const int gq = item / CW, j4 = item - gq * CW;
+        const int r0 = 4 * gq, nr = min(4, th - r0);
+        const int i = i0 + r0;
+        if (nr == 4 && i >= 2 && i + 3 < Ho - 2) {
+            const int g = i * Wo + 4 * j4;
+            float4 nz[4];
+            if (nplane) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) nz[o] = ld_stream4(nplane + g + o * Wo);
+            }
+            float4 acc[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* src = sTmp + (R * i - OFF - in_lo) * Wo + 4 * j4;
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
-                const float w = p.wint[t];
-                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            for (int q = 0; q < 3 * R + T; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(src + q * Wo);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int t = q - R * o;
+                    if (t >= 0 && t < T) {
+                        const float w = p.wint[t];
+                        acc[o].x = fmaf(w, v.x, acc[o].x); acc[o].y = fmaf(w, v.y, acc[o].y);
+                        acc[o].z = fmaf(w, v.z, acc[o].z); acc[o].w = fmaf(w, v.w, acc[o].w);
+                    }
+                }
             }
-        } else {
-            const float* src = sTmp + (rowTab.xmin[k] - in_lo) * Wo + 4 * j4;
-            for (int t = 0; t < rowTab.xsize[k]; ++t) {
-                const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
-                const float w = rowTab.w[k][t];
-                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (nplane) {
+                    acc[o].x = fmaf(p.sigma, nz[o].x, acc[o].x); acc[o].y = fmaf(p.sigma, nz[o].y, acc[o].y);
+                    acc[o].z = fmaf(p.sigma, nz[o].z, acc[o].z); acc[o].w = fmaf(p.sigma, nz[o].w, acc[o].w);
+                }
+                st_stream4(yplane + g + o * Wo, acc[o]);
             }
+            continue;
         }
-        if (nplane) {
-            acc.x = fmaf(p.sigma, nz.x, acc.x); acc.y = fmaf(p.sigma, nz.y, acc.y);
-            acc.z = fmaf(p.sigma, nz.z, acc.z); acc.w = fmaf(p.sigma, nz.w, acc.w);
+        for (int rr = 0; rr < nr; ++rr) {
+            const int ii = i + rr;
+            const int g = ii * Wo + 4 * j4;
+            float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nplane) nz = ld_stream4(nplane + g);
+            const int k = border_slot(ii, Ho);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < 0) {
+                const float* src = sTmp + (R * ii - OFF - in_lo) * Wo + 4 * j4;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
+                    const float w = p.wint[t];
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+            } else {
+                const float* src = sTmp + (rowTab.xmin[k] - in_lo) * Wo + 4 * j4;
+                for (int t = 0; t < rowTab.xsize[k]; ++t) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + t * Wo);
+                    const float w = rowTab.w[k][t];
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+            }
+            if (nplane) {
+                acc.x = fmaf(p.sigma, nz.x, acc.x); acc.y = fmaf(p.sigma, nz.y, acc.y);
+                acc.z = fmaf(p.sigma, nz.z, acc.z); acc.w = fmaf(p.sigma, nz.w, acc.w);
+            }
+            st_stream4(yplane + g, acc);
         }
-        st_stream4(yplane + g, acc);
     }
 }
 
@@ -517,21 +560,30 @@ static int down_common(const float* in, float* out, long long planes, int H, int
                     (!noise || aligned16(noise));
     size_t smem = 0;
     if (tiled_ok) {
-        const size_t budget = std::min((size_t)dp.smem_optin, (size_t)110 * 1024);
+        const size_t budget_dflt = getenv("SEI_DOWN_SMEM_KB") ? (size_t)atoi(getenv("SEI_DOWN_SMEM_KB")) * 1024 : (size_t)110 * 1024;
+        const size_t budget = std::min((size_t)dp.smem_optin, budget_dflt);
         if (!transpose) {
-            p.CH = std::max(1, (int)(16384 / ((size_t)W * 4)));
+            // rows per streamed chunk: one barrier round per chunk, so chunks must be large enough to amortise it
+            // (x4, 4 KB rows: 4-row chunks 77 us, 8-row chunks 58 us; profiles/r01_sr_variants.md); halved until a
+            // band fits next to the two stages (very wide images)
+            int ch = getenv("SEI_DOWN_CH_KB") ? std::max(1, (int)((size_t)atoi(getenv("SEI_DOWN_CH_KB")) * 1024 / ((size_t)W * 4)))
+                                              : std::max(8, (int)(16384 / ((size_t)W * 4)));
             int best = 0;
             const int th_max = getenv("SEI_DOWN_TH") ? atoi(getenv("SEI_DOWN_TH")) : 16;
-            for (int th = 4; th <= th_max; th += 4) {
-                const size_t need = ((size_t)(rate * th + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
-                if (need <= budget) best = th;
+            for (;; ch = std::max(1, ch / 2)) {
+                for (int th = 4; th <= th_max; th += 4) {
+                    const size_t need = ((size_t)(rate * th + 3 * rate) * Wo + (size_t)2 * ch * W) * 4;
+                    if (need <= budget) best = th;
+                }
+                if (best > 0 || ch == 1) break;
             }
+            p.CH = ch;
             p.TH = std::min(best, ((Ho + 3) / 4) * 4);
             p.nbands = p.TH ? (Ho + p.TH - 1) / p.TH : 0;
             smem = ((size_t)(rate * p.TH + 3 * rate) * Wo + (size_t)2 * p.CH * W) * 4;
         } else {
             int best = 0;
-            const int th_max = getenv("SEI_DOWNT_TH") ? atoi(getenv("SEI_DOWNT_TH")) : 32;
+            const int th_max = getenv("SEI_DOWNT_TH") ? atoi(getenv("SEI_DOWNT_TH")) : 16;   // 16 measured best for x4 (58 vs 63 us), neutral for x2
             for (int th = 8; th <= th_max; th += 8) {
                 const size_t need = ((size_t)(th / rate + 8) * Wo + (size_t)th * Wo) * 4;
                 if (need <= budget) best = th;
