@@ -179,6 +179,9 @@ int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, l
  * copies of the activations.  lda, ldb multiples of 8; K = pixels.  Split-K with fp32 atomics when M*N is small. */
 int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long long K, int M, int N,
                       long long lda, long long ldb, void* stream);
+/* D += A^T B (same operands): the weight gradient accumulated in place into the parameter's fp32 gradient buffer. */
+int sei_gemm_bf16_atb_accumulate(const void* A, const void* B, float* D, long long K, int M, int N,
+                                 long long lda, long long ldb, void* stream);
 
 /* Batched operator product  D_b[M, N] = A[M, K] * X_b[K, N]  (bf16, fp32 accumulation, bf16 result), A shared by
  * all batch entries and resident in shared memory, X streamed once.  Replaces the rfft2 / fftshift / mask or

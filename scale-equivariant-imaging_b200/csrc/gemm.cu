@@ -139,6 +139,7 @@ struct GemmParams {
     int kb_per_split;    // k-blocks per grid.z slice (split-K: fp32 output only, slices accumulate with atomics)
     int splits;
     int tma_store;       // bf16 output staged through shared memory and written with bulk tensor stores
+    int accumulate;      // fp32 output: add to D instead of overwriting it (weight gradients accumulated in place)
 };
 
 // first version: one output tile per CTA (kept for A/B measurements: SEI_GEMM_V1=1)
@@ -234,7 +235,7 @@ gemm_bf16_tn_kernel_v1(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     for (int j = 0; j < 32; ++j)
                         if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
                 }
-                if (OUT_F32 && p.splits > 1) {
+                if (OUT_F32 && (p.splits > 1 || p.accumulate)) {
                     float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -293,11 +294,18 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
         for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
     }
-    if (OUT_F32 && p.splits > 1) {
+    if (OUT_F32 && (p.splits > 1 || p.accumulate)) {
         float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+        if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
+            // 16-byte vector reductions (red.global.add.v4.f32): a lane owns one row, so scalar atomics would touch
+            // 32 sectors with 4 bytes each per instruction
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+            for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+        }
     } else if (OUT_F32) {
         float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
         if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
@@ -1104,7 +1112,7 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
     rc = make_map_bf16(&mb, B, N, K, ldb, bn);
     if (rc) return rc;
     GemmParams p;
-    p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd;
+    p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
     p.tma_store = (!out_f32 && bn >= 64 && ldd % 8 == 0 && !(nts && *nts == '1')) ? 1 : 0;
@@ -1151,8 +1159,25 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
 
 // D[M, N] (fp32) = A[K, M]^T * B[K, N]: both operands MN-major (the contraction index is the row).  The weight
 // gradient of a pointwise convolution: A = dL/dy (pixels x C_out), B = x (pixels x C_in), D = dL/dW (C_out x C_in).
+static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long K, int M, int N,
+                             long long lda, long long ldb, int accumulate, void* stream);
+
 extern "C" int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long long K, int M, int N,
                                  long long lda, long long ldb, void* stream)
+{
+    return gemm_bf16_atb_impl(A, B, D, K, M, N, lda, ldb, 0, stream);
+}
+
+// D += A^T B: the weight gradient added straight into the parameter's gradient buffer (fp32 atomic adds from the
+// epilogue), instead of a temporary plus a separate accumulation pass over all parameters
+extern "C" int sei_gemm_bf16_atb_accumulate(const void* A, const void* B, float* D, long long K, int M, int N,
+                                            long long lda, long long ldb, void* stream)
+{
+    return gemm_bf16_atb_impl(A, B, D, K, M, N, lda, ldb, 1, stream);
+}
+
+static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long K, int M, int N,
+                             long long lda, long long ldb, int accumulate, void* stream)
 {
     SEI_REQUIRE(A && B && D, "null pointer argument");
     SEI_REQUIRE(M > 0 && N > 0 && K > 0 && K < (1ll << 31), "bad shape M=%d N=%d K=%lld", M, N, K);
@@ -1170,7 +1195,7 @@ extern "C" int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long lo
     rc = make_map_bf16_mn(&mb, B, K, N, ldb);
     if (rc) return rc;
     GemmParams p;
-    p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0;
+    p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
@@ -1181,7 +1206,7 @@ extern "C" int sei_gemm_bf16_atb(const void* A, const void* B, float* D, long lo
         want = std::max(1, std::min(want, 512));
         p.kb_per_split = (nk + want - 1) / want;
         p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
-        if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+        if (p.splits > 1 && !accumulate) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
     }
     switch (bn) {
     case 64: return launch_gemm_mn<64, 8>(ma, mb, p, dp.sm_count, st);

@@ -28,6 +28,7 @@ CL = torch.channels_last
 # activation / GEMM operand dtype.  bf16 is the only dtype the tcgen05 kernel takes; the unit tests set this to
 # float32 together with a patched _gemm_tn to check the network's structure against the reference at fp32 accuracy.
 COMPUTE_DTYPE = torch.bfloat16
+_NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"     # A/B switch for measurements
 
 
 def _gemm_tn(a, b, bias, out_dtype):
@@ -35,19 +36,21 @@ def _gemm_tn(a, b, bias, out_dtype):
     return ops.gemm_bf16_tn(a, b, bias, out_dtype=out_dtype)
 
 
-def _gemm_atb(a, b):
-    """D (fp32) = a^T @ b with both operands read in place (sei_gemm_bf16_atb, MN-major UMMA operands)"""
-    return ops.gemm_bf16_atb(a, b)
+def _gemm_atb(a, b, out=None):
+    """D (fp32) = a^T @ b with both operands read in place (sei_gemm_bf16_atb, MN-major UMMA operands); with `out`
+    the product is accumulated into it"""
+    return ops.gemm_bf16_atb(a, b, out=out)
 
 
 class _GemmTN(torch.autograd.Function):
     """out[T, N] = x[T, K] @ w[N, K]^T + bias[N]; all three passes on sei_gemm_bf16_tn."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, wt_getter):
+    def forward(ctx, x, weight, bias, w_bf16, wt_getter, param=None):
         ctx.save_for_backward(x, w_bf16)
         ctx.has_bias = bias is not None
         ctx.wt_getter = wt_getter
+        ctx.param = param                      # nn.Parameter whose .grad may receive the weight gradient in place
         return _gemm_tn(x, w_bf16, bias, COMPUTE_DTYPE)
 
     @staticmethod
@@ -59,7 +62,16 @@ class _GemmTN(torch.autograd.Function):
             gx = _gemm_tn(_pad_k(gy), ctx.wt_getter(), None, COMPUTE_DTYPE)          # dgrad: gy[T,N] @ w[N,K]
         if ctx.needs_input_grad[1]:
             if gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0:
-                gw = _gemm_atb(gy, x)                                                # wgrad: gy[T,N]^T @ x[T,K], in place
+                g = None if (ctx.param is None or _NO_WGRAD_ACC) else ctx.param.grad
+                if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda
+                        and g.numel() == gy.shape[1] * x.shape[1] and COMPUTE_DTYPE == torch.bfloat16):
+                    # accumulate straight into the parameter's gradient buffer (allocated by a previous backward /
+                    # zero_grad(set_to_none=False) / the data-parallel flat buckets): no temporary, no separate
+                    # accumulation pass over the 645 M parameters for each of the three network passes of a step
+                    _gemm_atb(gy, x, out=g.view(gy.shape[1], x.shape[1]))
+                    gw = None
+                else:
+                    gw = _gemm_atb(gy, x)                                            # wgrad: gy[T,N]^T @ x[T,K], in place
             elif x.shape[1] % 8 == 0:                         # 3-channel output edge: pad gy's columns, not transposes
                 gw = _gemm_atb(_pad_k(gy), x)[: gy.shape[1]]
             else:
@@ -67,7 +79,7 @@ class _GemmTN(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             # one pass, fp32 accumulation, fixed order (csrc/cnn_elem.cu); library reduction for odd channel counts
             gb = ops.colsum_bf16(gy) if ops.ln_cl_supported(gy) else torch.sum(gy, 0, dtype=torch.float32)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 def _pad_k(a):
@@ -134,7 +146,9 @@ class _GemmConv2d(Conv2d):
         if x2.shape[1] != w_bf16.shape[1]:
             x2 = F.pad(x2, (0, w_bf16.shape[1] - x2.shape[1]))
         w2p = w2 if w2.shape[1] == w_bf16.shape[1] else F.pad(w2, (0, w_bf16.shape[1] - w2.shape[1]))
-        out = _GemmTN.apply(x2, w2p, self.bias if use_bias else None, w_bf16, self._weight_matrix_t)
+        in_place_ok = self.kernel_size == (1, 1) and w2p is w2 and w_bf16.shape == w2.shape
+        out = _GemmTN.apply(x2, w2p, self.bias if use_bias else None, w_bf16, self._weight_matrix_t,
+                            self.weight if in_place_ok else None)
         return out.view(B, H, W, -1).permute(0, 3, 1, 2)                        # logical NCHW, channels-last memory
 
 

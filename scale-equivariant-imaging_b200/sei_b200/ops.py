@@ -251,8 +251,9 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     return d
 
 
-def gemm_bf16_atb(a, b):
-    """D[M,N] (fp32) = a[K,M]^T @ b[K,N] on the tcgen05 tensor cores, both operands read in place (MN-major)."""
+def gemm_bf16_atb(a, b, out=None):
+    """D[M,N] (fp32) = a[K,M]^T @ b[K,N] on the tcgen05 tensor cores, both operands read in place (MN-major).
+    out: contiguous fp32 [M, N] tensor to ACCUMULATE into (D += a^T b) instead of allocating a result."""
     for t, name in ((a, "a"), (b, "b")):
         if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
             raise SeiError(f"gemm_bf16_atb: {name} must be a 2-D CUDA bf16 tensor with a contiguous last dimension")
@@ -260,6 +261,13 @@ def gemm_bf16_atb(a, b):
     K2, N = b.shape
     if K != K2:
         raise SeiError(f"gemm_bf16_atb: contraction dimensions differ ({K} vs {K2})")
+    if out is not None:
+        if out.dtype != torch.float32 or tuple(out.shape) != (M, N) or not out.is_contiguous() or out.device != a.device:
+            raise SeiError("gemm_bf16_atb: out must be a contiguous float32 [M, N] tensor on the operands' device")
+        with torch.cuda.device(a.device):
+            check(_lib.load().sei_gemm_bf16_atb_accumulate(_ptr(a), _ptr(b), _ptr(out), K, M, N, a.stride(0), b.stride(0),
+                                                           _stream(a)))
+        return out
     d = torch.empty((M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         check(_lib.load().sei_gemm_bf16_atb(_ptr(a), _ptr(b), _ptr(d), K, M, N, a.stride(0), b.stride(0), _stream(a)))

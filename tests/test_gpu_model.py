@@ -65,7 +65,8 @@ def test_cnn_forward_backward_bf16(golden, dev, name, monkeypatch):
     # (b) same precision, library matmul (fp32 accumulate, bf16 / fp32 output like the kernel)
     monkeypatch.setattr(mc, "_gemm_tn", lambda a, b, bias, out_dtype:
                         (a.float() @ b.float().t() + (bias if bias is not None else 0)).to(out_dtype))
-    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b: a.float().t() @ b.float())
+    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b, out=None: (a.float().t() @ b.float()) if out is None
+                        else out.add_(a.float().t() @ b.float()))
     _, model_b = _load(golden, f"model_{name}", dev)
     out_b = model_b(y)
     (out_b * gout).sum().backward()
@@ -113,3 +114,18 @@ def test_full_step_cfg1_matches_reference(golden, dev):
     ref = float(g["loss"])
     assert abs(float(loss) - ref) < 3e-2 * abs(ref), (float(loss), ref)
     _check_grads(net, _golden_grads(g))
+
+
+def test_weight_gradients_accumulate_in_place(golden, dev):
+    """second and later backward passes add the weight gradients straight into the existing .grad buffers
+    (sei_gemm_bf16_atb_accumulate); the result must equal the sum of separately computed gradients"""
+    g, model = _load(golden, "model_deblur", dev)
+    y, gout = torch.from_numpy(g["y"]).to(dev), torch.from_numpy(g["gout"]).to(dev)
+    (model(y) * gout).sum().backward()
+    once = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    ptrs = {k: p.grad.data_ptr() for k, p in model.named_parameters()}
+    (model(y) * gout).sum().backward()                       # accumulates
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == ptrs[k]
+        ref = 2 * once[k]
+        assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-7, k

@@ -35,7 +35,7 @@ def test_network_structure_fp32(golden, name, monkeypatch):
     g, model = _load(golden, name)
     monkeypatch.setattr(mc, "COMPUTE_DTYPE", torch.float32)
     monkeypatch.setattr(mc, "_gemm_tn", lambda a, b, bias, out_dtype: (a @ b.t() + (bias if bias is not None else 0)).to(out_dtype))
-    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b: (a.t() @ b).float())
+    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b, out=None: (a.t() @ b).float())
     y = torch.from_numpy(g["y"])
     out = model(y)
     assert rel_err(out.detach().numpy(), g["out"]) < 2e-5
