@@ -13,7 +13,7 @@ half spectrum R = Rr + i Ri -> real through the real-linear c2r transform (Ir, I
 
 Gi does not vanish because the kept frequency band [hc, H - hc) of the shifted spectrum is not symmetric.  The four
 matrices are obtained by pushing identity matrices through torch.fft in float64, i.e. they ARE the reference's
-operator (tests/test_resample.py::test_resample_operators_match_reference: 1e-12 against fixtures from the reference).
+operator (tests/test_cnn_kernels.py::test_resample_operators_match_reference: 1e-12 against fixtures from the reference).
 
 On the GPU the two contractions run as batched tensor-core products on channels-last bf16 activations
 (csrc/bgemm.cu, sei_bgemm_bf16): width first over batch = (image, row) with A = [P; Q], then height over
