@@ -1,10 +1,15 @@
-"""The CNN's ideal (Fourier-domain) resamplers as explicit operators (models/resample.py, csrc/bgemm.cu) against
-fixtures produced by running the reference's IdealUpsample / IdealDownsample (tests/golden/make_golden.py
-gen_resample, float64): outputs and the autograd vector-Jacobian products.
+"""The hand-written kernels of the restoration CNN beyond the GEMMs (csrc/bgemm.cu, gemm.cu:bgemm_tc_kernel, cnn_elem.cu).
+
+Ideal (Fourier-domain) resamplers as explicit operators (models/resample.py) against fixtures produced by running the
+reference's IdealUpsample / IdealDownsample (tests/golden/make_golden.py gen_resample, float64): outputs and the
+autograd vector-Jacobian products.
   CPU:  the four operator matrices reproduce the reference to 1e-12 (forward and transposed).
-  GPU:  the batched tensor-core product against fp32 matmul of the same bf16 operands (accumulation order only:
-        8e-3 covers the bf16 rounding of the result), and the resamplers on bf16 channels-last activations against
-        the float64 fixtures within the bf16 tolerance 2e-2 (max |a-b| / max |b|)."""
+  GPU:  the batched tensor-core products (tcgen05 and mma.sync kernels) against fp32 matmul of the same bf16 operands
+        (accumulation order only: 8e-3 covers the bf16 rounding of the result), and the resamplers on bf16
+        channels-last activations against the float64 fixtures within the bf16 tolerance 2e-2 (max |a-b| / max |b|).
+Channel LayerNorm, column sums, depthwise 7x7, the 3x3 output convolution and GELU (GPU): against the PyTorch fp32
+formulation of the same op on the same bf16 inputs -- forward / input gradients within bf16 rounding of the result
+(4e-3 .. 6e-3), parameter gradients 2e-3 (fp32 sums)."""
 import numpy as np
 import pytest
 import torch
