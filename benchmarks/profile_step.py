@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--cnn-scales", type=int, default=5)
     ap.add_argument("--rows", type=int, default=45)
     ap.add_argument("--torch-adam", action="store_true")
+    ap.add_argument("--sr", type=int, default=0, help="SR factor (0: deblurring)")
     ap.add_argument("--copies", action="store_true", help="attribute copy / cat / add kernels to source lines")
     args = ap.parse_args()
     import losses
@@ -28,12 +29,17 @@ def main():
     import physics
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    phys = physics.get_physics(bench.loss_args(), device=dev)
-    loss_fn = losses.get_loss(bench.loss_args(), phys)
-    model = models.get_model(bench.model_args(args.cnn_hidden, args.cnn_scales), physics=phys, device=dev).to(dev)
+    largs, margs = bench.loss_args(), bench.model_args(args.cnn_hidden, args.cnn_scales)
+    if args.sr:                                     # BASELINE configs[2]: SR x2 / x4 instead of deblurring
+        for a in (largs, margs):
+            a.task, a.sr_factor = "sr", args.sr
+        largs.kernel = None
+    phys = physics.get_physics(largs, device=dev)
+    loss_fn = losses.get_loss(largs, phys)
+    model = models.get_model(margs, physics=phys, device=dev).to(dev)
     from sei_b200.optim import Adam as SeiAdam
     opt = SeiAdam(model.parameters(), lr=1e-4) if not args.torch_adam else torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
-    x = torch.rand(args.batch, 3, 256, 256, device=dev)
+    x = torch.rand(args.batch, 3, 256 * (args.sr or 1), 256 * (args.sr or 1), device=dev)
     y = phys(x)
 
     def step():

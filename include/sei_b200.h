@@ -255,6 +255,15 @@ int sei_bias_pattern_add_bf16(void* out, const float* pat, const float* bias, lo
 int sei_bias_pattern_grad_bf16(const void* gy, const float* pat, float* gbias, void* workspace, long long T, int C, int period,
                                void* stream);
 
+/* The same channel LayerNorm for 1..32 channels of any count (one thread per row): the 3-channel normalisation of the SR
+ * model's input stage (reference Upsample(in_channels=3), src/models/convolutional.py:95-104).  Same semantics as
+ * sei_ln_cl_*; workspace of sei_ln_small_workspace_bytes(C) bytes. */
+long long sei_ln_small_workspace_bytes(int C);
+int sei_ln_small_forward_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                              long long T, int C, float eps, void* stream);
+int sei_ln_small_backward_bf16(const void* gy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                               void* dx, float* dgamma, float* dbeta, void* workspace, long long T, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1279,3 +1279,140 @@ extern "C" int sei_bias_pattern_grad_bf16(const void* gy, const float* pat, floa
                                                       colsum_slots(C, threads), C, C);
     return finish_launch("colsum_final_kernel");
 }
+
+// ---------------------------------------------------------------- channel LayerNorm for a handful of channels
+// The SR model's input stage normalises over the 3 image channels (reference Upsample(in_channels=3): LayerNorm(3),
+// src/models/convolutional.py:95-104): 2.1 M rows of 3 values at 512 x 512 x 8.  The library's row-wise kernels
+// take 9 ms per call on such rows; one thread per row is all it needs.  Any C <= 32.
+namespace sei {
+
+constexpr int kLnSmallMaxC = 32;
+
+__global__ void __launch_bounds__(256) ln_small_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                           float* __restrict__ mean, float* __restrict__ rstd,
+                                                           long long T, int C, float eps)
+{
+    const float invC = 1.0f / (float)C;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < T; r += (long long)gridDim.x * blockDim.x) {
+        float v[kLnSmallMaxC];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kLnSmallMaxC; ++c)
+            if (c < C) {
+                v[c] = __bfloat162float(x[r * C + c]);
+                s += v[c];
+            }
+        const float mu = s * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < kLnSmallMaxC; ++c)
+            if (c < C) q = fmaf(v[c] - mu, v[c] - mu, q);
+        const float rs = rsqrtf(q * invC + eps);
+#pragma unroll
+        for (int c = 0; c < kLnSmallMaxC; ++c)
+            if (c < C) y[r * C + c] = __float2bfloat16_rn(fmaf((v[c] - mu) * rs, __ldg(gamma + c), __ldg(beta + c)));
+        mean[r] = mu;
+        rstd[r] = rs;
+    }
+}
+
+// dx per row; per-CTA partial sums of dgamma / dbeta -> partial[cta][2][C] (combined by colsum_final_kernel)
+__global__ void __launch_bounds__(256) ln_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                                                           float* __restrict__ partial, long long T, int C)
+{
+    __shared__ float red[8][2 * kLnSmallMaxC];
+    const float invC = 1.0f / (float)C;
+    float dg[kLnSmallMaxC], db[kLnSmallMaxC];
+#pragma unroll
+    for (int c = 0; c < kLnSmallMaxC; ++c) dg[c] = db[c] = 0.f;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < T; r += (long long)gridDim.x * blockDim.x) {
+        const float mu = mean[r], rs = rstd[r];
+        float xh[kLnSmallMaxC], g[kLnSmallMaxC];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < kLnSmallMaxC; ++c)
+            if (c < C) {
+                xh[c] = (__bfloat162float(x[r * C + c]) - mu) * rs;
+                const float go = __bfloat162float(gy[r * C + c]);
+                dg[c] = fmaf(go, xh[c], dg[c]);
+                db[c] += go;
+                g[c] = go * __ldg(gamma + c);
+                s1 += g[c];
+                s2 = fmaf(g[c], xh[c], s2);
+            }
+        const float m1 = s1 * invC, m2 = s2 * invC;
+#pragma unroll
+        for (int c = 0; c < kLnSmallMaxC; ++c)
+            if (c < C) dx[r * C + c] = __float2bfloat16_rn(rs * (g[c] - m1 - xh[c] * m2));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < kLnSmallMaxC; ++c)
+        if (c < C) {
+            const float a = warp_sum(dg[c]), b = warp_sum(db[c]);
+            if (lane == 0) {
+                red[warp][c] = a;
+                red[warp][C + c] = b;
+            }
+        }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * C) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 2 * C + threadIdx.x] = s;
+    }
+}
+
+static int ln_small_ctas(int sm_count) { return sm_count * 8; }
+
+}  // namespace sei
+
+extern "C" long long sei_ln_small_workspace_bytes(int C)
+{
+    DeviceProps dp;
+    if (get_device_props(&dp) || C < 1 || C > kLnSmallMaxC) return -1;
+    return (long long)ln_small_ctas(dp.sm_count) * 2 * C * (long long)sizeof(float);
+}
+
+extern "C" int sei_ln_small_forward_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                         float* rstd, long long T, int C, float eps, void* stream)
+{
+    SEI_REQUIRE(x && gamma && beta && y && mean && rstd, "null pointer argument");
+    SEI_REQUIRE(T >= 0 && C >= 1 && C <= kLnSmallMaxC, "bad shape T=%lld C=%d (1..%d channels)", T, C, kLnSmallMaxC);
+    if (T == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<long long>((T + 255) / 256, (long long)ln_small_ctas(dp.sm_count));
+    ln_small_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, T, C, eps);
+    return finish_launch("ln_small_fwd_kernel");
+}
+
+extern "C" int sei_ln_small_backward_bf16(const void* gy, const void* x, const float* mean, const float* rstd,
+                                          const float* gamma, void* dx, float* dgamma, float* dbeta, void* workspace,
+                                          long long T, int C, void* stream)
+{
+    SEI_REQUIRE(gy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "null pointer argument");
+    SEI_REQUIRE(T >= 0 && C >= 1 && C <= kLnSmallMaxC, "bad shape T=%lld C=%d (1..%d channels)", T, C, kLnSmallMaxC);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (T == 0) {
+        SEI_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
+        SEI_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+        return 0;
+    }
+    const int grid = (int)std::min<long long>((T + 255) / 256, (long long)ln_small_ctas(dp.sm_count));
+    ln_small_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gy), mean,
+                                              rstd, gamma, static_cast<__nv_bfloat16*>(dx), static_cast<float*>(workspace), T, C);
+    rc = finish_launch("ln_small_bwd_kernel");
+    if (rc) return rc;
+    colsum_final_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), dgamma, dbeta, grid, 2 * C, C);
+    return finish_launch("colsum_final_kernel");
+}

@@ -760,7 +760,9 @@ struct BgemmTcParams {
     long long items;             // batches * n_tiles
 };
 
-template <int BN, int STAGES>
+// RES: the operator block is resident in shared memory (loaded once); otherwise its 128 x 64 tiles travel through the
+// ring next to the X tiles (operators too large to keep: K > 512 at two row blocks), re-read from L2 per work item.
+template <int BN, int STAGES, bool RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_d, const __grid_constant__ BgemmTcParams p)
@@ -773,8 +775,10 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* sA = smem_raw + (((raw + 1023u) & ~1023u) - raw);           // [mb][kb] tiles of 128 x 64, K-major SW128
-    unsigned char* sX = sA + (size_t)p.mb * p.kb * A_TILE;                      // [STAGES][BN/64] boxes of 64 k x 64 n
-    unsigned char* slabs0 = sX + (size_t)STAGES * X_STAGE;
+    const uint32_t a_stage = RES ? 0u : (uint32_t)p.mb * A_TILE;                // operator tiles inside a ring stage
+    const uint32_t stage_bytes = a_stage + X_STAGE;
+    unsigned char* sX = sA + (RES ? (size_t)p.mb * p.kb * A_TILE : 0);          // [STAGES]([mb] A tiles,) [BN/64] boxes of 64 k x 64 n
+    unsigned char* slabs0 = sX + (size_t)STAGES * stage_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_row0 = blockIdx.y * p.mb * 128;
@@ -808,11 +812,12 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // resident operator
-            mbar_arrive_expect_tx(&a_bar, (uint32_t)(p.mb * p.kb) * A_TILE);
-            for (int mb = 0; mb < p.mb; ++mb)
-                for (int kb = 0; kb < p.kb; ++kb)
-                    tma_load_2d(sA + (size_t)(mb * p.kb + kb) * A_TILE, &map_a, kb * BK, m_row0 + mb * 128, &a_bar);
+            if (RES) {          // resident operator
+                mbar_arrive_expect_tx(&a_bar, (uint32_t)(p.mb * p.kb) * A_TILE);
+                for (int mb = 0; mb < p.mb; ++mb)
+                    for (int kb = 0; kb < p.kb; ++kb)
+                        tma_load_2d(sA + (size_t)(mb * p.kb + kb) * A_TILE, &map_a, kb * BK, m_row0 + mb * 128, &a_bar);
+            }
             uint32_t it = 0;
             for (long long w = blockIdx.x; w < p.items; w += gridDim.x) {
                 const long long bt = w / p.n_tiles;
@@ -821,19 +826,23 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, use = it / STAGES;
                     if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
-                    mbar_arrive_expect_tx(&full_bar[s], X_STAGE);
+                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    unsigned char* st = sX + (size_t)s * stage_bytes;
+                    if (!RES)
+                        for (int mb = 0; mb < p.mb; ++mb)
+                            tma_load_2d(st + (size_t)mb * A_TILE, &map_a, kb * BK, m_row0 + mb * 128, &full_bar[s]);
                     const int k0 = kb * BK;
                     const int ko = k0 / p.k_inner, ki = k0 - ko * p.k_inner;
 #pragma unroll
                     for (int nb = 0; nb < BN / 64; ++nb)
-                        tma_load_5d(sX + (size_t)s * X_STAGE + nb * (BK * 128), &map_x, n0 + 64 * nb, ki, ko, bi, bo, &full_bar[s]);
+                        tma_load_5d(st + a_stage + nb * (BK * 128), &map_x, n0 + 64 * nb, ki, ko, bi, bo, &full_bar[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16_kmn(128, BN);
-            mbar_wait(&a_bar, 0);
+            if (RES) mbar_wait(&a_bar, 0);
             tc_fence_after();
             uint32_t it = 0, tcount = 0;
             for (long long w = blockIdx.x; w < p.items; w += gridDim.x, ++tcount) {
@@ -844,9 +853,11 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t s = it % STAGES;
                     mbar_wait(&full_bar[s], (it / STAGES) & 1);
                     tc_fence_after();
-                    const uint64_t dx = umma_smem_desc_mn_sw128(smem_u32(sX + (size_t)s * X_STAGE), BK * 128);
+                    unsigned char* st = sX + (size_t)s * stage_bytes;
+                    const uint64_t dx = umma_smem_desc_mn_sw128(smem_u32(st + a_stage), BK * 128);
                     for (int mb = 0; mb < p.mb; ++mb) {
-                        const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + (size_t)(mb * p.kb + kb) * A_TILE));
+                        const uint64_t da = umma_smem_desc_sw128(smem_u32(RES ? sA + (size_t)(mb * p.kb + kb) * A_TILE
+                                                                              : st + (size_t)mb * A_TILE));
                         const uint32_t tmem_d = tmem_base + (acc * (uint32_t)p.mb + (uint32_t)mb) * BN;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -1049,10 +1060,15 @@ int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int
     if (dp.cc_major != 10) return 1;
     // shape rules: see the kernel comment
     const int mb_total = (M + 127) / 128;
-    const int mb = std::min(2, mb_total);                                   // 128-row blocks per CTA
+    int mb = std::min(2, mb_total);                                         // 128-row blocks per CTA
     const int kb = Kpad / 64;
     // (rows of A beyond rows_a are out of the tensor map's bounds: TMA zero-fills them)
-    if ((long long)mb * kb * 16384 > 128 * 1024) return 1;
+    bool resident = true;
+    if ((long long)mb * kb * 16384 > 128 * 1024) mb = 1;                    // one row block resident (K <= 512)
+    if ((long long)mb * kb * 16384 > 128 * 1024) {                          // stream the operator through the ring
+        resident = false;
+        mb = std::min(2, mb_total);
+    }
     if (N % 8 != 0 || K % 16 != 0 || batches % b_inner != 0) return 1;
     if (!(k_inner % 64 == 0 || (pow2(k_inner) && k_inner < 64)) || K % k_inner != 0) return 1;
     if (!(m_inner % 32 == 0 || (pow2(m_inner) && m_inner < 32)) || M % m_inner != 0) return 1;
@@ -1074,14 +1090,26 @@ int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int
     const int m_blocks = (mb_total + mb - 1) / mb;
     const unsigned gx = (unsigned)std::min<long long>(p.items, std::max(1, dp.sm_count / m_blocks));
     constexpr int ST = 3;
-    if (bn == 64) {
-        const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * 64 * 64 * 2 + 4 * 2 * 32 * 128 + 1024;
-        SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST>, smem));
-        bgemm_tc_kernel<64, ST><<<dim3(gx, m_blocks), kGemmThreads, smem, st>>>(ma, mx, md, p);
+    const size_t slabs = 4 * 2 * 32 * 128 + 1024;
+    const dim3 grid(gx, m_blocks);
+    if (resident) {
+        const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * bn * 64 * 2 + slabs;
+        if (bn == 64) {
+            SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST, true>, smem));
+            bgemm_tc_kernel<64, ST, true><<<grid, kGemmThreads, smem, st>>>(ma, mx, md, p);
+        } else {
+            SEI_CUDA(allow_smem(bgemm_tc_kernel<128, ST, true>, smem));
+            bgemm_tc_kernel<128, ST, true><<<grid, kGemmThreads, smem, st>>>(ma, mx, md, p);
+        }
     } else {
-        const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * 128 * 64 * 2 + 4 * 2 * 32 * 128 + 1024;
-        SEI_CUDA(allow_smem(bgemm_tc_kernel<128, ST>, smem));
-        bgemm_tc_kernel<128, ST><<<dim3(gx, m_blocks), kGemmThreads, smem, st>>>(ma, mx, md, p);
+        const size_t smem = (size_t)ST * ((size_t)mb * 16384 + (size_t)bn * 64 * 2) + slabs;
+        if (bn == 64) {
+            SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST, false>, smem));
+            bgemm_tc_kernel<64, ST, false><<<grid, kGemmThreads, smem, st>>>(ma, mx, md, p);
+        } else {
+            SEI_CUDA(allow_smem(bgemm_tc_kernel<128, ST, false>, smem));
+            bgemm_tc_kernel<128, ST, false><<<grid, kGemmThreads, smem, st>>>(ma, mx, md, p);
+        }
     }
     return finish_launch("bgemm_tc_kernel");
 }

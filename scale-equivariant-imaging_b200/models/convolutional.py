@@ -173,7 +173,7 @@ class LayerNorm(Module):
     def forward(self, x):
         xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)                   # channels last: a view
         rows = xl.reshape(-1, xl.shape[-1])
-        if ops.ln_cl_supported(rows):                                             # hand-written kernels (csrc/cnn_elem.cu)
+        if ops.ln_any_supported(rows):                                            # hand-written kernels (csrc/cnn_elem.cu)
             out = ops.layer_norm_cl(rows, self.ln.weight, self.ln.bias, self.ln.eps).view(xl.shape)
             return out.permute(0, 3, 1, 2)
         out = F.layer_norm(xl, self.ln.normalized_shape, self.ln.weight.to(xl.dtype), self.ln.bias.to(xl.dtype),

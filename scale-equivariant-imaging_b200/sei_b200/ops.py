@@ -301,6 +301,13 @@ def ln_cl_supported(x_rows):
             and x_rows.shape[1] % 8 == 0 and _lib.load().sei_ln_cl_backward_workspace_bytes(int(x_rows.shape[1])) >= 0)
 
 
+def ln_any_supported(x_rows):
+    """rows the channel LayerNorm kernels take: the vectorised ones (ln_cl_supported) or, for up to 32 channels of any
+    count, the one-thread-per-row ones"""
+    return ln_cl_supported(x_rows) or (x_rows.is_cuda and x_rows.dtype == torch.bfloat16 and x_rows.dim() == 2
+                                       and x_rows.is_contiguous() and 1 <= x_rows.shape[1] <= 32)
+
+
 class _LayerNormCL(torch.autograd.Function):
     """y = LayerNorm_C(x) on rows [T, C] (bf16), fp32 affine parameters; backward by the hand-written kernels"""
 
@@ -311,9 +318,10 @@ class _LayerNormCL(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(T, dtype=torch.float32, device=x.device)
         rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+        ctx.small = not ln_cl_supported(x)
+        fwd = _lib.load().sei_ln_small_forward_bf16 if ctx.small else _lib.load().sei_ln_cl_forward_bf16
         with torch.cuda.device(x.device):
-            check(_lib.load().sei_ln_cl_forward_bf16(_ptr(x), _ptr(g32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), T, Cc,
-                                                     float(eps), _stream(x)))
+            check(fwd(_ptr(x), _ptr(g32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), T, Cc, float(eps), _stream(x)))
         ctx.save_for_backward(x, mean, rstd, g32)
         ctx.param_dtypes = (gamma.dtype, beta.dtype)
         return y
@@ -327,10 +335,12 @@ class _LayerNormCL(torch.autograd.Function):
         dx = torch.empty_like(x)
         dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
         db = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+        ws_bytes = lib.sei_ln_small_workspace_bytes(Cc) if ctx.small else lib.sei_ln_cl_backward_workspace_bytes(Cc)
+        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
+        bwd = lib.sei_ln_small_backward_bf16 if ctx.small else lib.sei_ln_cl_backward_bf16
         with torch.cuda.device(x.device):
-            check(lib.sei_ln_cl_backward_bf16(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(dx), _ptr(dg),
-                                              _ptr(db), _ptr(ws), T, Cc, _stream(x)))
+            check(bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(dx), _ptr(dg), _ptr(db), _ptr(ws), T, Cc,
+                      _stream(x)))
         return dx, dg.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
 
 
