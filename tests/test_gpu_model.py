@@ -129,3 +129,51 @@ def test_weight_gradients_accumulate_in_place(golden, dev):
         assert p.grad.data_ptr() == ptrs[k]
         ref = 2 * once[k]
         assert float((p.grad - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-7, k
+
+
+def test_training_reduces_loss_and_tracks_torch_adam(dev):
+    """end-to-end sanity of the whole stack (operators, losses, CNN kernels, optimizer, weight shadows): 25 supervised
+    steps on a fixed batch must reduce the loss, and sei_b200.optim.Adam must follow torch.optim.Adam's trajectory"""
+    from argparse import Namespace
+    import losses
+    import models.convolutional as mc
+    import physics
+    from sei_b200.optim import Adam as SeiAdam
+    args = Namespace(task="deblurring", noise_level=5, physics_v2=True, kernel="Gaussian_R2", sr_factor=None,
+                     physics_true_adjoint=False, partial_sure=True, sure_margin=None, partial_sure_sr=False,
+                     Loss__crop_training_pairs=False, Loss__crop_size=48, ProposedLoss__stop_gradient=True,
+                     ProposedLoss__sure_alternative=None, ProposedLoss__alpha_tradeoff=1.0,
+                     ProposedLoss__transforms="Scaling_Transforms", ScalingTransform__kind="padded",
+                     ScalingTransform__antialias=False, method="supervised", sure_cropped_div=True,
+                     sure_averaged_cst=None)
+    phys = physics.get_physics(args, device=dev)
+    loss_fn = losses.get_loss(args, phys)
+    torch.manual_seed(0)
+    x = torch.rand(4, 3, 64, 64, device=dev)
+    y = phys(x)
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, inp, *a):
+            return self.m(inp)
+
+    curves = {}
+    for name, make in (("sei", lambda ps: SeiAdam(ps, lr=2e-3)), ("torch", lambda ps: torch.optim.Adam(ps, lr=2e-3))):
+        torch.manual_seed(1)
+        net = mc.ConvolutionalModel(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+                                    hidden_channels=16, inout_convs=True, scales=3).to(dev)
+        model, opt = Wrapped(net), make(net.parameters())
+        curve = []
+        for _ in range(25):
+            opt.zero_grad(set_to_none=False)
+            loss = loss_fn(x=x, y=y, model=model)
+            loss.backward()
+            opt.step()
+            curve.append(float(loss.detach()))
+        curves[name] = curve
+    for name, c in curves.items():
+        assert c[-1] < 0.7 * c[0], (name, c[0], c[-1])
+    assert abs(curves["sei"][-1] - curves["torch"][-1]) < 0.15 * curves["torch"][-1], (curves["sei"][-1], curves["torch"][-1])
