@@ -174,6 +174,12 @@ int sei_add_noise_f32(const float* y, const float* noise, long long n, float sig
 int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                      long long lda, long long ldb, long long ldd, int out_f32, int tile_n, void* stream);
 
+/* D (bf16) = (A B^T) * gelu'(H), element-wise in the epilogue: the input gradient of the convolution that FOLLOWS the
+ * GELU of a ConvBlock (reference src/models/convolutional.py:40-42: conv2 -> gelu -> conv3) with the GELU backward
+ * fused in, H = the saved pre-activation [M, N] (bf16, row pitch ld_h).  N % 64 == 0, ldd % 8 == 0. */
+int sei_gemm_bf16_tn_gelu_bwd(const void* A, const void* B, void* D, const void* H, long long M, int N, int K,
+                              long long lda, long long ldb, long long ldd, long long ld_h, void* stream);
+
 /* D[M, N] (fp32) = A[K, M]^T * B[K, N]: both operands are read with the contraction index as their ROW (UMMA MN-major
  * shared-memory layout), so the weight gradient dL/dW = (dL/dy)^T x of a pointwise convolution needs no transposed
  * copies of the activations.  lda, ldb multiples of 8; K = pixels.  Split-K with fp32 atomics when M*N is small. */

@@ -12,6 +12,7 @@
 // small, so every warp-level access is a contiguous >= 512-byte run whatever C is.  VPL > 0: the row is cached in
 // registers (C = 8 * G * VPL); VPL = 0: any C % 8 == 0, the row is re-read from L1/L2 for each pass.
 #include "sei_common.cuh"
+#include "gelu.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
 
@@ -1090,20 +1091,6 @@ extern "C" int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* g
 // Abramowitz-Stegun 7.1.26 rational form (|error| < 1.5e-7, far below bf16 resolution): one MUFU.RCP, one MUFU.EX2 and
 // a degree-5 polynomial.  The backward kernel shares the exponential: gelu'(x) = Phi(x) + x phi(x).
 namespace sei {
-
-__device__ __forceinline__ void gelu_parts(float x, float& Phi, float& phi)
-{
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));     // MUFU.RCP (the rounded reciprocal costs ~8 instructions)
-    const float e = __expf(-z * z);                                  // exp(-x^2 / 2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erf_abs = fmaf(-poly * t, e, 1.0f);                  // erf(|x| / sqrt 2)
-    Phi = 0.5f * (1.0f + copysignf(erf_abs, x));
-    phi = 0.39894228040143268f * e;
-}
 
 // Software-pipelined: the loads of the next group of kGeluUnroll vectors are issued before the current group is
 // evaluated.  All threads run the same grid-stride loop in lock step, so without the prefetch the memory system idles

@@ -18,6 +18,7 @@
 //            convert, store 16-byte vectors
 // Out-of-range rows/columns/k are zero-filled by TMA on load and masked on store.
 #include "sei_common.cuh"
+#include "gelu.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -140,6 +141,8 @@ struct GemmParams {
     int splits;
     int tma_store;       // bf16 output staged through shared memory and written with bulk tensor stores
     int accumulate;      // fp32 output: add to D instead of overwriting it (weight gradients accumulated in place)
+    const __nv_bfloat16* gelu_h;   // optional [M, N] (row pitch ld_h): D = (A B^T) * gelu'(gelu_h)  (TMA-store epilogue only)
+    int ld_h;
 };
 
 // first version: one output tile per CTA (kept for A/B measurements: SEI_GEMM_V1=1)
@@ -279,6 +282,38 @@ gemm_bf16_tn_kernel_v1(const __grid_constant__ CUtensorMap map_a, const __grid_c
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The GELU backward fused into the input-gradient GEMM of the layer that follows it (reference ConvBlock: conv2 -> GELU
+// -> conv3): the epilogue thread that owns a row chunk of dL/da = gy W3 multiplies it by gelu'(h) read from the saved
+// pre-activation, so dL/dh is written directly (no separate pass over the 4C-wide gradient).
+__device__ __forceinline__ void epilogue_gelu_bwd(const GemmParams& p, int row, int col0, uint32_t (&r0)[32], uint32_t (&r1)[32])
+{
+    if (row >= p.M) return;
+    const uint4* hp = reinterpret_cast<const uint4*>(p.gelu_h + (size_t)row * p.ld_h + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (col0 + 8 * j + 8 > p.N) break;
+        const uint4 raw = __ldg(hp + j);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 hv = __bfloat1622float2(h2[e]);
+            float Phi, phi;
+            const int cc = 8 * j + 2 * e;
+            gelu_parts(hv.x, Phi, phi);
+            const float d0 = fmaf(hv.x, phi, Phi);
+            gelu_parts(hv.y, Phi, phi);
+            const float d1 = fmaf(hv.y, phi, Phi);
+            if (cc < 32) {
+                r0[cc] = __float_as_uint(__uint_as_float(r0[cc]) * d0);
+                r0[cc + 1] = __float_as_uint(__uint_as_float(r0[cc + 1]) * d1);
+            } else {
+                r1[cc - 32] = __float_as_uint(__uint_as_float(r1[cc - 32]) * d0);
+                r1[cc - 31] = __float_as_uint(__uint_as_float(r1[cc - 31]) * d1);
+            }
+        }
+    }
 }
 
 // epilogue of one 32-column chunk held in registers: bias, convert, store (masked at the matrix edge)
@@ -469,6 +504,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
                     tmem_ld_wait();
+                    if (p.gelu_h) epilogue_gelu_bwd(p, row, n0 + c, r0, r1);
                     unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;   // alternates across tiles too
                     if (lane == 0) bulk_wait_read<1>();      // the store that last read this slab has finished reading
                     __syncwarp();
@@ -683,6 +719,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
                 tmem_ld_wait();
+                if (p.gelu_h) epilogue_gelu_bwd(p, m0 + q * 32 + lane, n0 + c, r0, r1);
                 unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;
                 if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
@@ -1118,8 +1155,29 @@ int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int
 
 using namespace sei;
 
+static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
+                            long long lda, long long ldb, long long ldd, int out_f32, int tile_n,
+                            const void* gelu_h, long long ld_h, void* stream);
+
 extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                                 long long lda, long long ldb, long long ldd, int out_f32, int tile_n, void* stream)
+{
+    return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, out_f32, tile_n, nullptr, 0, stream);
+}
+
+// D (bf16) = (A B^T) * gelu'(H): the input gradient of `conv3` with the GELU backward applied in the epilogue.
+// H: bf16 [M, N] with row pitch ld_h (multiple of 8); needs N % 64 == 0 and ldd % 8 == 0 (TMA-store epilogue).
+extern "C" int sei_gemm_bf16_tn_gelu_bwd(const void* A, const void* B, void* D, const void* H, long long M, int N, int K,
+                                         long long lda, long long ldb, long long ldd, long long ld_h, void* stream)
+{
+    SEI_REQUIRE(H != nullptr && aligned16(H) && ld_h % 8 == 0 && ld_h >= N, "H must be 16-byte aligned with a row pitch >= N that is a multiple of 8");
+    SEI_REQUIRE(N % 64 == 0 && ldd % 8 == 0, "the fused GELU backward needs N %% 64 == 0 and ldd %% 8 == 0 (N=%d)", N);
+    return gemm_bf16_tn_impl(A, B, D, nullptr, M, N, K, lda, ldb, ldd, 0, 0, H, ld_h, stream);
+}
+
+static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
+                            long long lda, long long ldb, long long ldd, int out_f32, int tile_n,
+                            const void* gelu_h, long long ld_h, void* stream)
 {
     SEI_REQUIRE(A && B && D, "null pointer argument");
     SEI_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "bad shape M=%lld N=%d K=%d", M, N, K);
@@ -1141,9 +1199,11 @@ extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const flo
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
+    p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
     p.tma_store = (!out_f32 && bn >= 64 && ldd % 8 == 0 && !(nts && *nts == '1')) ? 1 : 0;
+    SEI_REQUIRE(!gelu_h || p.tma_store, "the fused GELU backward needs the TMA-store epilogue (N >= 64, ldd %% 8 == 0)");
     CUtensorMap md = ma;
     if (p.tma_store) {
         rc = make_map_bf16(&md, D, M, N, ldd, 32);
@@ -1224,6 +1284,7 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
+    p.gelu_h = nullptr; p.ld_h = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);

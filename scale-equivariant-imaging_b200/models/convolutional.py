@@ -29,6 +29,10 @@ CL = torch.channels_last
 # float32 together with a patched _gemm_tn to check the network's structure against the reference at fp32 accuracy.
 COMPUTE_DTYPE = torch.bfloat16
 _NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"     # A/B switch for measurements
+# gelu'(h) in the epilogue of conv3's input-gradient GEMM (sei_gemm_bf16_tn_gelu_bwd).  Measured on B200: it removes the
+# 9 ms GELU-backward pass but the four epilogue warps then spend longer on the erf arithmetic than the tensor cores
+# on the tile (CTA-pair GEMMs 76 -> 93 ms, N = 128 GEMMs 6 -> 13 ms per step): off by default.
+_GELU_FUSION = __import__("os").environ.get("SEI_GELU_FUSION", "0") == "1"
 
 
 def _gemm_tn(a, b, bias, out_dtype):
@@ -82,6 +86,39 @@ class _GemmTN(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
+class _GeluGemmTN(torch.autograd.Function):
+    """out[T, N] = gelu(h[T, K]) @ w[N, K]^T + bias: the GELU and the pointwise convolution after it (ConvBlock.gelu,
+    ConvBlock.conv3) as one autograd node, so that the backward pass can apply gelu'(h) in the epilogue of the
+    input-gradient GEMM (sei_gemm_bf16_tn_gelu_bwd) instead of a separate pass over the 4C-wide gradient."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, w_bf16, wt_getter, param=None):
+        a = ops.gelu_raw(h)
+        ctx.save_for_backward(h, a, w_bf16)
+        ctx.has_bias = bias is not None
+        ctx.wt_getter = wt_getter
+        ctx.param = param
+        return _gemm_tn(a, w_bf16, bias, COMPUTE_DTYPE)
+
+    @staticmethod
+    def backward(ctx, gy):
+        h, a, w_bf16 = ctx.saved_tensors
+        gy = gy.contiguous()
+        gh = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gh = ops.gemm_bf16_tn_gelu_bwd(gy, ctx.wt_getter(), h)                    # (gy @ w) * gelu'(h)
+        if ctx.needs_input_grad[1]:
+            g = None if (ctx.param is None or _NO_WGRAD_ACC) else ctx.param.grad
+            if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda
+                    and g.numel() == gy.shape[1] * a.shape[1]):
+                _gemm_atb(gy, a, out=g.view(gy.shape[1], a.shape[1]))
+            else:
+                gw = _gemm_atb(gy, a)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum_bf16(gy) if ops.ln_cl_supported(gy) else torch.sum(gy, 0, dtype=torch.float32)
+        return gh, gw, gb, None, None, None
+
+
 def _pad_k(a):
     """contiguous copy of a 2-D bf16 matrix with its last (contraction) dimension padded to a multiple of 8"""
     a = a.contiguous()
@@ -131,6 +168,19 @@ class _GemmConv2d(Conv2d):
 
     def forward_nobias(self, x):
         return self.forward(x, use_bias=False)
+
+    def gelu_fusable(self, h):
+        """gelu(h) -> this convolution can run as one node with the GELU backward in the dgrad epilogue"""
+        return (self.kernel_size == (1, 1) and h.is_cuda and h.dtype == torch.bfloat16 == COMPUTE_DTYPE
+                and h.is_contiguous(memory_format=CL) and self.in_channels % 64 == 0 and self.out_channels % 8 == 0
+                and _GELU_FUSION)
+
+    def forward_after_gelu(self, h):
+        B, C, H, W = h.shape
+        h2 = h.permute(0, 2, 3, 1).reshape(B * H * W, C)                            # view of the channels-last tensor
+        w2, w_bf16 = self._weight_matrix()
+        out = _GeluGemmTN.apply(h2, w2, self.bias, w_bf16, self._weight_matrix_t, self.weight)
+        return out.view(B, H, W, -1).permute(0, 3, 1, 2)
 
     def forward(self, x, use_bias=True):
         B, C, H, W = x.shape
@@ -218,8 +268,11 @@ class ConvBlock(Module):
             x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
-        x1 = ops.gelu(x1) if ops.gelu_supported(x1) else self.gelu(x1)
-        x1 = self.conv3(x1)
+        if self.conv3.gelu_fusable(x1):
+            x1 = self.conv3.forward_after_gelu(x1)            # gelu + conv3, gelu' fused into conv3's dgrad epilogue
+        else:
+            x1 = ops.gelu(x1) if ops.gelu_supported(x1) else self.gelu(x1)
+            x1 = self.conv3(x1)
         return x + x1
 
 

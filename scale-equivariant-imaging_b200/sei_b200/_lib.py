@@ -35,6 +35,7 @@ SIGNATURES = {
     "sei_roll_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "sei_add_noise_f32": (C.c_int, [_vp, _vp, _ll, _f, _vp, _vp]),
     "sei_gemm_bf16_atb": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _vp]),
+    "sei_gemm_bf16_tn_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_gemm_bf16_atb_accumulate": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _vp]),
     "sei_gemm_bf16_tn": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),
     "sei_ln_cl_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),

@@ -251,6 +251,31 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     return d
 
 
+def gemm_bf16_tn_gelu_bwd(a, b, h):
+    """D[M,N] (bf16) = (a[M,K] @ b[N,K]^T) * gelu'(h[M,N]): dgrad of the layer after a GELU with the GELU backward in the
+    GEMM epilogue (sei_gemm_bf16_tn_gelu_bwd)"""
+    for t, name in ((a, "a"), (b, "b"), (h, "h")):
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise SeiError(f"gemm_bf16_tn_gelu_bwd: {name} must be a 2-D CUDA bf16 tensor with a contiguous last dimension")
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2 or tuple(h.shape) != (M, N):
+        raise SeiError("gemm_bf16_tn_gelu_bwd: shape mismatch")
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn_gelu_bwd(_ptr(a), _ptr(b), _ptr(d), _ptr(h), M, N, K, a.stride(0), b.stride(0), N,
+                                                    h.stride(0), _stream(a)))
+    return d
+
+
+def gelu_raw(x):
+    """gelu(x) without autograd bookkeeping (dense bf16 CUDA tensor)"""
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_gelu_bf16(_ptr(x), None, _ptr(y), x.numel(), _stream(x)))
+    return y
+
+
 def gemm_bf16_atb(a, b, out=None):
     """D[M,N] (fp32) = a[K,M]^T @ b[K,N] on the tcgen05 tensor cores, both operands read in place (MN-major).
     out: contiguous fp32 [M, N] tensor to ACCUMULATE into (D += a^T b) instead of allocating a result."""

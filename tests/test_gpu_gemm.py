@@ -107,3 +107,18 @@ def test_gemm_throughput_smoke(dev):
     d = ops.gemm_bf16_tn(a, b, None)
     ref = (a[:64].float() @ b.float().t())
     assert float((d[:64].float() - ref).abs().max() / ref.abs().max()) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 256, 64), (300, 128, 32), (8192, 2048, 512), (130, 64, 16), (2048, 512, 128)])
+def test_gemm_with_gelu_backward_epilogue(dev, M, N, K):
+    """(A B^T) * gelu'(H) in the epilogue (single-CTA and CTA-pair kernels) vs the unfused fp32 formulation"""
+    from sei_b200 import ops
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    h = (torch.randn(M, N, device=dev) * 2).bfloat16()
+    d = ops.gemm_bf16_tn_gelu_bwd(a, b, h)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).sum().backward()
+    ref = (a.float() @ b.float().t()) * hf.grad
+    assert float((d.float() - ref).abs().max() / ref.abs().max()) < 8e-3
