@@ -67,6 +67,17 @@ def test_argument_validation_needs_no_device():
     assert rc == -22 and b"rate" in lib.sei_last_error()
     with pytest.raises(_lib.SeiError):
         _lib.check(rc)
+    # the CNN-side entry points validate before touching a device as well
+    assert lib.sei_ln_cl_forward_bf16(None, None, None, None, None, None, 4, 32, 1e-6, None) == -22
+    assert lib.sei_ln_cl_forward_bf16(1, 1, 1, 1, 1, 1, 4, 12, 1e-6, None) == -22 and b"multiple of 8" in lib.sei_last_error()
+    assert lib.sei_ln_small_forward_bf16(1, 1, 1, 1, 1, 1, 4, 33, 1e-6, None) == -22
+    assert lib.sei_dwconv7_cl_bf16(None, None, None, None, 1, 8, 8, 8, None) == -22
+    assert lib.sei_dwconv7_cl_bf16(16, 16, None, 16, 1, 8, 8, 12, None) == -22
+    assert lib.sei_conv3x3_small_forward_bf16(16, 16, None, 16, 1, 8, 8, 32, 5, None) == -22 and b"Cout" in lib.sei_last_error()
+    assert lib.sei_gelu_bf16(16, None, 16, 12, None) == -22 and b"multiple of 8" in lib.sei_last_error()
+    assert lib.sei_bgemm_bf16(16, 16, 16, 8, 8, 12, 64, 16, 1, 1, 0, 0, 8, 0, 16, 0, 0, 8, 0, 16, None) == -22
+    assert lib.sei_adam_step_f32(None, None, None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, None) == -22
+    assert lib.sei_gemm_bf16_tn_gelu_bwd(16, 16, 16, None, 128, 64, 64, 64, 64, 64, 64, None) == -22
 
 
 def test_cpu_tensors_fail_loudly():
