@@ -188,14 +188,21 @@ __device__ __forceinline__ void blur_hpass(const float* __restrict__ sMid, int W
 // profile of the 4-wide version showed the LSU shared-memory pipe at 71 % and the FMA pipe at 42 %).  Lanes are
 // laid out 4 rows x 8 column blocks per warp (lane = 4 * block + row); with the intermediate's pitch = 4 (mod 32)
 // every quarter-warp load is conflict-free.  Requires W % 16 == 0 and the padded intermediate.
-template <int K, bool NOISE>
+// XCHG: the two lanes that own adjacent 16-column blocks of a row (lane ^ 4) swap half of their results before storing,
+// so that every store (and noise load) instruction covers whole 32-byte sectors: lane E writes chunks 0 and 2 of both
+// blocks, lane O chunks 1 and 3.  Without it a store instruction wrote 16 bytes at a 64-byte stride per lane and ncu
+// reported 50 % excess L2 sectors for the global stores.  All 32 lanes must execute the item (warp shuffles).
+template <int K, bool NOISE, bool XCHG>
 __device__ __forceinline__ void blur_hpass16_item(const float* __restrict__ src, const float (&tap)[K],
                                                   float* __restrict__ ydst, const float* __restrict__ ndst, float sigma)
 {
     using G = BlurGeom<K>;
     constexpr int P = G::P, LCH = G::LCH, LEFT = G::LEFT, NCH = 4 + 2 * LCH;
+    const bool odd = XCHG && (threadIdx.x & 4) != 0;
+    // element offset of this lane's i-th 16-byte access relative to its own block
+    auto off = [&](int i) { return XCHG ? (odd ? 8 * i - 12 : 8 * i) : 4 * i; };
     float4 nz[4];
-    if (NOISE) {
+    if (NOISE) {          // own block (added before the exchange): the four 16-byte loads of a lane share L1 lines
 #pragma unroll
         for (int i = 0; i < 4; ++i) nz[i] = ld_stream4(ndst + 4 * i);
     }
@@ -213,14 +220,37 @@ __device__ __forceinline__ void blur_hpass16_item(const float* __restrict__ src,
 #pragma unroll
         for (int o = 0; o < 16; ++o) out[o] = fmaf(tap[t], v[LEFT + o + t - P], out[o]);
     }
+    if (NOISE) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (NOISE) {
+        for (int i = 0; i < 4; ++i) {
             out[4 * i + 0] = fmaf(sigma, nz[i].x, out[4 * i + 0]); out[4 * i + 1] = fmaf(sigma, nz[i].y, out[4 * i + 1]);
             out[4 * i + 2] = fmaf(sigma, nz[i].z, out[4 * i + 2]); out[4 * i + 3] = fmaf(sigma, nz[i].w, out[4 * i + 3]);
         }
-        st_stream4(ydst + 4 * i, make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
     }
+    if (XCHG) {
+        // E (even block) sends chunks 1, 3 and receives the partner's chunks 0, 2; O sends 0, 2 and receives 1, 3
+        float rcv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float s0 = odd ? out[e] : out[4 + e], s1 = odd ? out[8 + e] : out[12 + e];
+            rcv[e] = __shfl_xor_sync(0xffffffffu, s0, 4);
+            rcv[4 + e] = __shfl_xor_sync(0xffffffffu, s1, 4);
+        }
+        float fin[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // E: own c0, own c2, partner c0, partner c2;  O: partner c1, partner c3, own c1, own c3
+            fin[e] = odd ? rcv[e] : out[e];
+            fin[4 + e] = odd ? rcv[4 + e] : out[8 + e];
+            fin[8 + e] = odd ? out[4 + e] : rcv[e];
+            fin[12 + e] = odd ? out[12 + e] : rcv[4 + e];
+        }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) out[o] = fin[o];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_stream4(ydst + off(i), make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
 }
 
 template <int K, int NT, bool NOISE, int WT, bool TWO>
@@ -235,26 +265,33 @@ __device__ __forceinline__ void blur_hpass16(const float* __restrict__ sMid, int
     for (int t = 0; t < K; ++t) asm volatile("mov.f32 %0, %1;" : "=f"(tap[t]) : "f"(ch[t]));
     const int nitems = ((th + 3) >> 2) * 4 * NB;
     const bool whole = (th & 3) == 0;      // every item maps to a row of the band: no per-item row check
-    auto run = [&](int item, bool check) {
+    // lane exchange only when every warp is full in every iteration (items per row quad = 4 * NB a multiple of 32)
+    // and only without the noise epilogue: with it the exchange was measured slower (A+noise 61.7 us plain, 64.5 us with
+    // paired noise loads, 68 us with the noise added before the exchange; A alone 49.3 -> 47.0 us with the exchange)
+    const bool xchg = !NOISE && whole && (NB & 7) == 0;
+    auto run = [&](int item, int mode) {   // mode 0: exchange, 1: plain, 2: plain with a row check
         const int j = item & 3, q = item >> 2;
         const int rg = q / NB, k = q - rg * NB;
         const int r = 4 * rg + j;
-        if (!check || r < th) {
-            const int g = r * W + 16 * k;
-            blur_hpass16_item<K, NOISE>(sMid + r * pitch + 16 * k, tap, yrow0 + g, NOISE ? nrow0 + g : nullptr, sigma);
-        }
+        const int g = r * W + 16 * k;
+        if (mode == 0)
+            blur_hpass16_item<K, NOISE, true>(sMid + r * pitch + 16 * k, tap, yrow0 + g, NOISE ? nrow0 + g : nullptr, sigma);
+        else if (mode == 1 || r < th)
+            blur_hpass16_item<K, NOISE, false>(sMid + r * pitch + 16 * k, tap, yrow0 + g, NOISE ? nrow0 + g : nullptr, sigma);
     };
     int item = threadIdx.x;
-    if (whole) {
+    if (xchg) {
         if (TWO) {
             for (; item + NT < nitems; item += 2 * NT) {
-                run(item, false);
-                run(item + NT, false);
+                run(item, 0);
+                run(item + NT, 0);
             }
         }
-        for (; item < nitems; item += NT) run(item, false);
+        for (; item < nitems; item += NT) run(item, 0);
+    } else if (whole) {
+        for (; item < nitems; item += NT) run(item, 1);
     } else {
-        for (; item < nitems; item += NT) run(item, true);
+        for (; item < nitems; item += NT) run(item, 2);
     }
 }
 
