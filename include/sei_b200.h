@@ -270,6 +270,12 @@ int sei_ln_small_forward_bf16(const void* x, const float* gamma, const float* be
 int sei_ln_small_backward_bf16(const void* gy, const void* x, const float* mean, const float* rstd, const float* gamma,
                                void* dx, float* dgamma, float* dbeta, void* workspace, long long T, int C, void* stream);
 
+/* Bicubic resize by a fractional factor: y[planes, Ho, Wo] from x[planes, H, W], scale_* = 1 / scale_factor.  Replaces the
+ * per-image F.interpolate(x_i, scale_factor=rate, mode="bicubic", antialias=...) loop of the reference's
+ * normal_downsampling_transform (src/transforms.py:112-124); antialias selects ATen's _upsample_bicubic2d_aa weights. */
+int sei_resize_bicubic_f32(const float* x, float* y, long long planes, int H, int W, int Ho, int Wo,
+                           float scale_h, float scale_w, int antialias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,6 +152,55 @@ def up_bicubic(y, rate):
     return x
 
 
+def _resize_axis_matrix(n_in, scale_factor, antialias):
+    """dense (n_out, n_in) weight matrix of F.interpolate(mode='bicubic') along one axis, in float64.
+    scale = 1 / scale_factor, n_out = floor(n_in * scale_factor)  (ATen upsample_bicubic2d / _upsample_bicubic2d_aa)."""
+    import math
+    n_out = int(math.floor(n_in * float(scale_factor)))
+    scale = 1.0 / float(scale_factor)
+    M = np.zeros((n_out, n_in), dtype=np.float64)
+    for i in range(n_out):
+        if not antialias:
+            real = scale * (i + 0.5) - 0.5              # area_pixel_compute_source_index(cubic=True): no clamping
+            i0 = math.floor(real)
+            t = real - i0
+            A = -0.75                                   # get_cubic_upsample_coefficients
+            c = [((A * (t + 1) - 5 * A) * (t + 1) + 8 * A) * (t + 1) - 4 * A,
+                 ((A + 2) * t - (A + 3)) * t * t + 1,
+                 ((A + 2) * (1 - t) - (A + 3)) * (1 - t) * (1 - t) + 1,
+                 ((A * (2 - t) - 5 * A) * (2 - t) + 8 * A) * (2 - t) - 4 * A]
+            for k in range(4):
+                M[i, min(max(i0 - 1 + k, 0), n_in - 1)] += c[k]
+        else:
+            support = 2.0 * scale if scale >= 1.0 else 2.0
+            invscale = 1.0 / scale if scale >= 1.0 else 1.0
+            center = scale * (i + 0.5)
+            lo = max(int(center - support + 0.5), 0)
+            hi = min(int(center + support + 0.5), n_in)
+            a = -0.5
+
+            def cubic(v):
+                v = abs(v)
+                if v < 1.0:
+                    return ((a + 2) * v - (a + 3)) * v * v + 1
+                if v < 2.0:
+                    return (((v - 5) * v + 8) * v - 4) * a
+                return 0.0
+
+            w = np.array([cubic((j + lo - center + 0.5) * invscale) for j in range(hi - lo)])
+            M[i, lo:hi] = w / w.sum()
+    return M
+
+
+def resize_bicubic(x, scale_factor, antialias):
+    """normal_downsampling_transform (reference src/transforms.py:112-124): F.interpolate(x_i, scale_factor=rate,
+    mode='bicubic', antialias=antialiased) for every image, restated with dense per-axis weight matrices."""
+    x = np.asarray(x)
+    My = _resize_axis_matrix(x.shape[-2], scale_factor, antialias)
+    Mx = _resize_axis_matrix(x.shape[-1], scale_factor, antialias)
+    return np.einsum("ih,bchw,jw->bcij", My, x.astype(np.float64), Mx).astype(x.dtype)
+
+
 def scale_grid(B, S, rate, center, dtype):
     rate = _c(rate, dtype).reshape(B)
     center = _c(center, dtype).reshape(B, 2)
@@ -248,10 +297,11 @@ class OraclePhysics:
 
 
 def proposed_loss(physics, model, y, draws, margin, cropped_div=True, averaged_cst=None,
-                  alpha=1.0, tau=1e-2, sure_sigma=5 / 255):
+                  alpha=1.0, tau=1e-2, sure_sigma=5 / 255, kind="padded", antialias=False):
     """ProposedLoss.forward for transforms="Scaling_Transforms", stop_gradient=True.
     draws = dict(b=..., u_rate=..., u_center=..., noise=...) in the reference's draw order
-    (SURVEY.md section 3.1).  Returns the loss and the intermediates the tests compare."""
+    (SURVEY.md section 3.1).  Returns the loss and the intermediates the tests compare.
+    kind="normal" (src/transforms.py:127-145): draws["u_rate"] is the single scalar draw, no centres."""
     # SureGaussianLoss gets sigma = noise_level/255 as a Python float (src/losses/__init__.py:104),
     # while the noise model holds it as a float32 Parameter (deepinv GaussianNoise)
     sigma2 = sure_sigma ** 2
@@ -262,8 +312,12 @@ def proposed_loss(physics, model, y, draws, margin, cropped_div=True, averaged_c
     y2 = physics.A(x_net2)
     margin_div = margin if cropped_div else 0
     l_sure, mse_v, div_v = sure_loss(y1, y2, y, b, margin, margin_div, tau, sigma2, averaged_cst)
-    rate, center = sample_params_from_uniforms(draws["u_rate"], draws["u_center"])
-    x2 = scale_transform(x_net, rate, center)
+    if kind == "normal":
+        rates = [0.75, 0.5]
+        x2 = resize_bicubic(x_net, rates[int(np.floor(len(rates) * float(draws["u_rate"])))], antialias)
+    else:
+        rate, center = sample_params_from_uniforms(draws["u_rate"], draws["u_center"])
+        x2 = scale_transform(x_net, rate, center)
     y_ei = add_noise(physics.A(x2), draws["noise"], physics.sigma)
     x3 = model(y_ei)
     l_ei = alpha * mse(x3, x2)

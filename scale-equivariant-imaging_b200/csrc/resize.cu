@@ -1,0 +1,113 @@
+// resize.cu -- bicubic resize by a fractional factor: the "normal" scale transform of the reference
+// (src/transforms.py:112-145 NormalDownsamplingTransform -> F.interpolate(x, scale_factor=rate, mode="bicubic",
+// antialias=...), rate in {0.75, 0.5}).  A non-default variant (demo/train.py defaults to kind="padded"), so one direct
+// kernel: a thread per output element, separable weights evaluated on the fly.
+//   antialias = 0: ATen upsample_bicubic2d -- source coordinate scale * (dst + 0.5) - 0.5 (no clamping), Keys cubic
+//                  A = -0.75 on the four neighbours, indices clamped to the image;
+//   antialias = 1: ATen _upsample_bicubic2d_aa -- window [center - support, center + support) with support = 2 * scale
+//                  for scale >= 1, cubic a = -0.5 stretched by 1 / scale, weights renormalised (sei::aa_axis_weights).
+// scale = 1 / scale_factor, as ATen computes it when a scale factor is given.
+#include "sei_common.cuh"
+#include <algorithm>
+
+namespace sei {
+
+struct ResizeParams {
+    const float* x;
+    float* y;
+    int H, W, Ho, Wo, aa;
+    float sh, sw;
+    long long total;
+};
+
+__device__ __forceinline__ void aa_axis_weights_f(int i, int in_size, float scale, float (&w)[kAaMaxTaps], int& xmin, int& xsize)
+{
+    const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * ((float)i + 0.5f);
+    int lo = (int)(center - support + 0.5f);
+    if (lo < 0) lo = 0;
+    int hi = (int)(center + support + 0.5f);
+    if (hi > in_size) hi = in_size;
+    xmin = lo;
+    xsize = min(hi - lo, kAaMaxTaps);
+    float total = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kAaMaxTaps; ++j) {
+        float wj = 0.0f;
+        if (j < xsize) wj = aa_cubic(((float)(j + lo) - center + 0.5f) * invscale);
+        w[j] = wj;
+        total += wj;
+    }
+    if (total != 0.0f) {
+#pragma unroll
+        for (int j = 0; j < kAaMaxTaps; ++j) w[j] = w[j] / total;
+    }
+}
+
+__global__ void __launch_bounds__(256) resize_bicubic_kernel(const __grid_constant__ ResizeParams p)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % p.Wo);
+        const long long t = idx / p.Wo;
+        const int i = (int)(t % p.Ho);
+        const float* xp = p.x + (t / p.Ho) * (long long)p.H * p.W;
+        float acc = 0.f;
+        if (!p.aa) {
+            const float ry = p.sh * ((float)i + 0.5f) - 0.5f, rx = p.sw * ((float)j + 0.5f) - 0.5f;
+            const float fy = floorf(ry), fx = floorf(rx);
+            float cy[4], cx[4];
+            keys_coeffs(ry - fy, cy);
+            keys_coeffs(rx - fx, cx);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int r = min(max((int)fy - 1 + a, 0), p.H - 1);
+                float row = 0.f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int c = min(max((int)fx - 1 + b, 0), p.W - 1);
+                    row = fmaf(__ldg(xp + (size_t)r * p.W + c), cx[b], row);
+                }
+                acc = fmaf(row, cy[a], acc);
+            }
+        } else {
+            float wy[kAaMaxTaps], wx[kAaMaxTaps];
+            int ymin, ysize, xmin, xsize;
+            aa_axis_weights_f(i, p.H, p.sh, wy, ymin, ysize);
+            aa_axis_weights_f(j, p.W, p.sw, wx, xmin, xsize);
+            for (int a = 0; a < ysize; ++a) {
+                const float* row = xp + (size_t)(ymin + a) * p.W + xmin;
+                float rv = 0.f;
+                for (int b = 0; b < xsize; ++b) rv = fmaf(__ldg(row + b), wx[b], rv);
+                acc = fmaf(rv, wy[a], acc);
+            }
+        }
+        p.y[idx] = acc;
+    }
+}
+
+}  // namespace sei
+
+using namespace sei;
+
+// y[planes, Ho, Wo] = bicubic resize of x[planes, H, W]; scale_h / scale_w = 1 / scale_factor per axis
+extern "C" int sei_resize_bicubic_f32(const float* x, float* y, long long planes, int H, int W, int Ho, int Wo,
+                                      float scale_h, float scale_w, int antialias, void* stream)
+{
+    SEI_REQUIRE(x && y, "null pointer argument");
+    SEI_REQUIRE(planes >= 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "bad shape planes=%lld %dx%d -> %dx%d", planes, H, W, Ho, Wo);
+    SEI_REQUIRE(scale_h > 0.f && scale_w > 0.f, "scales must be positive");
+    SEI_REQUIRE(!antialias || (4.0f * std::max(scale_h, scale_w) + 2.0f <= (float)kAaMaxTaps),
+                "antialiased resize supports scale factors down to 0.29 (%d taps per axis)", kAaMaxTaps);
+    if (planes == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    ResizeParams p;
+    p.x = x; p.y = y; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.aa = antialias ? 1 : 0; p.sh = scale_h; p.sw = scale_w;
+    p.total = planes * (long long)Ho * Wo;
+    const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
+    resize_bicubic_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return finish_launch("resize_bicubic_kernel");
+}

@@ -128,6 +128,22 @@ def up_bicubic(y, rate):
     return x
 
 
+def resize_bicubic(x, scale_factor, antialias):
+    """F.interpolate(x, scale_factor=scale_factor, mode='bicubic', antialias=antialias) (sei_resize_bicubic_f32);
+    no autograd: the reference only uses it under the EI loss's stop-gradient"""
+    import math
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    Ho, Wo = int(math.floor(H * float(scale_factor))), int(math.floor(W * float(scale_factor)))
+    if Ho < 1 or Wo < 1:
+        raise SeiError(f"resize_bicubic: scale factor {scale_factor} leaves no pixels of a {H}x{W} image")
+    y = torch.empty((B, Cc, Ho, Wo), dtype=x.dtype, device=x.device)
+    s = 1.0 / float(scale_factor)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_resize_bicubic_f32(_ptr(x), _ptr(y), B * Cc, H, W, Ho, Wo, s, s, int(bool(antialias)), _stream(x)))
+    return y
+
+
 def scale_params(u_rate, u_center, rates):
     u_rate, u_center = _t(u_rate, "u_rate"), _t(u_center, "u_center")
     B = u_rate.numel()

@@ -2,7 +2,7 @@
 
 Same public names and call signatures: sample_from, sample_downsampling_parameters,
 get_downsampling_grid, padded_downsampling_transform, PaddedDownsamplingTransform,
-ScalingTransform, CombinedTransform.  The sampling grid is never materialised on the hot path:
+normal_downsampling_transform, NormalDownsamplingTransform, ScalingTransform, CombinedTransform.  The sampling grid is never materialised on the hot path:
 the kernel recomputes its coordinates with the reference's fp32 rounding sequence."""
 import torch
 from torch.nn import Module
@@ -83,10 +83,27 @@ class PaddedDownsamplingTransform(Module):
         return ops.ei_remeasure(x_net, rate, center, args["kernel_host"], r, noise, sigma)
 
 
+def normal_downsampling_transform(x, downsampling_rate, mode, antialiased):
+    """Every image resized by the same factor (reference :112-124: a per-image F.interpolate loop); one kernel here."""
+    if mode != "bicubic":
+        raise NotImplementedError("only mode='bicubic' (the only one the reference passes, src/transforms.py:139) is built")
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("normal_downsampling_transform has no backward here: the reference uses it under the EI "
+                                  "loss's stop-gradient (ProposedLoss__stop_gradient=True, the default)")
+    return ops.resize_bicubic(x, float(downsampling_rate), antialiased)
+
+
 class NormalDownsamplingTransform(Module):
+    """reference :127-145: ONE rate for the whole batch, drawn with sample_from(shape=()) and read on the host"""
+
     def __init__(self, antialias, downsampling_rates):
         super().__init__()
-        raise NotImplementedError("ScalingTransform(kind='normal') is not built yet (SURVEY.md section 8f, N3)")
+        self.antialias = antialias
+        self.downsampling_rates = downsampling_rates
+
+    def forward(self, x):
+        rate = sample_from(self.downsampling_rates, shape=(), dtype=x.dtype, device=x.device).item()
+        return normal_downsampling_transform(x, downsampling_rate=rate, mode="bicubic", antialiased=self.antialias)
 
 
 class ScalingTransform(Module):
@@ -104,7 +121,8 @@ class ScalingTransform(Module):
         return self.transform(x)
 
     def fused_remeasure(self, x_net, physics, apply_noise=True):
-        out = self.transform.fused_remeasure(x_net, physics, apply_noise=apply_noise)
+        fused = getattr(self.transform, "fused_remeasure", None)          # only the padded transform has a fused kernel
+        out = fused(x_net, physics, apply_noise=apply_noise) if fused is not None else None
         if out is None:
             x2 = self.transform(x_net)
             return x2, (physics(x2) if apply_noise else physics.A(x2))

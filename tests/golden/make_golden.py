@@ -277,6 +277,8 @@ def gen_losses():
         ("deblur_gauss2_nostopgrad", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__stop_gradient=False), (2, 3, 32, 32)),
         ("deblur_gauss2_shifts", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Shifts"), (2, 3, 32, 32)),
         ("sr2_nostopgrad", dict(task="sr", kernel=None, sr_factor=2, method="proposed", ProposedLoss__stop_gradient=False), (2, 3, 16, 16)),
+        ("deblur_gauss2_normalT", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ScalingTransform__kind="normal"), (2, 3, 32, 32)),
+        ("deblur_gauss2_normalT_aa", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ScalingTransform__kind="normal", ScalingTransform__antialias=True), (2, 3, 32, 32)),
     ]
     only = os.environ.get("GOLDEN_ONLY", "")
     for name, kw, yshape in cases:
@@ -402,6 +404,22 @@ def gen_model():
     shapes = [list(big.state_dict()[n].shape) for n in names]
     save("model_default_layout", names=np.array(names), shapes=np.array([repr(s_) for s_ in shapes]),
          n_params=np.array(sum(p_.numel() for p_ in big.parameters())))
+
+
+def gen_normal_transform():
+    """normal_downsampling_transform (src/transforms.py:112-124) for both rates and both antialias settings, fp64 + fp32"""
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    shapes = [(2, 3, 32, 32), (1, 2, 48, 40), (1, 1, 21, 37)]
+    for i, shape in enumerate(shapes):
+        x = torch.rand(shape, generator=g, dtype=torch.float64)
+        out[f"x{i}"] = np_(x)
+        for rate in (0.75, 0.5):
+            for aa in (False, True):
+                tag = f"{i}_r{int(rate * 100)}_aa{int(aa)}"
+                out[f"y64_{tag}"] = np_(ref_transforms.normal_downsampling_transform(x, rate, "bicubic", aa))
+                out[f"y32_{tag}"] = np_(ref_transforms.normal_downsampling_transform(x.float(), rate, "bicubic", aa))
+    save("normal_transform", **out)
 
 
 def gen_resample():

@@ -388,7 +388,8 @@ def test_randomly_degrade(golden, dev):
 LOSS_CASES = ["deblur_gauss2_proposed", "deblur_box3_proposed", "deblur_gauss2_v1_proposed", "sr2_proposed",
               "sr4_proposed", "sr2_partial_proposed", "deblur_gauss2_sure", "deblur_gauss2_sure_avgcst",
               "deblur_gauss2_sure_nocrop", "deblur_gauss2_supervised", "sr2_css", "deblur_gauss2_proposed_alpha",
-              "cfg1_deblur_gauss2_proposed", "deblur_gauss2_r2r", "sr2_r2r", "deblur_gauss2_nostopgrad", "sr2_nostopgrad", "deblur_gauss2_shifts"]
+              "cfg1_deblur_gauss2_proposed", "deblur_gauss2_r2r", "sr2_r2r", "deblur_gauss2_nostopgrad", "sr2_nostopgrad", "deblur_gauss2_shifts",
+              "deblur_gauss2_normalT", "deblur_gauss2_normalT_aa"]
 LOSS_ARGS = {
     "deblur_gauss2_proposed": dict(), "deblur_box3_proposed": dict(kernel="Box_R3"),
     "deblur_gauss2_v1_proposed": dict(physics_v2=False),
@@ -404,6 +405,8 @@ LOSS_ARGS = {
     "deblur_gauss2_nostopgrad": dict(ProposedLoss__stop_gradient=False),
     "sr2_nostopgrad": dict(task="sr", kernel=None, sr_factor=2, ProposedLoss__stop_gradient=False),
     "deblur_gauss2_shifts": dict(ProposedLoss__transforms="Shifts"),
+    "deblur_gauss2_normalT": dict(ScalingTransform__kind="normal"),
+    "deblur_gauss2_normalT_aa": dict(ScalingTransform__kind="normal", ScalingTransform__antialias=True),
 }
 
 
@@ -510,3 +513,33 @@ def test_cuda_graph_capture(dev):
     ref = ops.ei_remeasure(x, rate, center, kern, 1, n, 0.02)
     assert torch.equal(x2, ref[0]) and torch.equal(y, ref[1])
     assert float(m) == float(ops.mse(ref[0], ref[1])) and float(m) != float(m_eager)
+
+
+@pytest.mark.parametrize("rate", [0.75, 0.5])
+@pytest.mark.parametrize("aa", [False, True])
+def test_normal_transform_vs_reference(golden, dev, rate, aa):
+    """ScalingTransform(kind="normal"): sei_resize_bicubic_f32 against fixtures produced by the reference's
+    normal_downsampling_transform and against the oracle, 1e-5 relative"""
+    import transforms
+    g = golden("normal_transform")
+    for i in range(3):
+        x = g[f"x{i}"].astype(np.float32)
+        got = transforms.normal_downsampling_transform(cu(x, dev), rate, "bicubic", aa).cpu().numpy()
+        ref = g[f"y32_{i}_r{int(rate * 100)}_aa{int(aa)}"]
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) < 1e-5, (i, rate, aa)
+        assert rel_err(got, orc.resize_bicubic(x, rate, aa)) < 1e-5
+
+
+def test_normal_scaling_transform_module(dev):
+    import transforms
+    from sei_b200 import draws, last_kernel
+    t = transforms.ScalingTransform(kind="normal", antialias=True)
+    x = torch.rand(2, 3, 64, 64, device=dev)
+    with draws.inject([np.array(0.7, dtype=np.float32)]):          # floor(2 * 0.7) = 1 -> rate 0.5
+        y = t(x)
+    assert y.shape == (2, 3, 32, 32) and last_kernel() == "resize_bicubic_kernel"
+    with draws.inject([np.array(0.2, dtype=np.float32)]):          # rate 0.75
+        assert t(x).shape == (2, 3, 48, 48)
+    with pytest.raises(NotImplementedError):
+        t(x.clone().requires_grad_(True))

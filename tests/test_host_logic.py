@@ -196,7 +196,10 @@ def test_draw_injection_is_strict():
 
 def test_unbuilt_variants_say_so():
     import transforms
+    t = transforms.ScalingTransform(kind="normal", antialias=False)          # built: resize kernel (GPU tests)
+    assert isinstance(t.transform, transforms.NormalDownsamplingTransform)
     with pytest.raises(NotImplementedError):
-        transforms.ScalingTransform(kind="normal", antialias=False)
+        transforms.padded_downsampling_transform(torch.zeros(1, 1, 8, 8), torch.ones(1), torch.zeros(1, 1, 1, 2),
+                                                 "bicubic", "reflection", True)
     with pytest.raises(ValueError):
         transforms.ScalingTransform(kind="other", antialias=False)

@@ -118,6 +118,8 @@ LOSS_CASES = [
     ("sr2_partial_proposed", "sr", None, 2, 2, {}),
     ("deblur_gauss2_proposed_alpha", "deblurring", "Gaussian_R2", 1, 6, {"alpha": 0.3}),
     ("cfg1_deblur_gauss2_proposed", "deblurring", "Gaussian_R2", 1, 6, {}),
+    ("deblur_gauss2_normalT", "deblurring", "Gaussian_R2", 1, 6, {"kind": "normal"}),
+    ("deblur_gauss2_normalT_aa", "deblurring", "Gaussian_R2", 1, 6, {"kind": "normal", "antialias": True}),
 ]
 
 
@@ -130,7 +132,10 @@ def test_proposed_loss(golden, case, tag):
     g = golden(f"loss_{name}_{tag}")
     kern = orc.named_kernel(kname) if kname else None
     phys = orc.OraclePhysics(task, kernel=kern, rate=rate, sigma=float(np.float32(5 / 255)))
-    draws = dict(b=None, u_rate=g["draw1_rand"], u_center=g["draw2_rand"], noise=g["draw3_randn_like"])
+    if kw.get("kind") == "normal":       # one scalar rate draw, then the noise
+        draws = dict(b=None, u_rate=g["draw1_rand"], u_center=None, noise=g["draw2_randn_like"])
+    else:
+        draws = dict(b=None, u_rate=g["draw1_rand"], u_center=g["draw2_rand"], noise=g["draw3_randn_like"])
     y = g["y"]
     b0 = g["draw0_randn"] if "draw0_randn" in g else g["draw0_randn_like"]
     b = np.zeros_like(y)
@@ -230,3 +235,16 @@ def test_scale_transform_vjp_through_no_stop_gradient_loss(golden, tag):
     tol = 1e-9 if tag == "f64" else 2e-5
     assert rel_err(g_xnet, g["model_out0_grad"]) < tol
     assert rel_err(g_x3, g["model_out2_grad"]) < tol
+
+
+def test_oracle_resize_bicubic_matches_reference(golden):
+    """normal_downsampling_transform (reference src/transforms.py:112-124), both rates, with and without antialiasing"""
+    g = golden("normal_transform")
+    for i in range(3):
+        x = g[f"x{i}"]
+        for rate in (0.75, 0.5):
+            for aa in (0, 1):
+                tag = f"{i}_r{int(rate * 100)}_aa{aa}"
+                assert rel_err(orc.resize_bicubic(x, rate, bool(aa)), g[f"y64_{tag}"]) < 1e-11, tag
+                # the reference's float32 run rounds its source coordinates / weights in fp32 (scale 4/3): 3e-6
+                assert rel_err(orc.resize_bicubic(x.astype(np.float32), rate, bool(aa)), g[f"y32_{tag}"]) < 5e-6, tag
