@@ -39,6 +39,26 @@ def main():
         shapes.append((f"s{s} ConvBlock {dim}->{4 * dim}", batch * hw, 4 * dim, dim))
         shapes.append((f"s{s} ConvBlock {4 * dim}->{dim}", batch * hw, dim, 4 * dim))
     shapes.append(("square 8192^3", 8192, 8192, 8192))
+    if only == "--wgrad":
+        # weight-gradient products D[Cout, Cin] += gy[pixels, Cout]^T x[pixels, Cin] (sei_gemm_bf16_atb_accumulate), in place
+        print(f"| layer | pixels | Cout | Cin | sei us | sei TFLOP/s | frac of {peak} | cuBLAS (gy.t() @ x) us | kernel |")
+        print("|---|---|---|---|---|---|---|---|---|")
+        from sei_b200 import last_kernel
+        for name, M, N, K in shapes[:-1]:
+            if M * K * 2 > 8e9 or M * N * 2 > 8e9:
+                M = M // 4
+                name += " (M/4)"
+            gy = torch.randn(M, N, device=dev).bfloat16()
+            x = torch.randn(M, K, device=dev).bfloat16()
+            out = torch.zeros(N, K, device=dev)
+            flops = 2.0 * M * N * K
+            ms = bench(lambda: ops.gemm_bf16_atb(gy, x, out=out))
+            kern = last_kernel()
+            ms_ref = bench(lambda: gy.t() @ x)
+            print(f"| {name} | {M} | {N} | {K} | {ms * 1e3:.1f} | {flops / ms / 1e9:.1f} | {flops / ms / 1e9 / peak:.3f} | "
+                  f"{ms_ref * 1e3:.1f} | {kern} |")
+            del gy, x, out
+        return
     print(f"| layer | M | N | K | sei us | sei TFLOP/s | frac of {peak} | cuBLAS us | cuBLAS TFLOP/s |")
     print("|---|---|---|---|---|---|---|---|---|")
     for name, M, N, K in shapes:

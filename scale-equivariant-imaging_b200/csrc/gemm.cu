@@ -760,6 +760,135 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
 }
 
+// CTA-pair kernel for the weight gradient: D[M, N] (fp32) (+)= A[K, M]^T B[K, N], both operands MN-major (read in place),
+// M = 256 per cluster (128 rows of D per CTA), N = 256 (each CTA stages 128 of the 256 columns of B), split-K across
+// clusters with vector-atomic accumulation.  Same barrier protocol as gemm_bf16_tn_2cta_kernel; the operand tiles are
+// the MN-major boxes of the single-CTA kernel (64 MN-elements x BK k-rows, 8 KB each): two per operand and CTA.
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_atb_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ GemmParams p)
+{
+    constexpr int BM = kGemmBM, BK = kGemmBK, BN = 256, BNH = 128;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t BOX_BYTES = BK * 128;             // one 64-element MN block
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;
+    const int nk_total = (p.K + BK - 1) / BK;
+    const long long tiles_mn = (long long)tiles_m * tiles_n;
+    const long long total = tiles_mn * p.splits;
+    const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 256);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long w = cluster_id; w < total; w += n_clusters) {
+                const int split = (int)(w / tiles_mn);
+                const long long rem = w - split * tiles_mn;
+                const int m0 = (int)(rem % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(rem / tiles_m) * BN + (int)rank * BNH;
+                const int kb0 = split * p.kb_per_split;
+                const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
+                    const int k0 = (kb0 + kb) * BK;
+#pragma unroll
+                    for (int mb = 0; mb < BM / 64; ++mb) tma_load_2d_2sm(a_dst + mb * BOX_BYTES, &map_a, m0 + 64 * mb, k0, &full_bar[s]);
+#pragma unroll
+                    for (int nb = 0; nb < BNH / 64; ++nb)
+                        tma_load_2d_2sm(a_dst + A_BYTES + nb * BOX_BYTES, &map_b, n0 + 64 * nb, k0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, true);
+            uint32_t it = 0, tcount = 0;
+            for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
+                const int split = (int)(w / tiles_mn);
+                const int kb0 = split * p.kb_per_split;
+                const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
+                const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+                if (tcount >= 2) mbar_wait(&tmem_empty_bar[acc], (acc_use - 1) & 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const uint32_t s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc_mn_sw128(a_addr, BOX_BYTES), db = umma_smem_desc_mn_sw128(a_addr + A_BYTES, BOX_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2sm(tmem_d, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        uint32_t tcount = 0;
+        for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
+            const int split = (int)(w / tiles_mn);
+            const long long rem = w - split * tiles_mn;
+            const int m0 = (int)(rem % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(rem / tiles_m) * BN;
+            const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            mbar_wait(&tmem_full_bar[acc], acc_use & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r);
+                tmem_ld_wait();
+                gemm_store_chunk<true>(p, r, row, n0 + c, false);
+            }
+            tc_fence_before();
+            mbar_arrive_leader(&tmem_empty_bar[acc]);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- batched operator product on tcgen05
 // D_b[M, N] = A[M, K] * X_b[K, N]  (csrc/bgemm.cu; the CNN's ideal resamplers).  The operator A (M <= 256 rows per
 // CTA, M * K <= 64 K elements) is loaded ONCE per persistent CTA into shared memory as K-major SWIZZLE_128B tiles and
@@ -1155,6 +1284,27 @@ int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int
 
 using namespace sei;
 
+// Split-K factor for `tiles` output tiles walked by `units` persistent CTAs (or CTA pairs) with a static stride: the
+// launch takes waves x (k-blocks per item + pipeline fill/drain), waves = ceil(items / units).  Picks the factor that
+// minimises it (smallest on ties: fewer atomic passes over D), e.g. 16 tiles on 74 pairs -> 9 slices (144 items, two
+// full waves) rather than 10 (160 items, a third wave at 16 % occupancy).
+static void choose_splits(long long tiles, int units, int nk, int* splits, int* kb_per_split)
+{
+    long long best_cost = -1;
+    const int smax = std::max(1, std::min(512, nk / 4));
+    for (int sp = 1; sp <= smax; ++sp) {
+        const int kbps = (nk + sp - 1) / sp;
+        const int real = (nk + kbps - 1) / kbps;
+        const long long waves = (tiles * real + units - 1) / units;
+        const long long cost = waves * (kbps + 4);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            *splits = real;
+            *kb_per_split = kbps;
+        }
+    }
+}
+
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                             long long lda, long long ldb, long long ldd, int out_f32, int tile_n,
                             const void* gelu_h, long long ld_h, void* stream);
@@ -1216,10 +1366,7 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     p.splits = 1;
     p.kb_per_split = nk;
     if (out_f32 && tiles < dp.sm_count && nk >= 8 && ldd == N) {
-        int want = (int)std::min<long long>((2ll * dp.sm_count + tiles - 1) / tiles, nk / 4);
-        want = std::max(1, std::min(want, 512));
-        p.kb_per_split = (nk + want - 1) / want;
-        p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
+        choose_splits(tiles, dp.sm_count, nk, &p.splits, &p.kb_per_split);
         if (p.splits > 1) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
     }
     // CTA-pair kernel for the large bf16-output TN products (forward / input gradient of the deep layers)
@@ -1288,13 +1435,26 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
+    // CTA-pair kernel for the wide weight matrices (256 x 256 tiles per cluster)
+    const char* no2 = getenv("SEI_GEMM_NO_2CTA_MN");
+    if (bn == 256 && M >= 256 && dp.sm_count >= 2 && !(no2 && *no2 == '1')) {
+        constexpr int ST2 = 6;
+        const long long ctiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
+        const int clusters = dp.sm_count / 2;
+        p.splits = 1;
+        p.kb_per_split = nk;
+        if (nk >= 8) choose_splits(ctiles, clusters, nk, &p.splits, &p.kb_per_split);
+        if (p.splits > 1 && !accumulate) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
+        constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024;
+        const unsigned grid = 2u * (unsigned)std::min<long long>(ctiles * p.splits, clusters);
+        SEI_CUDA(allow_smem(gemm_bf16_atb_2cta_kernel<ST2>, smem2));
+        gemm_bf16_atb_2cta_kernel<ST2><<<grid, kGemmThreads, smem2, st>>>(ma, mb, p);
+        return finish_launch("gemm_bf16_mn_2cta_kernel");
+    }
     p.splits = 1;
     p.kb_per_split = nk;
-    if (tiles < dp.sm_count && nk >= 8) {
-        int want = (int)std::min<long long>((2ll * dp.sm_count + tiles - 1) / tiles, nk / 4);
-        want = std::max(1, std::min(want, 512));
-        p.kb_per_split = (nk + want - 1) / want;
-        p.splits = (nk + p.kb_per_split - 1) / p.kb_per_split;
+    if (nk >= 8) {
+        choose_splits(tiles, dp.sm_count, nk, &p.splits, &p.kb_per_split);
         if (p.splits > 1 && !accumulate) SEI_CUDA(cudaMemsetAsync(D, 0, (size_t)M * N * sizeof(float), st));
     }
     switch (bn) {

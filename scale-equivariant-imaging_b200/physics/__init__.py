@@ -6,6 +6,7 @@ from os.path import exists
 import torch
 
 from rng import fork_rng
+from sei_b200 import draws, ops
 from sei_b200.linear_physics import GaussianNoise
 from .blur import Blur, BlurV2
 from .downsampling import Downsampling
@@ -55,6 +56,29 @@ class PhysicsManager:
             if seed is not None:
                 torch.manual_seed(seed)
             return self.physics.noise_model(self.physics.A(x))
+
+    def randomly_degrade_batch(self, x, seeds):
+        """The measurements the reference's datasets produce one image at a time (SyntheticDataset.__getitem__,
+        src/datasets/synthetic_dataset.py:26-40: x.unsqueeze(0) -> randomly_degrade(x, seed)), for a whole batch of
+        equally sized images with ONE operator launch: image i gets the standard-normal draw of
+        `torch.manual_seed(seeds[i]); randn((1, C, h, w))` (or the next draw of the global stream where seeds[i] is
+        None / seeds is None, like the CSS re-degradation, src/datasets/__init__.py:70-75), and the noise add is the
+        operator's epilogue."""
+        B = x.shape[0]
+        seeds = [None] * B if seeds is None else list(seeds)
+        if len(seeds) != B:
+            raise ValueError(f"{B} images but {len(seeds)} seeds")
+        y_shape = tuple(x.shape)
+        if self.task == "sr":
+            r = self.physics.rate
+            y_shape = y_shape[:2] + (ops.down_out_size(x.shape[2], r), ops.down_out_size(x.shape[3], r))
+        noise = torch.empty(y_shape, device=x.device, dtype=x.dtype)
+        for i, seed in enumerate(seeds):
+            with fork_rng(enabled=seed is not None):
+                if seed is not None:
+                    torch.manual_seed(seed)
+                noise[i:i + 1] = draws.randn((1,) + tuple(y_shape[1:]), x.device, x.dtype)
+        return self.physics.measure_with_noise(x, noise)
 
 
 def get_physics(args, device):

@@ -86,7 +86,8 @@ def test_gemm_split_k_weight_gradient_shapes(dev):
 
 
 @pytest.mark.parametrize("K,M,N", [(4096, 128, 64), (65536, 128, 32), (10000, 512, 128), (2048, 2048, 512), (777, 136, 72),
-                                   (8192, 256, 1024)])
+                                   (8192, 256, 1024), (5000, 384, 264), (64, 256, 256), (100000, 1024, 256), (8192, 8192, 2048),
+                                   (3000, 136, 512)])
 def test_gemm_atb_mn_major(dev, K, M, N):
     """D = A^T B with both operands read in place (MN-major UMMA descriptors): the weight-gradient shape"""
     from sei_b200 import ops, last_kernel
@@ -95,8 +96,14 @@ def test_gemm_atb_mn_major(dev, K, M, N):
     b = torch.randn(K, N, device=dev).bfloat16()
     ref = a.float().t() @ b.float()
     d = ops.gemm_bf16_atb(a, b)
-    assert last_kernel() == "gemm_bf16_mn_kernel"
+    # wide weight matrices take the CTA-pair kernel (cta_group::2, 256 x 256 tiles per cluster)
+    assert last_kernel() == ("gemm_bf16_mn_2cta_kernel" if M >= 256 and N >= 256 else "gemm_bf16_mn_kernel")
     assert float((d - ref).abs().max() / ref.abs().max()) < 5e-5, float((d - ref).abs().max() / ref.abs().max())
+    d0 = torch.randn(M, N, device=dev)
+    acc = ops.gemm_bf16_atb(a, b, out=d0.clone())                     # in-place accumulation (weight gradients)
+    assert float((acc - d0 - ref).abs().max() / ref.abs().max()) < 5e-5
+    d2 = ops.gemm_bf16_atb(a, b)                                      # barriers / TMEM reused correctly by a second launch
+    assert float((d2 - ref).abs().max() / ref.abs().max()) < 5e-5
 
 
 def test_gemm_throughput_smoke(dev):

@@ -384,6 +384,34 @@ def test_randomly_degrade(golden, dev):
         assert abs(resid.std() - 5 / 255) < 0.1 * 5 / 255 and abs(resid.mean()) < 1e-3
 
 
+def test_randomly_degrade_batch_equals_per_image_calls(dev):
+    """N2: one operator launch for a batch of dataset items = the reference's per-item calls (same seeds, same draws)"""
+    import physics
+    for kw in [dict(), dict(physics_v2=False), dict(task="sr", kernel=None, sr_factor=2)]:
+        phys = physics.get_physics(base_args(**kw), device=dev)
+        mgr = getattr(phys, "__manager")
+        torch.manual_seed(5)
+        x = torch.rand(6, 3, 64, 64, device=dev)
+        seeds = [11, 12, 0, 0, 99, 7]
+        torch.manual_seed(77)
+        state = torch.cuda.get_rng_state(dev).clone()
+        yb = mgr.randomly_degrade_batch(x, seeds)
+        assert torch.equal(state, torch.cuda.get_rng_state(dev))          # seeded items leave the global stream alone
+        ys = torch.cat([mgr.randomly_degrade(x[i:i + 1], seed=s) for i, s in enumerate(seeds)])
+        # same draws; the fused epilogue rounds sigma * n + y once (fma), the two-kernel composition twice
+        assert yb.shape == ys.shape and float((yb - ys).abs().max()) < 5e-7
+        n2, n3 = yb[2] - phys.A(x[2:3])[0], yb[3] - phys.A(x[3:4])[0]                # same seed, same noise
+        assert float((n2 - n3).abs().max()) < 5e-7 and abs(float(n2.std()) - 5 / 255) < 0.1 * 5 / 255
+        # unseeded items (CSS re-degradation) consume the global stream in item order
+        torch.manual_seed(3)
+        yb = mgr.randomly_degrade_batch(x, None)
+        torch.manual_seed(3)
+        ys = torch.cat([mgr.randomly_degrade(x[i:i + 1], seed=None) for i in range(6)])
+        assert float((yb - ys).abs().max()) < 5e-7
+        with pytest.raises(ValueError):
+            mgr.randomly_degrade_batch(x, [1, 2])
+
+
 # ------------------------------------------------------------------------------------ full loss assembly vs the reference
 LOSS_CASES = ["deblur_gauss2_proposed", "deblur_box3_proposed", "deblur_gauss2_v1_proposed", "sr2_proposed",
               "sr4_proposed", "sr2_partial_proposed", "deblur_gauss2_sure", "deblur_gauss2_sure_avgcst",
