@@ -93,6 +93,12 @@ int sei_up_bicubic_f32(const float* y, float* x, long long planes, int h, int w,
  * (they are drawn on the device; no host sync). */
 int sei_scale_transform_f32(const float* x, float* out, int B, int C, int S,
                             const float* rate, const float* center, int path, void* stream);
+/* The grid_sample step of the same transform behind its anti-aliasing pre-filter
+ * (src/transforms.py:63-67,76-82, antialiased=True): x is the pre-filtered image,
+ * B x C x Ssrc x Ssrc (alias_free_interpolate :44-57 = sei_resize_bicubic_f32 with
+ * antialias), out is B x C x S x S, the grid is the one of an S x S image. */
+int sei_scale_transform_src_f32(const float* x, float* out, int B, int C, int Ssrc, int S,
+                                const float* rate, const float* center, void* stream);
 /* transpose of the above w.r.t. x (autograd through grid_sample; only reached with
  * --no-ProposedLoss__stop_gradient).  gx is overwritten. */
 int sei_scale_transform_backward_f32(const float* gout, float* gx, int B, int C, int S,

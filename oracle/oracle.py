@@ -224,6 +224,25 @@ def scale_transform(x, rate, center):
     return out
 
 
+def scale_transform_antialiased(x, rate, center):
+    """padded_downsampling_transform(..., antialiased=True) (src/transforms.py:60-83): alias_free_interpolate (:44-57,
+    F.interpolate(scale_factor=rate_i, antialias=True) per image + torch.stack, which needs equal rates) and then
+    grid_sample of the smaller image with the grid of the original shape"""
+    x = _c(x)
+    sfx, _ = _sfx(x)
+    B, Cc, S, S2 = x.shape
+    if S != S2:
+        raise ValueError("the scale transform is defined for square images only")
+    rate = _c(rate, x.dtype).reshape(B)
+    center = _c(center, x.dtype).reshape(B, 2)
+    if len(set(float(r) for r in rate)) != 1:
+        raise RuntimeError("stack expects each tensor to be equal size")
+    small = _c(resize_bicubic(x, float(rate[0]), True))
+    out = np.empty_like(x)
+    getattr(lib(), f"orc_scale_transform_src_{sfx}")(_p(small), _p(out), B, Cc, small.shape[-1], S, _p(rate), _p(center))
+    return out
+
+
 def scale_transform_vjp(gout, rate, center):
     """transpose of scale_transform w.r.t. its image argument (autograd through grid_sample)"""
     gout = _c(gout)

@@ -376,32 +376,34 @@ static int FN(orc_reflect_clip)(int idx, int S)
     return v < 0 ? 0 : (v > S - 1 ? S - 1 : v);
 }
 
-void FN(orc_scale_transform)(const REAL* x, REAL* out, int B, int C, int S,
-                             const REAL* rate, const REAL* center)
+/* x: B x C x Ss x Ss (Ss == S, or the pre-filtered smaller image of the antialiased variant, src/transforms.py:63-67:
+ * the grid keeps the ORIGINAL shape S and grid_sample un-normalises against the source size), out: B x C x S x S */
+void FN(orc_scale_transform_src)(const REAL* x, REAL* out, int B, int C, int Ss, int S,
+                                 const REAL* rate, const REAL* center)
 {
 #pragma omp parallel for schedule(static) collapse(2)
     for (int b = 0; b < B; ++b)
         for (int c = 0; c < C; ++c) {
             const REAL inv_rate = (REAL)1.0 / rate[b];
-            const REAL* xp = x + ((long)b * C + c) * S * S;
+            const REAL* xp = x + ((long)b * C + c) * Ss * Ss;
             REAL* op = out + ((long)b * C + c) * S * S;
             for (int i = 0; i < S; ++i) {
                 const REAL gy = FN(orc_grid_coord)(i, S, inv_rate, center[2 * b + 1]);
-                const REAL py = ((gy + 1) / 2) * (REAL)(S - 1);
+                const REAL py = ((gy + 1) / 2) * (REAL)(Ss - 1);
                 const REAL fy = (REAL)floor((double)py);
                 REAL cy[4]; FN(orc_cubic_coeffs)(py - fy, cy);
                 int ry[4];
-                for (int a = 0; a < 4; ++a) ry[a] = FN(orc_reflect_clip)((int)fy - 1 + a, S);
+                for (int a = 0; a < 4; ++a) ry[a] = FN(orc_reflect_clip)((int)fy - 1 + a, Ss);
                 for (int j = 0; j < S; ++j) {
                     const REAL gx = FN(orc_grid_coord)(j, S, inv_rate, center[2 * b + 0]);
-                    const REAL px = ((gx + 1) / 2) * (REAL)(S - 1);
+                    const REAL px = ((gx + 1) / 2) * (REAL)(Ss - 1);
                     const REAL fx = (REAL)floor((double)px);
                     REAL cx[4]; FN(orc_cubic_coeffs)(px - fx, cx);
                     int rx[4];
-                    for (int t = 0; t < 4; ++t) rx[t] = FN(orc_reflect_clip)((int)fx - 1 + t, S);
+                    for (int t = 0; t < 4; ++t) rx[t] = FN(orc_reflect_clip)((int)fx - 1 + t, Ss);
                     REAL acc = 0;
                     for (int a = 0; a < 4; ++a) {
-                        const REAL* row = xp + (long)ry[a] * S;
+                        const REAL* row = xp + (long)ry[a] * Ss;
                         const REAL interp = row[rx[0]] * cx[0] + row[rx[1]] * cx[1]
                                           + row[rx[2]] * cx[2] + row[rx[3]] * cx[3];
                         acc += interp * cy[a];
@@ -410,6 +412,12 @@ void FN(orc_scale_transform)(const REAL* x, REAL* out, int B, int C, int S,
                 }
             }
         }
+}
+
+void FN(orc_scale_transform)(const REAL* x, REAL* out, int B, int C, int S,
+                             const REAL* rate, const REAL* center)
+{
+    FN(orc_scale_transform_src)(x, out, B, C, S, S, rate, center);
 }
 
 /* transpose of orc_scale_transform w.r.t. x: what autograd computes through grid_sample when

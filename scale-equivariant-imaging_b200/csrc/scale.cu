@@ -195,13 +195,14 @@ struct ScaleDirectParams {
     const float* rate;
     const float* center;
     int C, S;
+    int Ssrc;            // source size (== S except behind the anti-aliasing pre-filter, which shrinks the source)
     float two_over_S;
     long long total;
 };
 
 __global__ void __launch_bounds__(256) scale_direct_kernel(const __grid_constant__ ScaleDirectParams p)
 {
-    const int S = p.S;
+    const int S = p.S, Ss = p.Ssrc;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % S);
@@ -211,13 +212,13 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const __grid_constant
         const int b = (int)(plane / p.C);
         const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
         AxisTap ty, tx;
-        scale_axis_tap(i, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b + 1), ty);
-        scale_axis_tap(j, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b), tx);
-        const float* xp = p.x + plane * (long long)S * S;
+        scale_axis_tap(i, Ss, p.two_over_S, inv_rate, __ldg(p.center + 2 * b + 1), ty);
+        scale_axis_tap(j, Ss, p.two_over_S, inv_rate, __ldg(p.center + 2 * b), tx);
+        const float* xp = p.x + plane * (long long)Ss * Ss;
         float acc = 0.f;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const float* row = xp + (size_t)ty.idx[a] * S;
+            const float* row = xp + (size_t)ty.idx[a] * Ss;
             float h = __ldg(row + tx.idx[0]) * tx.w[0];
             h = fmaf(__ldg(row + tx.idx[1]), tx.w[1], h);
             h = fmaf(__ldg(row + tx.idx[2]), tx.w[2], h);
@@ -345,11 +346,32 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
         return finish_launch("scale_band_kernel");
     }
     ScaleDirectParams d;
-    d.x = x; d.out = out; d.rate = rate; d.center = center; d.C = C; d.S = S;
+    d.x = x; d.out = out; d.rate = rate; d.center = center; d.C = C; d.S = S; d.Ssrc = S;
     d.two_over_S = two_over_S;
     d.total = planes * (long long)S * S;
     const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
     scale_direct_kernel<<<grid, 256, 0, st>>>(d);
+    return finish_launch("scale_direct_kernel");
+}
+
+// The same resampling from a source of another size: x is [B, C, Ssrc, Ssrc], out [B, C, S, S]; the grid is that of an
+// S x S image (reference src/transforms.py:63-83 with antialiased=True: the grid is built for the ORIGINAL shape and
+// grid_sample reads the pre-filtered, smaller image through normalised coordinates).
+extern "C" int sei_scale_transform_src_f32(const float* x, float* out, int B, int C, int Ssrc, int S,
+                                           const float* rate, const float* center, void* stream)
+{
+    SEI_REQUIRE(x && out && rate && center, "null pointer argument");
+    SEI_REQUIRE(B >= 0 && C > 0 && S > 0 && Ssrc > 0, "bad shape B=%d C=%d Ssrc=%d S=%d", B, C, Ssrc, S);
+    if (B == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    ScaleDirectParams d;
+    d.x = x; d.out = out; d.rate = rate; d.center = center; d.C = C; d.S = S; d.Ssrc = Ssrc;
+    d.two_over_S = (float)(2.0 / (double)S);
+    d.total = (long long)B * C * S * S;
+    const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
+    scale_direct_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d);
     return finish_launch("scale_direct_kernel");
 }
 
@@ -364,7 +386,7 @@ extern "C" int sei_scale_transform_backward_f32(const float* gout, float* gx, in
     int rc = get_device_props(&dp);
     if (rc) return rc;
     ScaleDirectParams d;
-    d.x = gout; d.out = gx; d.rate = rate; d.center = center; d.C = C; d.S = S;
+    d.x = gout; d.out = gx; d.rate = rate; d.center = center; d.C = C; d.S = S; d.Ssrc = S;
     d.two_over_S = (float)(2.0 / (double)S);
     d.total = (long long)B * C * S * S;
     SEI_CUDA(cudaMemsetAsync(gx, 0, (size_t)d.total * sizeof(float), st));

@@ -311,6 +311,7 @@ struct AxisTap {
     int idx[4];
 };
 
+// S: size of the SOURCE axis (the output axis enters through two_over_S only)
 __device__ __forceinline__ void scale_axis_tap(int i, int S, float two_over_S, float inv_rate, float c, AxisTap& t)
 {
     const float pix = scale_src_coord(i, two_over_S, inv_rate, c, (float)(S - 1));

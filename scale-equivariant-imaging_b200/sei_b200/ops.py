@@ -172,6 +172,24 @@ def scale_transform(x, rate, center, path=PATH_AUTO):
     return out
 
 
+def scale_transform_from(x_src, out_size, rate, center):
+    """grid_sample step of the scale transform reading a source of another (square) size: x_src [B, C, Ssrc, Ssrc]
+    -> [B, C, out_size, out_size] (sei_scale_transform_src_f32; the anti-aliased variant, no autograd)"""
+    x_src = _t(x_src, "x")
+    B, Cc, H, W = x_src.shape
+    if H != W:
+        raise SeiError("the scale transform is defined for square images only (like the reference's grid)")
+    rate = _t(rate, "downsampling_rate").reshape(-1)
+    center = _t(center, "center").reshape(-1)
+    if rate.numel() != B or center.numel() != 2 * B:
+        raise SeiError("downsampling_rate must have B entries and center B x 2")
+    out = torch.empty((B, Cc, out_size, out_size), dtype=x_src.dtype, device=x_src.device)
+    with torch.cuda.device(x_src.device):
+        check(_lib.load().sei_scale_transform_src_f32(_ptr(x_src), _ptr(out), B, Cc, H, out_size, _ptr(rate), _ptr(center),
+                                                      _stream(x_src)))
+    return out
+
+
 _ei_workspaces = {}
 
 

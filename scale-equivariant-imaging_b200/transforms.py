@@ -48,9 +48,24 @@ def padded_downsampling_transform(x, downsampling_rate, center, mode, padding_mo
         raise NotImplementedError("only mode='bicubic', padding_mode='reflection' (the only combination the "
                                   "reference ever passes, src/transforms.py:105-106) is built")
     if antialiased:
-        raise NotImplementedError("ScalingTransform(antialias=True) (per-image pre-filter) is not built yet; "
-                                  "the reference default is antialias=False (demo/train.py:49-51)")
+        return _antialiased_padded_transform(x, downsampling_rate, center)
     return ops._ScaleTransform.apply(x, downsampling_rate, center, ops.PATH_AUTO)
+
+
+def _antialiased_padded_transform(x, downsampling_rate, center):
+    """alias_free_interpolate (reference :44-57: per-image F.interpolate(scale_factor=rate_i.item(), antialias=True), then
+    torch.stack) followed by grid_sample of the SMALLER image with the grid of the original shape (:63-82).  Like the
+    reference it reads the rates on the host, and like the reference it only works when every image of the batch drew
+    the same rate: torch.stack of differently sized images raises a RuntimeError there, and so does this."""
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("the anti-aliased scale transform has no backward here: the reference uses it under "
+                                  "the EI loss's stop-gradient (ProposedLoss__stop_gradient=True, the default)")
+    rates = [float(r) for r in downsampling_rate.reshape(-1).tolist()]
+    if len(set(rates)) > 1:
+        raise RuntimeError("stack expects each tensor to be equal size: the anti-aliasing pre-filter resizes every image by "
+                           f"its own rate {sorted(set(rates))} (reference src/transforms.py:44-57 fails the same way)")
+    small = ops.resize_bicubic(x, rates[0], True)
+    return ops.scale_transform_from(small, x.shape[-1], downsampling_rate, center)
 
 
 class PaddedDownsamplingTransform(Module):

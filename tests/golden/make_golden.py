@@ -422,6 +422,33 @@ def gen_normal_transform():
     save("normal_transform", **out)
 
 
+def gen_transform_aa():
+    """padded_downsampling_transform(..., antialiased=True) (src/transforms.py:44-83): equal rates per batch (the only case
+    the reference's torch.stack accepts), fp64 + fp32; and the error it raises for mixed rates"""
+    g = torch.Generator().manual_seed(9090)
+    out = {}
+    for ci, (B, C, S, rate) in enumerate([(3, 3, 32, 0.75), (2, 1, 48, 0.5), (1, 3, 33, 0.75), (4, 2, 24, 0.5)]):
+        x64 = torch.rand((B, C, S, S), dtype=torch.float64, generator=g)
+        rate64 = torch.full((B,), rate, dtype=torch.float64)
+        center64 = 2 * torch.rand((B, 1, 1, 2), dtype=torch.float64, generator=g) - 1
+        out[f"c{ci}_x"], out[f"c{ci}_rate"], out[f"c{ci}_center"] = np_(x64), np_(rate64), np_(center64)
+        for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            y = ref_transforms.padded_downsampling_transform(
+                x64.to(dt), downsampling_rate=rate64.to(dt), center=center64.to(dt),
+                mode="bicubic", padding_mode="reflection", antialiased=True)
+            assert y.shape == x64.shape
+            out[f"c{ci}_T_{tag}"] = np_(y)
+    try:
+        ref_transforms.padded_downsampling_transform(
+            torch.rand(2, 1, 16, 16), downsampling_rate=torch.tensor([0.75, 0.5]), center=torch.zeros(2, 1, 1, 2),
+            mode="bicubic", padding_mode="reflection", antialiased=True)
+        msg = "no error"
+    except RuntimeError as e:
+        msg = str(e).splitlines()[0]
+    out["mixed_rates_error"] = np.array(msg)
+    save("transform_aa", **out)
+
+
 def gen_resample():
     """IdealUpsample / IdealDownsample of the reference's CNN (src/models/convolutional.py:48-133), float64, with the
     vector-Jacobian product autograd gives for a random output gradient (pins the transposed operators)."""

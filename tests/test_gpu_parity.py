@@ -559,6 +559,42 @@ def test_normal_transform_vs_reference(golden, dev, rate, aa):
         assert rel_err(got, orc.resize_bicubic(x, rate, aa)) < 1e-5
 
 
+def test_antialiased_padded_transform_vs_reference(golden, dev):
+    """ScalingTransform(kind="padded", antialias=True): sei_resize_bicubic_f32 (pre-filter) + sei_scale_transform_src_f32
+    against fixtures produced by the reference and against the oracle"""
+    import transforms
+    from sei_b200 import last_kernel
+    g = golden("transform_aa")
+    for ci in range(4):
+        x, rate, center = (g[f"c{ci}_{k}"].astype(np.float32) for k in ("x", "rate", "center"))
+        got = transforms.padded_downsampling_transform(cu(x, dev), cu(rate, dev), cu(center, dev), "bicubic", "reflection",
+                                                       True).cpu().numpy()
+        assert last_kernel() == "scale_direct_kernel"
+        assert got.shape == x.shape
+        assert rel_err(got, g[f"c{ci}_T_f32"]) < 1e-5, ci
+        assert rel_err(got, orc.scale_transform_antialiased(x, rate, center)) < 1e-5, ci
+    x = torch.rand(2, 3, 32, 32, device=dev)
+    with pytest.raises(RuntimeError, match="equal size"):          # the reference fails the same way (torch.stack)
+        transforms.padded_downsampling_transform(x, torch.tensor([0.75, 0.5], device=dev), torch.zeros(2, 1, 1, 2, device=dev),
+                                                 "bicubic", "reflection", True)
+    with pytest.raises(NotImplementedError):
+        transforms.padded_downsampling_transform(x.clone().requires_grad_(True), torch.full((2,), 0.5, device=dev),
+                                                 torch.zeros(2, 1, 1, 2, device=dev), "bicubic", "reflection", True)
+    # module form: EI re-measurement goes through the unfused composition
+    import physics
+    phys = physics.get_physics(base_args(), device=dev)
+    t = transforms.ScalingTransform(kind="padded", antialias=True)
+    with draws_inject_equal_rates(dev):
+        x2, y2 = t.fused_remeasure(x[:1], phys, apply_noise=False)
+    assert x2.shape == (1, 3, 32, 32) and y2.shape == (1, 3, 32, 32)
+    assert rel_err(npy(y2), npy(phys.A(x2))) < 1e-6
+
+
+def draws_inject_equal_rates(dev):
+    from sei_b200 import draws
+    return draws.inject([np.array([0.7], dtype=np.float32), np.array([[0.25, 0.5]], dtype=np.float32)])
+
+
 def test_normal_scaling_transform_module(dev):
     import transforms
     from sei_b200 import draws, last_kernel

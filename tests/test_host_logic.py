@@ -198,8 +198,12 @@ def test_unbuilt_variants_say_so():
     import transforms
     t = transforms.ScalingTransform(kind="normal", antialias=False)          # built: resize kernel (GPU tests)
     assert isinstance(t.transform, transforms.NormalDownsamplingTransform)
+    # antialias=True is built too; mixed rates fail like the reference's torch.stack does (src/transforms.py:44-57)
+    with pytest.raises(RuntimeError, match="equal size"):
+        transforms.padded_downsampling_transform(torch.zeros(2, 1, 8, 8), torch.tensor([0.75, 0.5]), torch.zeros(2, 1, 1, 2),
+                                                 "bicubic", "reflection", True)
     with pytest.raises(NotImplementedError):
         transforms.padded_downsampling_transform(torch.zeros(1, 1, 8, 8), torch.ones(1), torch.zeros(1, 1, 1, 2),
-                                                 "bicubic", "reflection", True)
+                                                 "nearest", "reflection", False)
     with pytest.raises(ValueError):
         transforms.ScalingTransform(kind="other", antialias=False)

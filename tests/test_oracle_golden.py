@@ -237,6 +237,20 @@ def test_scale_transform_vjp_through_no_stop_gradient_loss(golden, tag):
     assert rel_err(g_x3, g["model_out2_grad"]) < tol
 
 
+def test_oracle_antialiased_scale_transform_matches_reference(golden):
+    """padded_downsampling_transform(antialiased=True) (reference src/transforms.py:44-83): pre-filter + grid_sample of the
+    smaller image; equal rates only -- the reference's torch.stack raises for mixed rates, and so does the oracle"""
+    g = golden("transform_aa")
+    assert "stack expects each tensor to be equal size" in str(g["mixed_rates_error"])
+    for ci in range(4):
+        x, rate, center = g[f"c{ci}_x"], g[f"c{ci}_rate"], g[f"c{ci}_center"]
+        assert rel_err(orc.scale_transform_antialiased(x, rate, center), g[f"c{ci}_T_f64"]) < 1e-11
+        f = np.float32
+        assert rel_err(orc.scale_transform_antialiased(x.astype(f), rate.astype(f), center.astype(f)), g[f"c{ci}_T_f32"]) < 5e-6
+    with pytest.raises(RuntimeError, match="equal size"):
+        orc.scale_transform_antialiased(np.zeros((2, 1, 16, 16)), np.array([0.75, 0.5]), np.zeros((2, 2)))
+
+
 def test_oracle_resize_bicubic_matches_reference(golden):
     """normal_downsampling_transform (reference src/transforms.py:112-124), both rates, with and without antialiasing"""
     g = golden("normal_transform")
