@@ -281,6 +281,12 @@ int sei_ln_small_backward_bf16(const void* gy, const void* x, const float* mean,
  * normal_downsampling_transform (src/transforms.py:112-124); antialias selects ATen's _upsample_bicubic2d_aa weights. */
 int sei_resize_bicubic_f32(const float* x, float* y, long long planes, int H, int W, int Ho, int Wo,
                            float scale_h, float scale_w, int antialias, void* stream);
+/* deepinv.transform.Rotate (third-party, v0.2.0; used at src/losses/__init__.py:86-91): torchvision
+ * transforms.functional.rotate(x, angle) with its defaults = grid_sample(mode="nearest", padding_mode="zeros",
+ * align_corners=False) on torchvision's affine grid.  rescaled_theta: HOST pointer to the 3 x 2 fp32 matrix
+ * theta^T / [W/2, H/2] torchvision builds (row-major). */
+int sei_rotate_nearest_f32(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
+                           void* stream);
 
 #ifdef __cplusplus
 }

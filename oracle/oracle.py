@@ -201,6 +201,42 @@ def resize_bicubic(x, scale_factor, antialias):
     return np.einsum("ih,bchw,jw->bcij", My, x.astype(np.float64), Mx).astype(x.dtype)
 
 
+def rotate_nearest(x, angle):
+    """deepinv.transform.Rotate (third-party, deepinv v0.2.0 transform/rotate.py; absent from /root/reference, used at
+    src/losses/__init__.py:86-91) = torchvision.transforms.functional.rotate(x, angle) with its defaults, restated from
+    torchvision 0.26's tensor path: _get_inverse_affine_matrix(center=[0,0], -angle) -> _gen_affine_grid (linspace base grid,
+    theta^T / [w/2, h/2], bmm) -> F.grid_sample(mode="nearest", padding_mode="zeros", align_corners=False), all fp32.
+    Pinned against torchvision itself (tests/golden/rotate.npz): equal up to ~1e-6 of the pixels, whose source coordinate
+    sits on a rounding tie and follows the library's bmm summation order."""
+    import math
+    f = np.float32
+    x = np.asarray(x)
+    H, W = x.shape[-2:]
+    rot = math.radians(-float(angle))
+    a, b, c, d = math.cos(rot), -math.sin(rot), math.sin(rot), math.cos(rot)
+    theta = np.array([d, -b, 0.0, -c, a, 0.0], dtype=f).reshape(2, 3)
+    resc = (theta.T / np.array([0.5 * W, 0.5 * H], dtype=f)).astype(f)          # (3, 2)
+
+    def linspace(start, end, steps):                                            # ATen: from both ends towards the middle
+        start, end = f(start), f(end)
+        step = f((end - start) / f(steps - 1)) if steps > 1 else f(0)
+        i = np.arange(steps)
+        lo = (start + step * i.astype(f)).astype(f)
+        hi = (end - step * (steps - 1 - i).astype(f)).astype(f)
+        return np.where(i < steps // 2, lo, hi).astype(f)
+
+    bx = np.broadcast_to(linspace(-W * 0.5 + 0.5, W * 0.5 + 0.5 - 1, W)[None, :], (H, W))
+    by = np.broadcast_to(linspace(-H * 0.5 + 0.5, H * 0.5 + 0.5 - 1, H)[:, None], (H, W))
+    gx = ((bx * resc[0, 0]).astype(f) + (by * resc[1, 0]).astype(f)).astype(f) + resc[2, 0]
+    gy = ((bx * resc[0, 1]).astype(f) + (by * resc[1, 1]).astype(f)).astype(f) + resc[2, 1]
+    ix = np.rint((((gx + f(1)) * f(W)).astype(f) - f(1)) / f(2)).astype(np.int64)
+    iy = np.rint((((gy + f(1)) * f(H)).astype(f) - f(1)) / f(2)).astype(np.int64)
+    ok = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+    out = np.zeros_like(x)
+    out[..., ok] = x[..., iy[ok], ix[ok]]
+    return out
+
+
 def scale_grid(B, S, rate, center, dtype):
     rate = _c(rate, dtype).reshape(B)
     center = _c(center, dtype).reshape(B, 2)

@@ -87,6 +87,48 @@ __global__ void __launch_bounds__(256) resize_bicubic_kernel(const __grid_consta
     }
 }
 
+// Rotation by nearest-neighbour resampling: deepinv.transform.Rotate -> torchvision.transforms.functional.rotate(x, angle)
+// with its defaults (NEAREST, expand=False, zero fill), i.e. F.grid_sample(x, grid, mode="nearest", padding_mode="zeros",
+// align_corners=False) on the grid of torchvision's _gen_affine_grid.  The fp32 operation order of that grid (linspace
+// from both ends, rescaled matrix, unnormalisation, round-half-even) is kept so that the SAME source pixel is picked;
+// the six matrix entries arrive already rescaled (theta^T / [W/2, H/2], computed by the caller in fp32 like torchvision).
+struct RotateParams {
+    const float* x;
+    float* y;
+    int H, W;
+    float r00, r10, r20, r01, r11, r21;      // gx = bx * r00 + by * r10 + r20 ; gy = bx * r01 + by * r11 + r21
+    float x_start, x_end, x_step, y_start, y_end, y_step;
+    long long total;
+};
+
+// torch.linspace: start + step * i in the first half, end - step * (steps - 1 - i) in the second
+__device__ __forceinline__ float linspace_at(int i, int steps, float start, float end, float step)
+{
+    return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(steps - 1 - i)));
+}
+
+__global__ void __launch_bounds__(256) rotate_nearest_kernel(const __grid_constant__ RotateParams p)
+{
+    const int H = p.H, W = p.W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % W);
+        const long long t = idx / W;
+        const int i = (int)(t % H);
+        const long long plane = t / H;
+        const float bx = linspace_at(j, W, p.x_start, p.x_end, p.x_step), by = linspace_at(i, H, p.y_start, p.y_end, p.y_step);
+        const float gx = __fadd_rn(__fadd_rn(__fmul_rn(bx, p.r00), __fmul_rn(by, p.r10)), p.r20);
+        const float gy = __fadd_rn(__fadd_rn(__fmul_rn(bx, p.r01), __fmul_rn(by, p.r11)), p.r21);
+        // grid_sample, align_corners=False: ((g + 1) * size - 1) / 2, then nearbyint
+        const float fx = rintf(__fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 2.0f));
+        const float fy = rintf(__fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 2.0f));
+        float v = 0.0f;
+        if (fx >= 0.0f && fx <= (float)(W - 1) && fy >= 0.0f && fy <= (float)(H - 1))
+            v = __ldg(p.x + plane * (long long)H * W + (long long)(int)fy * W + (int)fx);
+        p.y[idx] = v;
+    }
+}
+
 }  // namespace sei
 
 using namespace sei;
@@ -110,4 +152,29 @@ extern "C" int sei_resize_bicubic_f32(const float* x, float* y, long long planes
     const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
     resize_bicubic_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return finish_launch("resize_bicubic_kernel");
+}
+
+extern "C" int sei_rotate_nearest_f32(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
+                                      void* stream)
+{
+    SEI_REQUIRE(x && y && rescaled_theta, "null pointer argument");
+    SEI_REQUIRE(planes >= 0 && H > 0 && W > 0, "bad shape planes=%lld %dx%d", planes, H, W);
+    if (planes == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    RotateParams p;
+    p.x = x; p.y = y; p.H = H; p.W = W;
+    // rescaled_theta: HOST pointer, 3 x 2 row-major (torchvision's rescaled_theta[0])
+    p.r00 = rescaled_theta[0]; p.r01 = rescaled_theta[1]; p.r10 = rescaled_theta[2]; p.r11 = rescaled_theta[3];
+    p.r20 = rescaled_theta[4]; p.r21 = rescaled_theta[5];
+    // linspace(-W/2 + 0.5, W/2 + 0.5 - 1, W) with the end points computed in double and rounded once, like the Python floats
+    p.x_start = (float)(-(double)W * 0.5 + 0.5); p.x_end = (float)((double)W * 0.5 + 0.5 - 1.0);
+    p.y_start = (float)(-(double)H * 0.5 + 0.5); p.y_end = (float)((double)H * 0.5 + 0.5 - 1.0);
+    p.x_step = W > 1 ? (p.x_end - p.x_start) / (float)(W - 1) : 0.0f;
+    p.y_step = H > 1 ? (p.y_end - p.y_start) / (float)(H - 1) : 0.0f;
+    p.total = planes * (long long)H * W;
+    const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
+    rotate_nearest_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return finish_launch("rotate_nearest_kernel");
 }

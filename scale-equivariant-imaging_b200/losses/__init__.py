@@ -7,7 +7,7 @@ from torch.nn import Module
 from torch.nn.functional import l1_loss
 
 from crop import CropPair
-from sei_b200.linear_physics import SupLoss, EILoss, Shift, mse
+from sei_b200.linear_physics import SupLoss, EILoss, Rotate, Shift, mse
 from transforms import ScalingTransform, CombinedTransform  # noqa: F401
 from .r2r import R2REILoss
 from .sure import SureGaussianLoss
@@ -56,9 +56,10 @@ def _ei_transform(transforms, blueprint):
         return ScalingTransform(**blueprint[ScalingTransform.__name__])
     if transforms == "Shifts":
         return Shift()
-    if transforms in ("Rotations+Shifts", "Rotations"):
-        raise NotImplementedError(f"ProposedLoss__transforms={transforms} (deepinv Rotate) is not built yet "
-                                  "(SURVEY.md section 8f, N3)")
+    if transforms == "Rotations+Shifts":
+        return CombinedTransform([Rotate(), Shift()])
+    if transforms == "Rotations":
+        return Rotate()
     raise ValueError(f"Unknown transforms: {transforms}")
 
 

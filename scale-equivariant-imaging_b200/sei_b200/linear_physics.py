@@ -173,3 +173,22 @@ class Shift(nn.Module):
         sh = int(torch.arange(-H_max, H_max)[draws.randperm(2 * H_max)][0])
         sw = int(torch.arange(-W_max, W_max)[draws.randperm(2 * W_max)][0])
         return ops._Roll.apply(x, sh, sw)
+
+
+class Rotate(nn.Module):
+    """deepinv.transform.Rotate (v0.2.0, n_trans = 1): one random rotation of the whole batch by an integer angle in
+    1..359 degrees, nearest-neighbour, same size, zero fill (torchvision's rotate defaults).  The draw follows
+    tests/golden/deepinv_shim (one CPU randperm(359)); the resampling is sei_rotate_nearest_f32."""
+
+    def __init__(self, n_trans=1, degrees=360):
+        super().__init__()
+        if n_trans != 1:
+            raise NotImplementedError("Rotate(n_trans != 1) is not used by the reference's losses")
+        self.n_trans, self.group_size = n_trans, degrees
+
+    def forward(self, x):
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("Rotate has no backward here: the reference uses it under the EI loss's "
+                                      "stop-gradient (ProposedLoss__stop_gradient=True, the default)")
+        theta = torch.arange(0, 360)[1:][draws.randperm(359)][: self.n_trans]
+        return ops.rotate_nearest(x, float(theta[0]))

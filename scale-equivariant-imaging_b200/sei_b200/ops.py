@@ -144,6 +144,28 @@ def resize_bicubic(x, scale_factor, antialias):
     return y
 
 
+def rotate_rescaled_theta(angle, H, W):
+    """The 3 x 2 fp32 matrix torchvision builds for rotate(x, angle): _get_inverse_affine_matrix(center=[0, 0], -angle,
+    translate=[0, 0], scale=1, shear=[0, 0]) -> theta (2 x 3, fp32) -> theta^T / [0.5 W, 0.5 H]."""
+    import math
+    rot = math.radians(-float(angle))
+    a, b, c, d = math.cos(rot), -math.sin(rot), math.sin(rot), math.cos(rot)
+    theta = np.array([d, -b, 0.0, -c, a, 0.0], dtype=np.float32).reshape(2, 3)
+    return np.ascontiguousarray(theta.T / np.array([0.5 * W, 0.5 * H], dtype=np.float32), dtype=np.float32)
+
+
+def rotate_nearest(x, angle):
+    """torchvision.transforms.functional.rotate(x, angle) with its defaults (nearest, same size, zero fill), the call
+    deepinv's Rotate makes (sei_rotate_nearest_f32); no autograd"""
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    r = rotate_rescaled_theta(angle, H, W)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_rotate_nearest_f32(_ptr(x), _ptr(y), B * Cc, H, W, C.c_void_p(r.ctypes.data), _stream(x)))
+    return y
+
+
 def scale_params(u_rate, u_center, rates):
     u_rate, u_center = _t(u_rate, "u_rate"), _t(u_center, "u_center")
     B = u_rate.numel()

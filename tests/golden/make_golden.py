@@ -278,6 +278,8 @@ def gen_losses():
         ("deblur_gauss2_shifts", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Shifts"), (2, 3, 32, 32)),
         ("sr2_nostopgrad", dict(task="sr", kernel=None, sr_factor=2, method="proposed", ProposedLoss__stop_gradient=False), (2, 3, 16, 16)),
         ("deblur_gauss2_normalT", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ScalingTransform__kind="normal"), (2, 3, 32, 32)),
+        ("deblur_gauss2_rotations", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Rotations"), (2, 3, 32, 32)),
+        ("deblur_gauss2_rotshift", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Rotations+Shifts"), (2, 3, 32, 32)),
         ("deblur_gauss2_normalT_aa", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ScalingTransform__kind="normal", ScalingTransform__antialias=True), (2, 3, 32, 32)),
     ]
     only = os.environ.get("GOLDEN_ONLY", "")
@@ -447,6 +449,30 @@ def gen_transform_aa():
         msg = str(e).splitlines()[0]
     out["mixed_rates_error"] = np.array(msg)
     save("transform_aa", **out)
+
+
+def gen_rotate():
+    """deepinv Rotate = torchvision.transforms.functional.rotate(x, angle), defaults (nearest, same size, zero fill): the real
+    torchvision function on CPU for a set of angles and shapes, plus the module form of the shim (draw + output)"""
+    from torchvision.transforms.functional import rotate
+    from deepinv.transform import Rotate
+    g = torch.Generator().manual_seed(606)
+    out = {}
+    shapes = [(2, 3, 32, 32), (1, 2, 48, 40), (1, 1, 21, 37), (1, 1, 96, 96)]
+    angles = [1, 17, 36, 45, 50, 90, 123, 180, 200, 270, 301, 359]
+    out["angles"] = np.array(angles)
+    for i, shape in enumerate(shapes):
+        x = torch.rand(shape, generator=g)
+        out[f"x{i}"] = np_(x)
+        for a in angles:
+            out[f"y{i}_a{a}"] = np_(rotate(x, float(a)))
+    x = torch.rand((2, 3, 24, 24), generator=g)
+    with DrawRecorder() as rec:
+        torch.manual_seed(8)
+        y = Rotate()(x)
+    out.update(rec.as_dict("module_draw"))
+    out["module_x"], out["module_y"] = np_(x), np_(y)
+    save("rotate", **out)
 
 
 def gen_resample():

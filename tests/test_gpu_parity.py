@@ -417,7 +417,7 @@ LOSS_CASES = ["deblur_gauss2_proposed", "deblur_box3_proposed", "deblur_gauss2_v
               "sr4_proposed", "sr2_partial_proposed", "deblur_gauss2_sure", "deblur_gauss2_sure_avgcst",
               "deblur_gauss2_sure_nocrop", "deblur_gauss2_supervised", "sr2_css", "deblur_gauss2_proposed_alpha",
               "cfg1_deblur_gauss2_proposed", "deblur_gauss2_r2r", "sr2_r2r", "deblur_gauss2_nostopgrad", "sr2_nostopgrad", "deblur_gauss2_shifts",
-              "deblur_gauss2_normalT", "deblur_gauss2_normalT_aa"]
+              "deblur_gauss2_normalT", "deblur_gauss2_normalT_aa", "deblur_gauss2_rotations", "deblur_gauss2_rotshift"]
 LOSS_ARGS = {
     "deblur_gauss2_proposed": dict(), "deblur_box3_proposed": dict(kernel="Box_R3"),
     "deblur_gauss2_v1_proposed": dict(physics_v2=False),
@@ -435,6 +435,8 @@ LOSS_ARGS = {
     "deblur_gauss2_shifts": dict(ProposedLoss__transforms="Shifts"),
     "deblur_gauss2_normalT": dict(ScalingTransform__kind="normal"),
     "deblur_gauss2_normalT_aa": dict(ScalingTransform__kind="normal", ScalingTransform__antialias=True),
+    "deblur_gauss2_rotations": dict(ProposedLoss__transforms="Rotations"),
+    "deblur_gauss2_rotshift": dict(ProposedLoss__transforms="Rotations+Shifts"),
 }
 
 
@@ -593,6 +595,29 @@ def test_antialiased_padded_transform_vs_reference(golden, dev):
 def draws_inject_equal_rates(dev):
     from sei_b200 import draws
     return draws.inject([np.array([0.7], dtype=np.float32), np.array([[0.25, 0.5]], dtype=np.float32)])
+
+
+def test_rotate_vs_torchvision(golden, dev):
+    """deepinv Rotate (torchvision rotate defaults): sei_rotate_nearest_f32 picks the same source pixels as torchvision's CPU
+    fixtures and as the oracle (ties in the rounding of a source coordinate excepted: at most 1e-4 of the pixels)"""
+    from sei_b200 import draws, last_kernel, ops
+    from sei_b200.linear_physics import Rotate
+    g = golden("rotate")
+    bad = bad_orc = tot = 0
+    for i in range(4):
+        x = g[f"x{i}"]
+        for a in g["angles"]:
+            got = ops.rotate_nearest(cu(x, dev), float(a)).cpu().numpy()
+            bad += int((got != g[f"y{i}_a{a}"]).sum())
+            bad_orc += int((got != orc.rotate_nearest(x, float(a))).sum())
+            tot += got.size
+    assert last_kernel() == "rotate_nearest_kernel"
+    assert bad <= 1e-4 * tot and bad_orc == 0, (bad, bad_orc, tot)
+    with draws.inject([g["module_draw0_randperm"]]):
+        y = Rotate()(cu(g["module_x"], dev))
+    assert int((npy(y) != g["module_y"]).sum()) <= 2
+    with pytest.raises(NotImplementedError):
+        Rotate()(cu(g["module_x"], dev).requires_grad_(True))
 
 
 def test_normal_scaling_transform_module(dev):

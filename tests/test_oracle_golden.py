@@ -251,6 +251,22 @@ def test_oracle_antialiased_scale_transform_matches_reference(golden):
         orc.scale_transform_antialiased(np.zeros((2, 1, 16, 16)), np.array([0.75, 0.5]), np.zeros((2, 2)))
 
 
+def test_oracle_rotate_matches_torchvision(golden):
+    """deepinv Rotate = torchvision rotate(x, angle) with its defaults; fixtures made by torchvision itself.  Index work:
+    identical pixels, except source coordinates on a rounding tie (bounded at 1e-4 of the pixels; 0 on these fixtures)"""
+    g = golden("rotate")
+    bad = tot = 0
+    for i in range(4):
+        for a in g["angles"]:
+            ref, got = g[f"y{i}_a{a}"], orc.rotate_nearest(g[f"x{i}"], float(a))
+            assert got.shape == ref.shape
+            bad += int((ref != got).sum())
+            tot += ref.size
+    assert bad <= 1e-4 * tot, (bad, tot)
+    x = g["x0"]
+    assert np.array_equal(orc.rotate_nearest(x, 180.0), x[..., ::-1, ::-1])        # exact for the half turn
+
+
 def test_oracle_resize_bicubic_matches_reference(golden):
     """normal_downsampling_transform (reference src/transforms.py:112-124), both rates, with and without antialiasing"""
     g = golden("normal_transform")
