@@ -1,5 +1,6 @@
 #!/bin/bash
-# resampler products at the real training shapes + a last test / smoke / bench pass
+# resampler products after the block-diagonal packing: parity, then the per-shape table
 set -x
 mkdir -p gpurun_out
-timeout 300 python benchmarks/resample_bench.py > gpurun_out/resample_bench.md 2>&1; cat gpurun_out/resample_bench.md
+timeout 600 python -m pytest tests/test_cnn_kernels.py tests/test_gpu_model.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python benchmarks/resample_bench.py > gpurun_out/resample_bench_packed.md 2>&1; cat gpurun_out/resample_bench_packed.md

@@ -46,25 +46,18 @@ def main():
             pk = resample._packed(kind, H, W, 2, dev)
             Ho, Wo = pk["Ho"], pk["Wo"]
             x = torch.randn(B, H, W, C, device=dev).bfloat16()
-            y = torch.empty((B, 2, H, Wo, C), dtype=x.dtype, device=dev)
             out = torch.empty((B, Ho, Wo, C), dtype=x.dtype, device=dev)
             gx = torch.empty_like(x)
-            a1, a2, a2t, a1t = pk["A1"], pk["A2"], pk["A2T"], pk["A1T"]
-            calls = [
-                ("fwd width", a1, C, B * H, x, y, lambda: ops.bgemm_bf16(a1.data, x, y, a1.M, a1.K, C, a1.tile, B * H, H, (H * W * C, W * C), W, (0, C),
-                                                                      (2 * H * Wo * C, Wo * C), Wo, (H * Wo * C, C))),
-                ("fwd height", a2, Wo * C, B, y, out, lambda: ops.bgemm_bf16(a2.data, y, out, a2.M, a2.K, Wo * C, a2.tile, B, 1, (2 * H * Wo * C, 0), 2 * H,
-                                                                          (0, Wo * C), (Ho * Wo * C, 0), Ho, (0, Wo * C))),
-                ("bwd height", a2t, Wo * C, B, out, y, lambda: ops.bgemm_bf16(a2t.data, out, y, a2t.M, a2t.K, Wo * C, a2t.tile, B, 1, (Ho * Wo * C, 0), Ho,
-                                                                           (0, Wo * C), (2 * H * Wo * C, 0), 2 * H, (0, Wo * C))),
-                ("bwd width", a1t, C, B * H, y, gx, lambda: ops.bgemm_bf16(a1t.data, y, gx, a1t.M, a1t.K, C, a1t.tile, B * H, H, (2 * H * Wo * C, Wo * C), Wo,
-                                                                        (H * Wo * C, C), (H * W * C, W * C), W, (0, C))),
-            ]
+            y = torch.empty((B, H, 2, Wo, C), dtype=x.dtype, device=dev)
+            calls = [("fwd width", pk["A1"], C, B * H, x, y), ("fwd height", pk["A2"], Wo * C, B, y, out),
+                     ("bwd height", pk["A2T"], Wo * C, B, out, y), ("bwd width", pk["A1T"], C, B * H, y, gx)]
+            calls = [(n_, a_, N_, it_, s_, d_, (lambda a_=a_, s_=s_, d_=d_, N_=N_, it_=it_: a_(s_, d_, N_, it_))) for n_, a_, N_, it_, s_, d_ in calls]
             for name, a, N, items, src, dst, fn in calls:
                 us = bench(fn)
                 total += us
                 gb = (src.numel() + dst.numel()) * 2 / 1e9
-                print(f"| {kind} | {lvl} | {tuple(x.shape)} | {name} | {a.M} | {a.K} | {N} | {items} | {us:.1f} | {gb / us * 1e6:.0f} | "
+                Pk = a._pack_factor(items)
+                print(f"| {kind} | {lvl} | {tuple(x.shape)} | {name} | {a.A.shape[0]} x{Pk} | {a.A.shape[1]} x{Pk} | {N} | {items // Pk} | {us:.1f} | {gb / us * 1e6:.0f} | "
                       f"{gb / us * 1e6 / peak:.2f} | {last_kernel()} |")
             del x, y, out, gx
     print(f"\nsum of the 32 calls: {total / 1e3:.2f} ms (a proposed step runs each forward pass 3 times and each backward pass about 3 times)")

@@ -17,7 +17,9 @@ operator (tests/test_cnn_kernels.py::test_resample_operators_match_reference: 1e
 
 On the GPU the two contractions run as batched tensor-core products on channels-last bf16 activations
 (csrc/bgemm.cu, sei_bgemm_bf16): width first over batch = (image, row) with A = [P; Q], then height over
-batch = image with A = [Gr | Gi]; the backward pass applies the transposed operators the same way.
+batch = image with A = [Gr | Gi] (columns interleaved to match the (row, term) order of the intermediate); the backward
+pass applies the transposed operators the same way.  Small operators are applied to several batch entries at once through
+a block-diagonal operator (_Product).
 """
 from math import ceil
 
@@ -94,47 +96,71 @@ class _Packed:
         self.data = buf.to(device=device, dtype=torch.bfloat16)
 
 
+class _Product:
+    """One of the four batched products of a resampler: D_b = A @ X_b with contiguous items (X_b: [K, N], D_b: [M, N],
+    consecutive batch entries back to back).  A small operator (M < 128 rows) fills only part of the 128 TMEM lanes of a
+    UMMA and leaves the epilogue of the tcgen05 kernel to one or two of its four warps (measured: 0.33-0.44 of the copy
+    peak at the deepest level, profiles/r01_resample_bench.md), so P consecutive batch entries are processed as ONE item
+    with the block-diagonal operator I_P (x) A: [P M, P K] @ [P K, N] -- the stacked entries ARE a contiguous [P K, N]
+    matrix.  The extra zero blocks cost tensor-core time only, of which there is plenty (the product is HBM-bound)."""
+
+    def __init__(self, A, device):
+        self.A, self.device, self._packs = A, device, {}
+
+    def _pack_factor(self, batches):
+        M, K = self.A.shape
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0          # noqa: E731
+        if not (pow2(M) and pow2(K)) or M >= 128:
+            return 1
+        P = 1
+        while P < 8 and 2 * P * M <= 128 and 2 * P * K <= 512 and batches % (2 * P) == 0:
+            P *= 2
+        return P
+
+    def __call__(self, src, dst, N, batches):
+        P = self._pack_factor(batches)
+        a = self._packs.get(P)
+        if a is None:
+            a = self._packs[P] = _Packed(torch.block_diag(*([self.A] * P)) if P > 1 else self.A, self.device)
+        ops.bgemm_bf16(a.data, src, dst, a.M, a.K, N, a.tile, batches // P, 1, (a.K * N, 0), a.K, (0, N),
+                       (a.M * N, 0), a.M, (0, N))
+        return dst
+
+
 def _packed(kind, H, W, rate, device):
     key = (kind, H, W, rate, str(device))
     if key not in _PACKED:
         Gr, Gi, P, Q = operator(kind, H, W, rate)
-        A1 = torch.cat([P, Q], 0)            # (2 Wo, W)
-        A2 = torch.cat([Gr, Gi], 1)          # (Ho, 2 H)
+        Ho, Wo = Gr.shape[0], P.shape[0]
+        A1 = torch.cat([P, Q], 0)                                             # (2 Wo, W): rows (term, wo)
+        A2 = torch.stack([Gr, Gi], 2).reshape(Ho, 2 * H)                      # (Ho, 2 H): columns (h, term) interleaved
         _PACKED[key] = {
-            "Ho": Gr.shape[0], "Wo": P.shape[0],
-            "A1": _Packed(A1, device), "A2": _Packed(A2, device),
-            "A2T": _Packed(A2.t().contiguous(), device), "A1T": _Packed(A1.t().contiguous(), device),
+            "Ho": Ho, "Wo": Wo,
+            "A1": _Product(A1, device), "A2": _Product(A2, device),
+            "A2T": _Product(A2.t().contiguous(), device), "A1T": _Product(A1.t().contiguous(), device),
         }
     return _PACKED[key]
 
 
 def _forward_cl(x, pk):
-    """x: (B, H, W, C) contiguous bf16 -> (B, Ho, Wo, C)"""
+    """x: (B, H, W, C) contiguous bf16 -> (B, Ho, Wo, C).  The two-term intermediate is laid out (B, H, 2, Wo, C): every
+    product then reads and writes plain contiguous matrices -- per image row [W, C] -> [2 Wo, C] along the width, per image
+    [2 H, Wo C] -> [Ho, Wo C] along the height (rows (h, term) match the interleaved columns of A2)."""
     B, H, W, C = x.shape
     Ho, Wo = pk["Ho"], pk["Wo"]
-    y = torch.empty((B, 2, H, Wo, C), dtype=x.dtype, device=x.device)
-    a = pk["A1"]
-    ops.bgemm_bf16(a.data, x, y, a.M, a.K, C, a.tile, B * H, H, (H * W * C, W * C), W, (0, C),
-                   (2 * H * Wo * C, Wo * C), Wo, (H * Wo * C, C))
+    y = torch.empty((B, H, 2, Wo, C), dtype=x.dtype, device=x.device)
+    pk["A1"](x, y, C, B * H)
     out = torch.empty((B, Ho, Wo, C), dtype=x.dtype, device=x.device)
-    a = pk["A2"]
-    ops.bgemm_bf16(a.data, y, out, a.M, a.K, Wo * C, a.tile, B, 1, (2 * H * Wo * C, 0), 2 * H, (0, Wo * C),
-                   (Ho * Wo * C, 0), Ho, (0, Wo * C))
-    return out
+    return pk["A2"](y, out, Wo * C, B)
 
 
 def _backward_cl(g, pk, H, W):
     """transposed operator: g (B, Ho, Wo, C) -> (B, H, W, C)"""
     B, Ho, Wo, C = g.shape
-    gy = torch.empty((B, 2, H, Wo, C), dtype=g.dtype, device=g.device)
-    a = pk["A2T"]
-    ops.bgemm_bf16(a.data, g, gy, a.M, a.K, Wo * C, a.tile, B, 1, (Ho * Wo * C, 0), Ho, (0, Wo * C),
-                   (2 * H * Wo * C, 0), 2 * H, (0, Wo * C))
+    gy = torch.empty((B, H, 2, Wo, C), dtype=g.dtype, device=g.device)
+    pk["A2T"](g, gy, Wo * C, B)
     gx = torch.empty((B, H, W, C), dtype=g.dtype, device=g.device)
-    a = pk["A1T"]
-    ops.bgemm_bf16(a.data, gy, gx, a.M, a.K, C, a.tile, B * H, H, (2 * H * Wo * C, Wo * C), Wo, (H * Wo * C, C),
-                   (H * W * C, W * C), W, (0, C))
-    return gx
+    return pk["A1T"](gy, gx, C, B * H)
 
 
 class _IdealResample(torch.autograd.Function):

@@ -107,7 +107,10 @@ def test_bgemm_split_rows(dev):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,W,C,kind", [(3, 16, 32, 16, "down"), (2, 64, 64, 8, "down"), (2, 32, 16, 64, "up"),
                                           (1, 128, 128, 32, "down"), (1, 64, 64, 128, "up"), (2, 256, 256, 8, "down"),
-                                          (1, 512, 512, 8, "down"), (1, 256, 256, 8, "up"), (1, 1024, 1024, 8, "down")])
+                                          (1, 512, 512, 8, "down"), (1, 256, 256, 8, "up"), (1, 1024, 1024, 8, "down"),
+                                          # small operators: 2 / 4 / 8 batch entries per UMMA through a block-diagonal operator
+                                          (32, 16, 16, 64, "up"), (8, 32, 32, 128, "down"), (4, 16, 16, 256, "up"),
+                                          (32, 8, 8, 64, "down"), (6, 32, 32, 32, "down"), (3, 16, 16, 64, "up")])
 def test_ideal_resample_tcgen05_path(dev, B, H, W, C, kind):
     """power-of-two shapes take the tcgen05 kernel (5-D tensor maps for the split rows): forward and transposed
     operator against the dense fp32 formulation of the same operator (models/resample.apply_dense)"""
