@@ -1260,7 +1260,14 @@ int bgemm_tc_try_launch(const void* A, const void* X, void* D, int M, int K, int
     const dim3 grid(gx, m_blocks);
     if (resident) {
         const size_t smem = (size_t)mb * kb * 16384 + (size_t)ST * bn * 64 * 2 + slabs;
-        if (bn == 64) {
+        // narrow tiles (N <= 64: the 32-channel level) move 8 KB per stage: a deeper ring keeps more bytes in flight
+        constexpr int ST_DEEP = 6;
+        const size_t smem_deep = (size_t)mb * kb * 16384 + (size_t)ST_DEEP * 64 * 64 * 2 + slabs;
+        const char* nodeep = getenv("SEI_BGEMM_NO_DEEP_RING");
+        if (bn == 64 && smem_deep + 2048 <= (size_t)dp.smem_optin && !(nodeep && *nodeep == '1')) {
+            SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST_DEEP, true>, smem_deep));
+            bgemm_tc_kernel<64, ST_DEEP, true><<<grid, kGemmThreads, smem_deep, st>>>(ma, mx, md, p);
+        } else if (bn == 64) {
             SEI_CUDA(allow_smem(bgemm_tc_kernel<64, ST, true>, smem));
             bgemm_tc_kernel<64, ST, true><<<grid, kGemmThreads, smem, st>>>(ma, mx, md, p);
         } else {
