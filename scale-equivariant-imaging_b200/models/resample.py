@@ -84,7 +84,7 @@ def apply_dense(kind, x, rate):
 class _Packed:
     """one operator matrix A[M, K] in the layout sei_bgemm_bf16 wants: bf16, K padded to 64, rows to the CTA tile"""
 
-    def __init__(self, A, device):
+    def __init__(self, A, device, dtype=torch.bfloat16):
         self.M, self.K = A.shape
         kpad = -(-self.K // 64) * 64
         self.tile = ops.bgemm_tile_rows(self.M, kpad)
@@ -93,7 +93,7 @@ class _Packed:
         rows = -(-self.M // self.tile) * self.tile
         buf = torch.zeros((rows, kpad), dtype=torch.float64)
         buf[:self.M, :self.K] = A
-        self.data = buf.to(device=device, dtype=torch.bfloat16)
+        self.data = buf.to(device=device, dtype=dtype)
 
 
 class _Product:
@@ -104,8 +104,8 @@ class _Product:
     with the block-diagonal operator I_P (x) A: [P M, P K] @ [P K, N] -- the stacked entries ARE a contiguous [P K, N]
     matrix.  The extra zero blocks cost tensor-core time only, of which there is plenty (the product is HBM-bound)."""
 
-    def __init__(self, A, device):
-        self.A, self.device, self._packs = A, device, {}
+    def __init__(self, A, device, dtype=torch.bfloat16):
+        self.A, self.device, self.dtype, self._packs = A, device, dtype, {}
 
     def _pack_factor(self, batches):
         M, K = self.A.shape
@@ -121,14 +121,15 @@ class _Product:
         P = self._pack_factor(batches)
         a = self._packs.get(P)
         if a is None:
-            a = self._packs[P] = _Packed(torch.block_diag(*([self.A] * P)) if P > 1 else self.A, self.device)
+            a = self._packs[P] = _Packed(torch.block_diag(*([self.A] * P)) if P > 1 else self.A, self.device, self.dtype)
         ops.bgemm_bf16(a.data, src, dst, a.M, a.K, N, a.tile, batches // P, 1, (a.K * N, 0), a.K, (0, N),
                        (a.M * N, 0), a.M, (0, N))
         return dst
 
 
-def _packed(kind, H, W, rate, device):
-    key = (kind, H, W, rate, str(device))
+def _packed(kind, H, W, rate, device, dtype=torch.bfloat16):
+    """the four products of one resampler; dtype other than bf16 only for the CPU emulation in tests/test_cnn_kernels.py"""
+    key = (kind, H, W, rate, str(device), str(dtype))
     if key not in _PACKED:
         Gr, Gi, P, Q = operator(kind, H, W, rate)
         Ho, Wo = Gr.shape[0], P.shape[0]
@@ -136,8 +137,8 @@ def _packed(kind, H, W, rate, device):
         A2 = torch.stack([Gr, Gi], 2).reshape(Ho, 2 * H)                      # (Ho, 2 H): columns (h, term) interleaved
         _PACKED[key] = {
             "Ho": Ho, "Wo": Wo,
-            "A1": _Product(A1, device), "A2": _Product(A2, device),
-            "A2T": _Product(A2.t().contiguous(), device), "A1T": _Product(A1.t().contiguous(), device),
+            "A1": _Product(A1, device, dtype), "A2": _Product(A2, device, dtype),
+            "A2T": _Product(A2.t().contiguous(), device, dtype), "A1T": _Product(A1.t().contiguous(), device, dtype),
         }
     return _PACKED[key]
 

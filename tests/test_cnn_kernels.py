@@ -33,6 +33,54 @@ def test_resample_operators_match_reference(golden, kind):
         assert rel_err(gx.numpy(), g[f"{kind}{i}_gx"]) < 1e-12, (kind, i)
 
 
+def _emulated_bgemm(A, x, out, M, K, N, tile_rows, batches, b_inner, x_b, k_inner, x_k, d_b, m_inner, d_m):
+    """sei_bgemm_bf16's addressing (include/sei_b200.h) restated with as_strided views, for CPU tensors of any dtype:
+    entry b = bo * b_inner + bi, row k = ko * k_inner + ki of X, row m = mo * m_inner + mi of D, columns contiguous"""
+    bo = batches // b_inner
+    xs = torch.as_strided(x, (bo, b_inner, K // k_inner, k_inner, N), (x_b[0], x_b[1], x_k[0], x_k[1], 1)).reshape(batches, K, N)
+    res = torch.matmul(A[:M, :K].to(x.dtype), xs)
+    torch.as_strided(out, (bo, b_inner, M // m_inner, m_inner, N), (d_b[0], d_b[1], d_m[0], d_m[1], 1)).copy_(
+        res.reshape(bo, b_inner, M // m_inner, m_inner, N))
+    return out
+
+
+@pytest.mark.parametrize("kind,B,H,W,C", [("down", 8, 32, 32, 8), ("up", 8, 16, 16, 16), ("down", 4, 64, 64, 8), ("up", 6, 8, 8, 8),
+                                          ("down", 3, 16, 32, 8), ("up", 2, 64, 64, 8)])
+def test_resampler_products_layout_and_batching(monkeypatch, kind, B, H, W, C):
+    """models/resample.py's four batched products (contiguous two-term intermediate, interleaved columns of the height
+    operator, block-diagonal batching of small operators) reproduce the dense operator: run on the CPU in float64 with the
+    addressing of sei_bgemm_bf16 emulated by strided views -- forward and transposed, 1e-12"""
+    from models import resample
+    from sei_b200 import ops
+    monkeypatch.setattr(ops, "bgemm_bf16", _emulated_bgemm)
+    monkeypatch.setattr(ops, "bgemm_tile_rows", lambda M, Kpad: 128)      # the library asks the device; only pads A's rows
+    torch.manual_seed(B * H + W)
+    pk = resample._packed(kind, H, W, 2, "cpu", dtype=torch.float64)
+    x = torch.randn(B, H, W, C, dtype=torch.float64)
+    y = resample._forward_cl(x, pk)
+    ref = resample.apply_dense(kind, x.permute(0, 3, 1, 2), 2)
+    assert rel_err(y.permute(0, 3, 1, 2).numpy(), ref.numpy()) < 1e-12
+    g = torch.randn_like(y)
+    gx = resample._backward_cl(g, pk, H, W)
+    Gr, Gi, P, Q = resample.operator(kind, H, W, 2)
+    gl = g.permute(0, 3, 1, 2)
+    gref = Gr.t() @ gl @ P + Gi.t() @ gl @ Q
+    assert rel_err(gx.permute(0, 3, 1, 2).numpy(), gref.numpy()) < 1e-12
+    # the batching factors: rows x P <= 128, columns x P <= 512, P | batches, powers of two only
+    for name, batches in (("A1", B * H), ("A2", B), ("A2T", B), ("A1T", B * H)):
+        prod = pk[name]
+        M, K = prod.A.shape
+        P_ = prod._pack_factor(batches)
+        assert batches % P_ == 0 and (P_ == 1 or (P_ * M <= 128 and P_ * K <= 512 and P_ <= 8))
+        if M >= 128 or M & (M - 1) or K & (K - 1):
+            assert P_ == 1
+        elif batches % 2 == 0 and 2 * M <= 128 and 2 * K <= 512:
+            assert P_ >= 2
+    assert resample._Product(torch.zeros(32, 32, dtype=torch.float64), "cpu")._pack_factor(32) == 4
+    assert resample._Product(torch.zeros(16, 64, dtype=torch.float64), "cpu")._pack_factor(1024) == 8
+    assert resample._Product(torch.zeros(24, 32, dtype=torch.float64), "cpu")._pack_factor(32) == 1
+
+
 def test_mirror_fft_path_matches_reference(golden):
     """the library (torch.fft) formulation kept for channel counts that are not a multiple of 8"""
     import models.convolutional as mc

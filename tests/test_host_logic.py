@@ -152,6 +152,15 @@ def test_factories_build_the_reference_objects():
     assert crop_loss.crop_fn is not None and crop_loss.xy_size_ratio == 1
 
 
+def test_batched_degradation_checks_its_seeds():
+    import physics
+    mgr = getattr(physics.get_physics(base_args(), device="cpu"), "__manager")
+    with pytest.raises(ValueError, match="3 images but 2 seeds"):
+        mgr.randomly_degrade_batch(torch.zeros(3, 3, 8, 8), [1, 2])
+    with pytest.raises(sei_b200.SeiError):                         # CPU tensors: no fallback, like every operator
+        mgr.randomly_degrade_batch(torch.zeros(2, 3, 16, 16), [1, 2])
+
+
 def test_crop_pair_matches_reference(golden):
     from crop import CropPair
     g = golden("crop")
