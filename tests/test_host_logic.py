@@ -38,6 +38,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.sei_abi_version() == 1
     assert lib.sei_reduce_workspace_bytes() > 0
+    integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()       # every entry point is mapped to the code it replaces
+    assert not [name for name in declared if name not in integration]
 
 
 def test_sass_is_blackwell_native():
