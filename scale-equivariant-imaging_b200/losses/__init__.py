@@ -51,16 +51,19 @@ class SURELoss(_ModelThenLoss):
                                                    averaged_cst=averaged_cst, margin=margin))
 
 
+_EI_TRANSFORMS = {
+    # ProposedLoss__transforms -> factory(blueprint)   (reference :84-96)
+    "Scaling_Transforms": lambda blueprint: ScalingTransform(**blueprint[ScalingTransform.__name__]),
+    "Shifts": lambda blueprint: Shift(),
+    "Rotations": lambda blueprint: Rotate(),
+    "Rotations+Shifts": lambda blueprint: CombinedTransform([Rotate(), Shift()]),
+}
+
+
 def _ei_transform(transforms, blueprint):
-    if transforms == "Scaling_Transforms":
-        return ScalingTransform(**blueprint[ScalingTransform.__name__])
-    if transforms == "Shifts":
-        return Shift()
-    if transforms == "Rotations+Shifts":
-        return CombinedTransform([Rotate(), Shift()])
-    if transforms == "Rotations":
-        return Rotate()
-    raise ValueError(f"Unknown transforms: {transforms}")
+    if transforms not in _EI_TRANSFORMS:
+        raise ValueError(f"Unknown transforms: {transforms}")
+    return _EI_TRANSFORMS[transforms](blueprint)
 
 
 class ProposedLoss(Module):
@@ -95,21 +98,19 @@ class Loss(Module):
     def __init__(self, physics, blueprint, noise_level, sure_cropped_div, sure_averaged_cst, sure_margin,
                  method, crop_training_pairs, crop_size):
         super().__init__()
-        if method == "supervised":
-            self.loss = SupervisedLoss(physics=physics)
-        elif method == "css":
-            self.loss = CSSLoss(physics=physics)
-        elif method == "noise2inverse":
-            self.loss = Noise2InverseLoss(physics=physics)
-        elif method == "sure":
-            self.loss = SURELoss(physics=physics, noise_level=noise_level, cropped_div=sure_cropped_div,
-                                 averaged_cst=sure_averaged_cst, margin=sure_margin)
-        elif method == "proposed":
-            self.loss = ProposedLoss(physics=physics, blueprint=blueprint, noise_level=noise_level,
-                                     sure_cropped_div=sure_cropped_div, sure_averaged_cst=sure_averaged_cst,
-                                     sure_margin=sure_margin, **blueprint[ProposedLoss.__name__])
-        else:
-            raise ValueError(f"Unknwon method: {method}")
+        sure = dict(noise_level=noise_level, sure_cropped_div=sure_cropped_div, sure_averaged_cst=sure_averaged_cst,
+                    sure_margin=sure_margin)
+        methods = {
+            "supervised": lambda: SupervisedLoss(physics=physics),
+            "css": lambda: CSSLoss(physics=physics),
+            "noise2inverse": lambda: Noise2InverseLoss(physics=physics),
+            "sure": lambda: SURELoss(physics=physics, noise_level=noise_level, cropped_div=sure_cropped_div,
+                                     averaged_cst=sure_averaged_cst, margin=sure_margin),
+            "proposed": lambda: ProposedLoss(physics=physics, blueprint=blueprint, **sure, **blueprint[ProposedLoss.__name__]),
+        }
+        if method not in methods:
+            raise ValueError(f"Unknwon method: {method}")          # (the reference's spelling)
+        self.loss = methods[method]()
 
         self.crop_fn = None
         if crop_training_pairs:

@@ -1,50 +1,61 @@
 """Recorrupted-to-Recorrupted loss and its equivariant companion (reference: src/losses/r2r.py), selected by
---ProposedLoss__sure_alternative r2r.  Same classes and signatures; the scaled noise additions, A and the
-MSE reductions run in libsei_b200 kernels."""
+--ProposedLoss__sure_alternative r2r.  Same class names, constructor arguments and attributes; every recorruption
+y + level * n is one streaming kernel (sei_add_noise_f32) on a standard-normal draw, A and the MSE reductions are the
+libsei_b200 operators."""
 import torch
-import torch.nn as nn
-from torch.nn import Module
+from torch import nn
 
 from sei_b200 import draws, ops
 from sei_b200.linear_physics import mse
 
 
+def _recorrupt(y, noise, level):
+    """y + level * noise (noise ~ N(0, 1) drawn by the caller, so that one draw can be used twice)"""
+    return ops._AddNoise.apply(y, noise, level)
+
+
 class R2RLoss(nn.Module):
+    """metric(A(model(y + eta alpha n)), y - (eta / alpha) n) for ONE draw n (reference :8-24)"""
+
     def __init__(self, metric=None, eta=0.1, alpha=0.5):
         super().__init__()
         self.name = "r2r"
-        self.metric = metric if metric is not None else mse()
-        self.eta = eta
-        self.alpha = alpha
+        self.metric = mse() if metric is None else metric
+        self.eta, self.alpha = eta, alpha
+
+    def recorrupted_pair(self, y):
+        n = draws.randn_like(y)
+        return _recorrupt(y, n, self.eta * self.alpha), _recorrupt(y, n, -self.eta / self.alpha)
 
     def forward(self, y, physics, model, **kwargs):
-        n = draws.randn_like(y)                                     # pert = n * eta
-        y_plus = ops._AddNoise.apply(y, n, self.eta * self.alpha)   # y + pert * alpha
-        y_minus = ops._AddNoise.apply(y, n, -self.eta / self.alpha)  # y - pert / alpha
-        output = model(y_plus, physics)
-        return self.metric(physics.A(output), y_minus)
+        network_input, target = self.recorrupted_pair(y)
+        return self.metric(physics.A(model(network_input, physics)), target)
 
 
-class R2REILoss(Module):
+class R2REILoss(nn.Module):
+    """R2R data term + an EI term whose two network inputs carry noise of the same total level 1.5 sigma: the measurement
+    (noise sigma) is recorrupted with 0.5 sigma, the clean re-measurement A(T(x1)) with 1.5 sigma (reference :27-57)"""
+
+    FIRST_PASS_LEVEL, SECOND_PASS_LEVEL = 0.5, 1.5
+
     def __init__(self, transform, sigma, no_grad=True, metric=None):
         super().__init__()
-        self.T = transform
-        self.sigma = sigma
-        self.no_grad = no_grad
-        self.metric = metric if metric is not None else mse()
+        self.T, self.sigma, self.no_grad = transform, sigma, no_grad
+        self.metric = mse() if metric is None else metric
         self.r2r_loss = R2RLoss(eta=self.sigma, alpha=0.5)
 
-    def forward(self, *kargs, **kwargs):
-        return self.r2r_loss(*kargs, **kwargs) + self.ei_loss(*kargs, **kwargs)
+    def _transformed(self, x):
+        # the stop-gradient of the EI target: T runs without a graph when no_grad is set
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not self.no_grad):
+            return self.T(x)
 
     def ei_loss(self, y, physics, model, **kwargs):
-        """EI with consistent input noise (reference :37-57): both network inputs carry noise of level 1.5 sigma"""
-        x1 = model(ops._AddNoise.apply(y, draws.randn_like(y), 0.5 * self.sigma), physics)
-        if self.no_grad:
-            with torch.no_grad():
-                x2 = self.T(x1)
-        else:
-            x2 = self.T(x1)
+        x1 = model(_recorrupt(y, draws.randn_like(y), self.FIRST_PASS_LEVEL * self.sigma), physics)
+        x2 = self._transformed(x1)
         y2 = physics.A(x2)
-        x3 = model(ops._AddNoise.apply(y2, draws.randn_like(y2), 1.5 * self.sigma), physics)
+        x3 = model(_recorrupt(y2, draws.randn_like(y2), self.SECOND_PASS_LEVEL * self.sigma), physics)
         return self.metric(x3, x2)
+
+    def forward(self, *kargs, **kwargs):
+        # draw order of the reference: the R2R pair first, then the two EI recorruptions
+        return self.r2r_loss(*kargs, **kwargs) + self.ei_loss(*kargs, **kwargs)

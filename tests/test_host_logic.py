@@ -218,3 +218,24 @@ def test_unbuilt_variants_say_so():
                                                  "nearest", "reflection", False)
     with pytest.raises(ValueError):
         transforms.ScalingTransform(kind="other", antialias=False)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """training.save_training_state / get_weights keep the reference's file format (src/training.py:6-45)"""
+    import training
+    net = torch.nn.Linear(3, 2)
+    net.get_weights = net.state_dict
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 10)
+    path = tmp_path / "run" / "checkpoints" / "ckp_007.pt"
+    training.save_training_state(7, net, opt, sched, str(path))
+    state = torch.load(path)
+    assert tuple(state) == ("epoch", "params", "optimizer", "scheduler") and state["epoch"] == 7
+    assert state["optimizer"]["param_groups"][0]["lr"] == 1e-3 and "last_epoch" in state["scheduler"]
+    w = training.get_weights(str(path), "cpu")                       # a training state is reduced to its params
+    assert set(w) == {"weight", "bias"} and torch.equal(w["weight"], net.weight)
+    bare = tmp_path / "weights.pt"
+    torch.save(net.state_dict(), bare)
+    assert torch.equal(training.get_weights(str(bare), "cpu")["bias"], net.bias)
+    training.save_training_state(0, net, opt, sched, "ckp_in_cwd_test.pt")      # no directory part
+    os.remove("ckp_in_cwd_test.pt")
