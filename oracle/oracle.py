@@ -273,9 +273,21 @@ def scale_transform_antialiased(x, rate, center):
     center = _c(center, x.dtype).reshape(B, 2)
     if len(set(float(r) for r in rate)) != 1:
         raise RuntimeError("stack expects each tensor to be equal size")
-    small = _c(resize_bicubic(x, float(rate[0]), True))
-    out = np.empty_like(x)
-    getattr(lib(), f"orc_scale_transform_src_{sfx}")(_p(small), _p(out), B, Cc, small.shape[-1], S, _p(rate), _p(center))
+    return scale_transform_from(resize_bicubic(x, float(rate[0]), True), S, rate, center)
+
+
+def scale_transform_from(x_src, S, rate, center):
+    """grid_sample step of the scale transform on a source of another size: x_src (B, C, Ss, Ss) -> (B, C, S, S) with the
+    grid of an S x S image (src/transforms.py:69-82 when the anti-aliasing pre-filter has shrunk the image)"""
+    x_src = _c(x_src)
+    sfx, _ = _sfx(x_src)
+    B, Cc, Ss, Ss2 = x_src.shape
+    if Ss != Ss2:
+        raise ValueError("the scale transform is defined for square images only")
+    rate = _c(rate, x_src.dtype).reshape(B)
+    center = _c(center, x_src.dtype).reshape(B, 2)
+    out = np.empty((B, Cc, S, S), dtype=x_src.dtype)
+    getattr(lib(), f"orc_scale_transform_src_{sfx}")(_p(x_src), _p(out), B, Cc, Ss, S, _p(rate), _p(center))
     return out
 
 
