@@ -239,3 +239,34 @@ def test_checkpoint_round_trip(tmp_path):
     assert torch.equal(training.get_weights(str(bare), "cpu")["bias"], net.bias)
     training.save_training_state(0, net, opt, sched, "ckp_in_cwd_test.pt")      # no directory part
     os.remove("ckp_in_cwd_test.pt")
+
+
+def test_adam_host_logic():
+    """sei_b200.optim.Adam: torch's constructor arguments and state-dict layout, no CPU fallback, unsupported options raise,
+    and every optimizer step of any optimizer advances the epoch that keys the low-precision weight copies"""
+    from sei_b200 import optim
+    w = torch.nn.Parameter(torch.zeros(4, 3))
+    with pytest.raises(NotImplementedError):
+        optim.Adam([w], weight_decay=0.1)
+    with pytest.raises(NotImplementedError):
+        optim.Adam([w], amsgrad=True)
+    opt = optim.Adam([w], lr=5e-4, betas=(0.9, 0.99))
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(4, 3))], lr=5e-4, betas=(0.9, 0.99))
+    g, gr = opt.state_dict()["param_groups"][0], ref.state_dict()["param_groups"][0]
+    assert (g["lr"], tuple(g["betas"]), g["eps"], g["params"]) == (gr["lr"], tuple(gr["betas"]), gr["eps"], gr["params"])
+    opt.step()                                        # nothing has a gradient: a no-op like torch's
+    assert not opt.state_dict()["state"]
+    w.grad = torch.ones_like(w)
+    with pytest.raises(sei_b200.SeiError, match="no CPU fallback"):
+        opt.step()
+    assert set(opt.state[w]) == {"step", "exp_avg", "exp_avg_sq"}         # torch.optim.Adam's per-parameter state
+    # the cache key of bf16 weight copies: advanced by ANY optimizer's step; None only while this Adam maintains the copy
+    before = optim.shadow_epoch(w)
+    ref.param_groups[0]["params"][0].grad = torch.ones(4, 3)
+    ref.step()
+    assert optim.shadow_epoch(w) == before + 1
+    w._sei_maintained = True
+    assert optim.shadow_epoch(w) is None
+    other = torch.optim.SGD([w], lr=0.1)
+    other.step()                                      # a foreign optimizer touched w: the maintained flag is dropped
+    assert optim.shadow_epoch(w) is not None
