@@ -13,8 +13,11 @@ losses.get_loss, models.get_model).  --network cnn (default) drives the referenc
 parameters) with every dense contraction on the tcgen05 GEMM; --network standin swaps in a 4-parameter
 pointwise network so that the line isolates the operator + loss-assembly path.
 
-Prints ONE JSON line (rank 0).  --impl reference times the CPU restatement of the same step
-(oracle/, the reference is pure Python and cannot travel to the GPU box) on the host cores.
+Prints ONE JSON line (rank 0).  --impl reference times the same step on the host cores: the reference's OWN
+modules (physics, losses, transforms, models/convolutional.py, staged unmodified under the git-ignored
+baseline/_ref/ by __graft_entry__.build(); deepinv is replaced by tests/golden/deepinv_shim) when that copy is
+present (cpu_baseline.kind = "reference"), else the oracle/ C restatement (kind = "port").  Each of its K + W steps
+is a bounded sample of the workload (a smaller batch of the same 256x256 crops) so that the run ends within minutes.
 """
 import argparse
 import json
@@ -26,15 +29,26 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "scale-equivariant-imaging_b200")
-for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+REF_SRC = os.path.join(ROOT, "baseline", "_ref", "src")
+SHIM = os.path.join(ROOT, "tests", "golden", "deepinv_shim")
+
+
+def _path(*dirs):
+    for p in dirs:
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+# the B200 arm imports the package's mirrors (physics, losses, ...); the reference arm imports the reference's own
+# modules of the same names from baseline/_ref/src, so the two never share a process (see run_reference_subprocess)
+_path(ROOT, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 BATCH, SIZE, CH = 32, 256, 3
 KERNEL, NOISE_LEVEL, MARGIN = "Gaussian_R2", 5, 6
+METRIC = "SEI training imgs/sec @256x256 (proposed step)"
 WORKLOAD = f"deblurring {KERNEL} method=proposed, synthetic {SIZE}x{SIZE} RGB crops, batch {BATCH} per GPU (BASELINE configs[1])"
 
 
@@ -128,8 +142,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_config(args, world):
+    """`config` of the JSON line; the reference arm prints the B200 arm's config verbatim (same workload, same network)"""
+    return {"workload": WORKLOAD.replace("batch 32", f"batch {args.batch}"),
+            "network": network_description(args), "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "l2": "inputs rotate over 8 resident batches (2 x 8 x 25 MB > 126 MB L2)"}
+
+
 # ----------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
+    _path(PKG)
     import torch.distributed as dist
     import losses
     import physics
@@ -140,7 +162,7 @@ def run_b200(args):
     from sei_b200 import parallel
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sei_b200 hot path has no CPU fallback "
-                         "(use --impl reference for the CPU restatement)")
+                         "(use --impl reference for the CPU arm)")
     rank, world, local_rank = parallel.init_distributed(backend="nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -171,26 +193,29 @@ def run_b200(args):
     host_y = [y.cpu().pin_memory() for y in ys[:2]]
     x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
     loss_static = torch.zeros((), device=dev)
-    allreduce_grads = parallel.GradAllReducer(params)      # one bucketed NCCL all-reduce (average) per step
+    reducer = parallel.GradAllReducer(params)      # bucketed NCCL all-reduce (average), overlapped with the backward pass
 
     def fwd_bwd():
         opt.zero_grad(set_to_none=False)
         loss = loss_fn(x=x_static, y=y_static, model=model)
+        reducer.arm()
         loss.backward()
+        reducer.finish()
         loss_static.copy_(loss.detach())
 
-    # capture forward+backward and the optimizer step as CUDA graphs (the step is ~40 small launches)
+    # capture forward+backward (+ the gradient all-reduce) and the optimizer step as ONE CUDA graph
     use_graph = not args.no_graph
-    g_fb = g_opt = None
+    g_step = None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    launches_per_step = 0
+    launches_per_step, flops_per_step = 0, 0.0
     with torch.cuda.stream(side):
         x_static.copy_(xs[0]); y_static.copy_(ys[0])
         for _ in range(3):
-            n_before = sei_b200.launch_count()
-            fwd_bwd(); allreduce_grads(); opt.step()
+            n_before, f_before = sei_b200.launch_count(), ops.flop_count()
+            fwd_bwd(); opt.step()
             launches_per_step = sei_b200.launch_count() - n_before
+            flops_per_step = ops.flop_count() - f_before
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     import gc
@@ -200,33 +225,31 @@ def run_b200(args):
           f"peak {torch.cuda.max_memory_allocated(dev) / 2 ** 30:.1f} GiB", file=sys.stderr)
     if use_graph:
         try:
-            g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fb, stream=side):
-                fwd_bwd()
-            with torch.cuda.graph(g_opt, stream=side):
-                opt.step()
+            g_step = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_step, stream=side):
+                fwd_bwd(); opt.step()
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {str(e)[:200]}); running eagerly", file=sys.stderr)
-            g_fb = g_opt = None
+            g_step = None
             torch.cuda.synchronize()
             gc.collect()
             torch.cuda.empty_cache()
 
     torch.cuda.synchronize()
 
+    def one_step():
+        if g_step is not None:
+            g_step.replay()
+        else:
+            fwd_bwd(); opt.step()
+
     def step_resident(i):
         x_static.copy_(xs[i % NBUF]); y_static.copy_(ys[i % NBUF])
-        if g_fb is not None:
-            g_fb.replay(); allreduce_grads(); g_opt.replay()
-        else:
-            fwd_bwd(); allreduce_grads(); opt.step()
+        one_step()
 
     def step_e2e(i):
         x_static.copy_(host_x[i % 2], non_blocking=True); y_static.copy_(host_y[i % 2], non_blocking=True)
-        if g_fb is not None:
-            g_fb.replay(); allreduce_grads(); g_opt.replay()
-        else:
-            fwd_bwd(); allreduce_grads(); opt.step()
+        one_step()
         return float(loss_static.item())       # device -> host read of the step's result
 
     def barrier():
@@ -280,11 +303,11 @@ def run_b200(args):
         achieved = alg_bytes / (us * 1e-6) / 1e9
         roofline_ops = {"kernel": "blur_band_kernel<13> (circular Gaussian_R2 blur, A / A^T)", "bound": "hbm",
                         "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": round(achieved / peaks["hbm"], 4), "traffic": 151.0e6,
+                        "frac": round(achieved / peaks["hbm"], 4), "traffic": None,
                         "peak_source": peaks["src"], "us_per_launch": round(us, 2),
                         "algorithmic_bytes_per_launch": alg_bytes,
                         "how": f"{reps} back-to-back launches on 128x{CH}x{SIZE}x{SIZE} fp32, 3 rotating inputs (400 MB > L2); "
-                               "traffic = dram bytes of one launch from ncu --set full (profiles/)"}
+                               "traffic: not measured in this run (ncu --set full captures of this kernel are under profiles/)"}
         del big
         roofline = roofline_ops
         if args.network == "cnn":
@@ -304,17 +327,23 @@ def run_b200(args):
             us = e0.elapsed_time(e1) * 1e3 / reps
             flops = 2.0 * T * dim * 4 * dim
             tf = flops / (us * 1e-6) / 1e12
+            step_tf = flops_per_step / (ms_step * 1e-3) / 1e12
+            # the kernel is timed alone (10 launches, ~30 ms): the burst cuBLAS figure is its denominator; the whole
+            # step (seconds under the power cap) is compared with the sustained figure
             roofline = {"kernel": f"{sei_b200.last_kernel()} (tcgen05 cta_group::2; deepest ConvBlock conv2: {T}x{dim} @ ({4 * dim}x{dim})^T)",
-                        "bound": "tensor", "achieved": round(tf, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": round(tf / peaks["tf_sustained"], 4), "frac_of_burst_peak": round(tf / peaks["tf_burst"], 4),
-                        "traffic": None, "peak_source": peaks["src"] + ", sustained cuBLAS bf16 figure",
+                        "bound": "tensor", "achieved": round(tf, 1), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                        "frac": round(tf / peaks["tf_burst"], 4), "frac_of_sustained_peak": round(tf / peaks["tf_sustained"], 4),
+                        "traffic": None, "peak_source": peaks["src"] + ", burst cuBLAS bf16 figure (kernel timed alone)",
                         "us_per_launch": round(us, 1), "algorithmic_flops_per_launch": flops,
-                        "how": f"{reps} back-to-back launches, CUDA events"}
+                        "step_tensor_flops": flops_per_step, "step_tflops": round(step_tf, 1),
+                        "step_frac_of_sustained_peak": round(step_tf / peaks["tf_sustained"], 4),
+                        "how": f"{reps} back-to-back launches, CUDA events; step_*: tensor-core flops of every GEMM launched in one "
+                               "step (counted by sei_b200.ops) / the timed step"}
             del a_, w_
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_reference_sample(args, seconds_budget=25.0)
+        cpu_baseline = run_reference_subprocess(args, seconds_budget=25.0)
 
     if world > 1:
         dist.barrier()
@@ -323,15 +352,12 @@ def run_b200(args):
         return
     imgs = BATCH * world
     out = {
-        "metric": "SEI training imgs/sec @256x256 (proposed step)", "value": round(imgs / (ms_step * 1e-3), 2),
+        "metric": METRIC, "value": round(imgs / (ms_step * 1e-3), 2),
         "unit": "imgs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 network (fp32 accumulate), f32 operators" if args.network == "cnn" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.replace(f"batch 32", f"batch {BATCH}"),
-                   "network": network_description(args), "n_params": n_params,
-                   "global_batch": imgs, "parallelism": f"dp{world}", "cuda_graph": g_fb is not None,
-                   "l2": f"inputs rotate over {NBUF} resident batches ({2 * NBUF * 25} MB > 126 MB L2)",
-                   "final_loss": final_loss},
+        "config": bench_config(args, world),
+        "n_params": n_params, "cuda_graph": g_step is not None, "final_loss": final_loss,
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "imgs/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": int(2 * xs[0].numel() * 4), "d2h_bytes_per_step": 4,
                 "how": "losses.get_loss(...)(x, y, model) + backward + Adam from pinned host x,y; loss.item() each step"},
@@ -343,26 +369,78 @@ def run_b200(args):
     print(json.dumps(out))
 
 
-# ----------------------------------------------------------------------------------------- CPU restatement arm
+# ----------------------------------------------------------------------------------------- CPU arm
+def reference_step_own(args, batch):
+    """One `proposed` training step by the REFERENCE'S OWN CODE on the host (fp32, PyTorch CPU): get_physics,
+    get_loss and ConvolutionalModel are the unmodified modules staged under baseline/_ref/src (demo/train.py:79-186,
+    258-270: zero_grad, loss(x=, y=, model=), backward, Adam step, loss.item())."""
+    _path(SHIM, REF_SRC)
+    import importlib.util
+    import physics as ref_physics
+    import losses as ref_losses
+    assert os.path.abspath(ref_physics.__file__).startswith(REF_SRC), ref_physics.__file__
+    largs = loss_args()
+    dev = "cpu"
+    phys = ref_physics.get_physics(largs, device=dev)
+    loss_fn = ref_losses.get_loss(args=largs, physics=phys)
+    if args.network == "cnn":
+        # src/models/__init__.py imports deepinv.models / bm3d (not installed): the CNN's own file is loaded by path
+        spec = importlib.util.spec_from_file_location("ref_convolutional", os.path.join(REF_SRC, "models", "convolutional.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        torch.manual_seed(0)
+        # the constructor arguments src/models/__init__.py:76-86 passes for task=deblurring
+        net = mod.ConvolutionalModel(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+                                     hidden_channels=args.cnn_hidden, inout_convs=True, scales=args.cnn_scales)
+    else:
+        from toy_model import ToyModel
+        net = ToyModel(rate=1)
+
+    class Wrapped(torch.nn.Module):          # Model.forward(x, *args) of src/models/__init__.py:148-149
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, *a):
+            return self.m(x)
+
+    model = Wrapped(net)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    torch.manual_seed(1)
+    x = torch.rand(batch, CH, SIZE, SIZE)
+    with torch.no_grad():
+        y = phys(x)
+
+    def step():
+        opt.zero_grad()
+        loss = loss_fn(x=x, y=y, model=model)
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+
+    return step, "reference"
+
+
 def cpu_network(args):
-    """The network of the step on the CPU in fp32: the same module tree with its contractions as plain torch
-    matmuls (what the reference's nn.Conv2d does on the host), or the stand-in network."""
+    """The network of the port's step on the CPU in fp32: this package's module tree with its contractions as plain
+    torch matmuls, or the stand-in network.  Only used when baseline/_ref/ is absent."""
     if args.network != "cnn":
         from toy_model import ToyModel
         return ToyModel(rate=1)
+    _path(PKG)
     import models
     import models.convolutional as mc
-    mc.COMPUTE_DTYPE = torch.float32
-    mc._gemm_tn = lambda a, b, bias, out_dtype: (a @ b.t() + (bias if bias is not None else 0)).to(out_dtype)
-    mc._gemm_atb = lambda a, b: (a.t() @ b).float()
+    import torch_formulation                 # tests/torch_formulation.py: fp32 library formulation of the operator hooks
+    torch_formulation.install(mc)
     torch.manual_seed(0)
     return models.get_model(model_args(args.cnn_hidden, args.cnn_scales), physics=None, device="cpu")
 
 
-def reference_step_factory(args, batch):
+def reference_step_port(args, batch):
     """One `proposed` training step on the host: physics, transform and loss reductions by the C oracle (OpenMP),
     the network and its backward by PyTorch on the CPU (as in the reference), Adam on the parameters."""
     from oracle import oracle as orc
+    orc.set_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(0)
     kern = orc.named_kernel(KERNEL)
     phys = orc.OraclePhysics("deblurring", kernel=kern, sigma=float(np.float32(NOISE_LEVEL / 255)))
@@ -401,43 +479,69 @@ def reference_step_factory(args, batch):
         opt.step()
         return loss
 
-    return step
+    return step, "port"
 
 
-def run_reference_sample(args, seconds_budget=25.0, batch=None, steps=None, warmup=1):
-    """Time the CPU restatement of the step on a bounded sample, using every host core."""
-    from oracle import oracle as orc
+def run_reference_sample(args, seconds_budget, steps, warmup):
+    """Time `warmup` + `steps` steps of the CPU arm, each on a bounded sample of the workload (a batch of `b` of the
+    same 256x256 crops, b chosen from a one-crop probe so that the whole run fits `seconds_budget`), every host core."""
     cores = os.cpu_count() or 1
-    orc.set_threads(cores)               # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
-    torch.set_num_threads(cores)
-    batch = batch or (1 if args.network == "cnn" else 8)
-    step = reference_step_factory(args, batch)
-    t0 = time.perf_counter()
+    torch.set_num_threads(cores)         # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
+    own = os.path.isdir(REF_SRC) and not args.force_port
+    factory = reference_step_own if own else reference_step_port
+    n_total = steps + warmup
+    batch = args.ref_batch
+    probe_s = None
+    if not batch:
+        step, kind = factory(args, 1)
+        step()                           # first call pays allocator / thread-pool start-up
+        t0 = time.perf_counter()
+        step()
+        probe_s = time.perf_counter() - t0
+        batch = int(max(1, min(args.batch, seconds_budget / max(n_total, 1) / max(probe_s, 1e-3))))
+        del step
+    step, kind = factory(args, batch)
     for _ in range(warmup):
         step()
-    one = (time.perf_counter() - t0) / max(warmup, 1)
-    n = steps or max(1, min(10, int(seconds_budget / max(one, 1e-3))))
     t0 = time.perf_counter()
-    for _ in range(n):
+    for _ in range(steps):
         step()
-    dt = (time.perf_counter() - t0) / n
-    return {"value": round(batch / dt, 4), "unit": "imgs/s", "cores": cores, "kind": "port",
-            "sample": f"{n} step(s) of the same proposed step on a batch of {batch} {SIZE}x{SIZE} RGB crop(s): operators and "
-                      f"loss by the oracle/ C restatement (OpenMP {cores} threads), network fwd/bwd + Adam by PyTorch CPU fp32 "
-                      f"({cores} threads), {dt * 1e3:.1f} ms/step",
-            "ms_per_step": round(dt * 1e3, 2), "batch": batch}
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    what = ("the reference's own physics / losses / transforms / ConvolutionalModel (baseline/_ref/src, deepinv names from "
+            "tests/golden/deepinv_shim), PyTorch CPU fp32, torch.optim.Adam" if kind == "reference" else
+            "operators and loss by the oracle/ C restatement (OpenMP), network fwd/bwd + Adam by PyTorch CPU fp32")
+    return {"value": round(batch / dt, 4), "unit": "imgs/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} timed + {warmup} warm-up step(s) of the same proposed step, each on a batch of {batch} of the "
+                      f"workload's {SIZE}x{SIZE} RGB crops (of {args.batch} per GPU step): {what}, {cores} threads, "
+                      f"{dt * 1e3:.1f} ms/step" + (f"; one-crop probe {probe_s * 1e3:.0f} ms" if probe_s else ""),
+            "ms_per_step": round(dt * 1e3, 2), "batch": batch, "steps": steps, "warmup": warmup}
+
+
+def run_reference_subprocess(args, seconds_budget):
+    """cpu_baseline leg of the B200 arm: the CPU arm in a process of its own (it imports the reference's modules, whose
+    names -- physics, losses, transforms -- are those of this package's mirrors already imported here)"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--network", args.network, "--cnn-hidden", str(args.cnn_hidden), "--cnn-scales", str(args.cnn_scales),
+           "--batch", str(args.batch), "--ref-budget-s", str(seconds_budget)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "imgs/s", "cores": os.cpu_count(), "kind": "unavailable",
+                "sample": f"CPU arm failed: {type(e).__name__}: {str(e)[:200]}"}
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    base = run_reference_sample(args, steps=min(args.steps, 3 if args.network == "cnn" else 10), warmup=1)
-    out = {"impl": "reference", "metric": "SEI training imgs/sec @256x256 (proposed step)", "value": base["value"],
+    base = run_reference_sample(args, seconds_budget=args.ref_budget_s, steps=args.steps, warmup=args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"],
            "unit": "imgs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "network": network_description(args).split(";")[0] + " (fp32 on the host)",
-                      "global_batch": base["batch"], "parallelism": "cpu"},
+           "config": bench_config(args, args.gpus),
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -456,6 +560,10 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: wall-clock budget of the whole K + W step run (sizes the per-step sample)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: crops per step (0 = from the budget)")
+    ap.add_argument("--force-port", action="store_true", help="--impl reference: use the oracle port even if baseline/_ref exists")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -363,6 +363,37 @@ class OraclePhysics:
         return down_aa_vjp(gy, self.rate, in_hw)
 
 
+def conjugate_gradient(op, b, max_iter, tol):
+    """deepinv.optim.utils.conjugate_gradient (v0.2.0; un-vendored dependency, restated in
+    tests/golden/deepinv_shim/deepinv/physics/forward.py): CG from x0 = 0 in b's dtype, stop once |r| < tol."""
+    x = np.zeros_like(b)
+    r = b
+    p = r
+    rsold = (r * r).sum(dtype=b.dtype)
+    for _ in range(int(max_iter)):
+        Ap = op(p)
+        alpha = rsold / (p * Ap).sum(dtype=b.dtype)
+        x = x + p * alpha
+        r = r + Ap * (-alpha)
+        rsnew = (r * r).sum(dtype=b.dtype)
+        if np.sqrt(rsnew) < tol:
+            break
+        p = r + p * (rsnew / rsold)
+        rsold = rsnew
+    return x
+
+
+def a_dagger(A, At, y, max_iter=50, tol=1e-3):
+    """deepinv LinearPhysics.A_dagger (call sites: reference demo/test.py:122, src/models/__init__.py:28): normal
+    equations A^T A x = A^T y when A^T y is smaller than y, else A A^T z = y and x = A^T z.  `At` is the physics
+    object's A_adjoint -- for the reference's default SR operator the plain bicubic upsample, not the transpose
+    (src/physics/downsampling/__init__.py:21-35)."""
+    Aty = At(y)
+    if Aty.size < y.size:
+        return conjugate_gradient(lambda v: At(A(v)), Aty, max_iter, tol)
+    return At(conjugate_gradient(lambda v: A(At(v)), y, max_iter, tol))
+
+
 def proposed_loss(physics, model, y, draws, margin, cropped_div=True, averaged_cst=None,
                   alpha=1.0, tau=1e-2, sure_sigma=5 / 255, kind="padded", antialias=False):
     """ProposedLoss.forward for transforms="Scaling_Transforms", stop_gradient=True.

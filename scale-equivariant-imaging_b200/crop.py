@@ -10,6 +10,8 @@ import torch
 import torch.nn.functional as F
 from torch.nn import Module
 
+from sei_b200 import draws
+
 
 class MinSizePadding(Module):
     def __init__(self, size, padding_mode="constant", fill=0):
@@ -43,8 +45,8 @@ class CropPair(Module):
         h, w = y.shape[-2:]
         if self.location == "random":
             # two draws from the CPU generator, rows first (reference :26-27)
-            i = torch.randint(0, h - self.size + 1, size=(1,)).item()
-            j = torch.randint(0, w - self.size + 1, size=(1,)).item()
+            i = draws.randint(0, h - self.size + 1)
+            j = draws.randint(0, w - self.size + 1)
         else:
             i = (h - self.size) // 2
             j = (w - self.size) // 2

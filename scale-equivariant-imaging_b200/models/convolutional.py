@@ -12,15 +12,21 @@ unchanged.  What differs is where the arithmetic runs:
   * the FFT "ideal" resamplers (including the reference's quirks: fftshift applied to the half-spectrum axis,
     ifftshift results discarded) are applied as the explicit linear operators they are, by two batched
     tensor-core products per call (models/resample.py, csrc/bgemm.cu) -- no cuFFT, no layout copies;
-  * depthwise 7x7, channel LayerNorm and GELU stay PyTorch library code.
-"""
-from math import ceil
+  * depthwise 7x7, channel LayerNorm, GELU and the output 3x3 convolution are hand-written kernels as well
+    (csrc/cnn_elem.cu).
 
+There is no library fallback: a CPU tensor, a dtype other than bf16 activations or a missing libsei_b200.so raises
+SeiError.  Channel counts the vectorised kernels do not take (3-channel layers of the SR / no-in-out-conv variants) are
+zero-padded to a multiple of 8 around the same kernels.  The unit tests that check the module tree against the
+reference at fp32 accuracy on the CPU install their own PyTorch formulation of the five operator hooks below
+(tests/torch_formulation.py); nothing in this package does.
+"""
 import torch
 import torch.nn.functional as F
 from torch.nn import Conv2d, GELU, LayerNorm as BaseLayerNorm, Module, ModuleList, Sequential
 
 from sei_b200 import ops
+from sei_b200._lib import SeiError
 from sei_b200.optim import shadow_epoch
 from . import resample
 
@@ -28,6 +34,7 @@ CL = torch.channels_last
 # activation / GEMM operand dtype.  bf16 is the only dtype the tcgen05 kernel takes; the unit tests set this to
 # float32 together with a patched _gemm_tn to check the network's structure against the reference at fp32 accuracy.
 COMPUTE_DTYPE = torch.bfloat16
+COMMUTE_DOWNSAMPLE = True      # Downsample: resample first, then the pointwise convolution on a quarter of the pixels
 _NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"     # A/B switch for measurements
 # gelu'(h) in the epilogue of conv3's input-gradient GEMM (sei_gemm_bf16_tn_gelu_bwd).  Measured on B200: it removes the
 # 9 ms GELU-backward pass but the four epilogue warps then spend longer on the erf arithmetic than the tensor cores
@@ -44,6 +51,80 @@ def _gemm_atb(a, b, out=None):
     """D (fp32) = a^T @ b with both operands read in place (sei_gemm_bf16_atb, MN-major UMMA operands); with `out`
     the product is accumulated into it"""
     return ops.gemm_bf16_atb(a, b, out=out)
+
+
+def _require_device_rows(t, what):
+    if not t.is_cuda or t.dtype != torch.bfloat16:
+        raise SeiError(f"{what}: got a {t.dtype} tensor on {t.device}; the restoration CNN runs on CUDA (sm_100a) in bf16 "
+                       "only -- there is no CPU / library fallback")
+
+
+def _pad_channels(xl):
+    """(B, H, W, C) -> (B, H, W, C8) zero-padded to a multiple of 8 channels (a copy only when C % 8 != 0)"""
+    c = xl.shape[-1]
+    return xl if c % 8 == 0 else F.pad(xl, (0, 8 - c % 8))
+
+
+def _op_layer_norm(rows, ln):
+    """channel LayerNorm of rows [T, C] (ln_fwd_kernel / ln_small kernels, csrc/cnn_elem.cu)"""
+    _require_device_rows(rows, "LayerNorm")
+    if not ops.ln_any_supported(rows):
+        raise SeiError(f"LayerNorm over {rows.shape[1]} channels: the kernels take C <= 32 or C % 8 == 0 up to 8192")
+    return ops.layer_norm_cl(rows, ln.weight, ln.bias, ln.eps)
+
+
+def _op_dwconv7(xl, conv):
+    """depthwise 7x7, padding 3, on a channels-last (B, H, W, C) tensor (dwconv7_kernel)"""
+    _require_device_rows(xl, "depthwise 7x7 convolution")
+    c = xl.shape[-1]
+    if c % 8 == 0:
+        if not ops.dwconv7_supported(xl):
+            raise SeiError(f"depthwise 7x7 convolution over {c} channels is not built")
+        return ops.dwconv7(xl, conv.weight, conv.bias)
+    pad = 8 - c % 8
+    w = F.pad(conv.weight, (0, 0, 0, 0, 0, 0, 0, pad))
+    b = None if conv.bias is None else F.pad(conv.bias, (0, pad))
+    return ops.dwconv7(_pad_channels(xl).contiguous(), w, b)[..., :c]
+
+
+def _op_gelu(x):
+    """erf GELU of a dense bf16 tensor (gelu_fwd_kernel / gelu_bwd_kernel)"""
+    _require_device_rows(x, "GELU")
+    if ops.gelu_supported(x):
+        return ops.gelu(x)
+    flat = x.contiguous(memory_format=CL).permute(0, 2, 3, 1).reshape(-1)
+    n = flat.numel()
+    out = ops.gelu(F.pad(flat, (0, (-n) % 8)))[:n]
+    return out.view(x.shape[0], x.shape[2], x.shape[3], x.shape[1]).permute(0, 3, 1, 2)
+
+
+def _op_ideal_resample(x, kind, rate):
+    """IdealUpsample / IdealDownsample as batched tensor-core operator products (models/resample.py)"""
+    _require_device_rows(x, f"ideal {kind}sampler")
+    if resample.supported(x):
+        return resample.ideal_resample(x, kind, rate)
+    c = x.shape[1]
+    xl = _pad_channels(x.contiguous(memory_format=CL).permute(0, 2, 3, 1)).contiguous().permute(0, 3, 1, 2)
+    return resample.ideal_resample(xl, kind, rate)[:, :c]
+
+
+def _op_conv3x3_small(xl, conv):
+    """the output layer (hidden -> <= 4 channels, 3x3 'same'): direct kernels, or None when the shape is not theirs"""
+    if ops.conv3x3_small_supported(xl, conv.out_channels):
+        return ops.conv3x3_small(xl, conv.weight, conv.bias)
+    return None
+
+
+def _op_bias_pattern(out, rows, pat, bias):
+    """out[b, c, i, j] += pat[i, j] * bias[c] on the rows view of a channels-last GEMM output (bias_pattern_add_kernel)"""
+    _require_device_rows(rows, "Downsample bias")
+    c = rows.shape[1]
+    if c % 8 != 0:                                   # edge layers of the no-in/out-conv variant: pad the columns
+        rows, bias = _pad_k(rows), F.pad(bias, (0, 8 - c % 8))
+    if not ops.ln_cl_supported(rows):
+        raise SeiError(f"Downsample bias over {c} channels: the kernel does not tile this width")
+    rows = ops.bias_pattern_add(rows, pat.reshape(-1), bias)[:, :c]
+    return rows.reshape(out.shape[0], out.shape[2], out.shape[3], c).permute(0, 3, 1, 2)
 
 
 class _GemmTN(torch.autograd.Function):
@@ -82,7 +163,7 @@ class _GemmTN(torch.autograd.Function):
                 gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             # one pass, fp32 accumulation, fixed order (csrc/cnn_elem.cu); library reduction for odd channel counts
-            gb = ops.colsum_bf16(gy) if ops.ln_cl_supported(gy) else torch.sum(gy, 0, dtype=torch.float32)
+            gb = _colsum(gy)
         return gx, gw, gb, None, None, None
 
 
@@ -115,8 +196,19 @@ class _GeluGemmTN(torch.autograd.Function):
             else:
                 gw = _gemm_atb(gy, a)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.colsum_bf16(gy) if ops.ln_cl_supported(gy) else torch.sum(gy, 0, dtype=torch.float32)
+            gb = _colsum(gy)
         return gh, gw, gb, None, None, None
+
+
+def _colsum(gy):
+    """fp32 column sums of a bf16 [T, N] matrix (bias gradient): colsum_kernel, one pass, fixed order; columns padded to
+    a multiple of 8 for the 3-channel edge layers"""
+    n = gy.shape[1]
+    _require_device_rows(gy, "bias gradient")
+    g8 = _pad_k(gy)
+    if not ops.ln_cl_supported(g8):
+        raise SeiError(f"bias gradient over {n} channels: the column-sum kernel does not tile this width")
+    return ops.colsum_bf16(g8)[:n]
 
 
 def _pad_k(a):
@@ -185,11 +277,11 @@ class _GemmConv2d(Conv2d):
     def forward(self, x, use_bias=True):
         B, C, H, W = x.shape
         xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)      # (B, H, W, C) view
-        if self.kernel_size == (3, 3) and ops.conv3x3_small_supported(xl, self.out_channels):
-            # the network's output layer (hidden -> 3 channels): direct kernel, no unfolded copy (csrc/cnn_elem.cu)
-            out = ops.conv3x3_small(xl, self.weight, self.bias)
-            return out[..., : self.out_channels].permute(0, 3, 1, 2)
         if self.kernel_size == (3, 3):
+            # the network's output layer (hidden -> 3 channels): direct kernel, no unfolded copy (csrc/cnn_elem.cu)
+            out = _op_conv3x3_small(xl, self)
+            if out is not None:
+                return out[..., : self.out_channels].permute(0, 3, 1, 2)
             xl = _unfold3x3(xl)
         x2 = xl.reshape(B * H * W, xl.shape[-1])
         w2, w_bf16 = self._weight_matrix()
@@ -223,32 +315,8 @@ class LayerNorm(Module):
     def forward(self, x):
         xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)                   # channels last: a view
         rows = xl.reshape(-1, xl.shape[-1])
-        if ops.ln_any_supported(rows):                                            # hand-written kernels (csrc/cnn_elem.cu)
-            out = ops.layer_norm_cl(rows, self.ln.weight, self.ln.bias, self.ln.eps).view(xl.shape)
-            return out.permute(0, 3, 1, 2)
-        out = F.layer_norm(xl, self.ln.normalized_shape, self.ln.weight.to(xl.dtype), self.ln.bias.to(xl.dtype),
-                           self.ln.eps)
+        out = _op_layer_norm(rows, self.ln).view(xl.shape)                        # hand-written kernels (csrc/cnn_elem.cu)
         return out.permute(0, 3, 1, 2)
-
-
-class _DepthwiseConv7(torch.autograd.Function):
-    """depthwise 7x7, padding 3 (reference ConvBlock.conv1 :36-38) through the library convolution.  The input
-    gradient is the same convolution with the taps flipped; asking the library for it that way uses its fast
-    channels-last FORWARD kernel (the profile showed its depthwise dgrad kernel 5x slower than its forward)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        return F.conv2d(x, w, b, padding=3, groups=x.shape[1])
-
-    @staticmethod
-    def backward(ctx, g):
-        x, w = ctx.saved_tensors
-        C = x.shape[1]
-        gx = F.conv2d(g, w.flip(2, 3), None, padding=3, groups=C) if ctx.needs_input_grad[0] else None
-        _, gw, gb = torch.ops.aten.convolution_backward(g, x, w, [C], [1, 1], [3, 3], [1, 1], False, [0, 0], C,
-                                                        [False, True, True])
-        return gx, gw, gb
 
 
 class ConvBlock(Module):
@@ -261,17 +329,14 @@ class ConvBlock(Module):
         self.conv3 = _conv(4 * dim, dim, 1)
 
     def forward(self, x):
-        xl = x.permute(0, 2, 3, 1)
-        if ops.dwconv7_supported(xl):                     # hand-written channels-last kernels (csrc/cnn_elem.cu)
-            x1 = ops.dwconv7(xl, self.conv1.weight, self.conv1.bias).permute(0, 3, 1, 2)
-        else:
-            x1 = _DepthwiseConv7.apply(x, self.conv1.weight.to(x.dtype), self.conv1.bias.to(x.dtype))
+        xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)
+        x1 = _op_dwconv7(xl, self.conv1).permute(0, 3, 1, 2)      # hand-written channels-last kernels (csrc/cnn_elem.cu)
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
         if self.conv3.gelu_fusable(x1):
             x1 = self.conv3.forward_after_gelu(x1)            # gelu + conv3, gelu' fused into conv3's dgrad epilogue
         else:
-            x1 = ops.gelu(x1) if ops.gelu_supported(x1) else self.gelu(x1)
+            x1 = _op_gelu(x1)
             x1 = self.conv3(x1)
         return x + x1
 
@@ -284,20 +349,7 @@ class IdealUpsample(Module):
         self.rate = rate
 
     def forward(self, x):
-        if resample.supported(x):       # bf16 channels-last on the GPU: two batched tensor-core products (bgemm.cu)
-            return resample.ideal_resample(x, "up", self.rate)
-        dtype = x.dtype
-        r = self.rate
-        s = (x.shape[-2], x.shape[-1])
-        X = torch.fft.fftshift(torch.fft.rfft2(x.float(), dim=(-2, -1)), dim=(-2, -1))
-        hs, ws = X.shape[-2], X.shape[-1]
-        X2 = torch.zeros((X.shape[0], X.shape[1], hs * r, ws * r), device=X.device, dtype=X.dtype)
-        mv, mh = (hs * (r - 1)) // 2, (ws * (r - 1)) // 2
-        mt, mb = (mv + 1, mv) if hs % 2 == 1 else (mv, mv)
-        ml, mr = (mh + 1, mh) if ws % 2 == 1 else (mh, mh)
-        X2[:, :, mt:-mb, ml:-mr] = X
-        out = torch.fft.irfft2(X2, dim=(-2, -1), s=(s[0] * r, s[1] * r))
-        return out.to(dtype)
+        return _op_ideal_resample(x, "up", self.rate)      # two batched tensor-core products (bgemm.cu), no cuFFT
 
 
 class Upsample(Module):
@@ -323,17 +375,7 @@ class IdealDownsample(Module):
         self.rate = rate
 
     def forward(self, x):
-        if resample.supported(x):
-            return resample.ideal_resample(x, "down", self.rate)
-        dtype = x.dtype
-        s = (x.shape[-2], x.shape[-1])
-        X = torch.fft.fftshift(torch.fft.rfft2(x.float(), dim=(-2, -1)), dim=(-2, -1))
-        hcsh = ceil(X.shape[-2] / (2 * self.rate))
-        hcsw = ceil(X.shape[-1] / (2 * self.rate))
-        otf = torch.zeros_like(X)
-        otf[:, :, hcsh:-hcsh, hcsw:-hcsw] = 1
-        out = torch.fft.irfft2(otf * X, dim=(-2, -1), s=s)
-        return out[:, :, :: self.rate, :: self.rate].to(dtype)
+        return _op_ideal_resample(x, "down", self.rate)
 
 
 class Downsample(Module):
@@ -348,7 +390,7 @@ class Downsample(Module):
 
     def forward(self, x):
         x = self.ln(x)
-        if resample.supported(x) and self.conv.kernel_size == (1, 1):
+        if self.conv.kernel_size == (1, 1) and COMMUTE_DOWNSAMPLE:
             # The pointwise convolution (channels) and the ideal resampler (space) are linear maps on different axes,
             # so they commute: resample the C-channel tensor first, then convolve a quarter of the pixels (4x fewer
             # resampler bytes and GEMM flops than conv -> resample).  The bias is a constant image per channel; the
@@ -358,12 +400,7 @@ class Downsample(Module):
             if self.conv.bias is not None:
                 pat = resample.constant_response("down", H, W, self.rate, x.device)                 # (Ho, Wo) fp32
                 rows = out.permute(0, 2, 3, 1).reshape(-1, out.shape[1])                            # view of the GEMM output
-                if ops.ln_cl_supported(rows):
-                    rows = ops.bias_pattern_add(rows, pat.reshape(-1), self.conv.bias)
-                    out = rows.view(out.shape[0], out.shape[2], out.shape[3], out.shape[1]).permute(0, 3, 1, 2)
-                else:
-                    bias_img = (pat[:, :, None] * self.conv.bias[None, None, :]).to(out.dtype)      # (Ho, Wo, C_out)
-                    out = out + bias_img.permute(2, 0, 1)[None]
+                out = _op_bias_pattern(out, rows, pat, self.conv.bias)
             return out
         return self.ideal_downsample(self.conv(x))
 

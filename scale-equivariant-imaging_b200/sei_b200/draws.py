@@ -54,3 +54,10 @@ def randperm(n):
     if _queue is not None:
         return _next((n,), "cpu", torch.int64)
     return torch.randperm(n)
+
+
+def randint(low, high):
+    """torch.randint(low, high, size=(1,)).item() on the CPU generator (CropPair's offsets, reference src/crop.py:26-27)"""
+    if _queue is not None:
+        return int(_next((1,), "cpu", torch.int64).item())
+    return int(torch.randint(low, high, size=(1,)).item())

@@ -58,24 +58,41 @@ class LinearPhysics(nn.Module):
         return ops._AddNoise.apply(self.A(x), noise, self.noise_model.sigma_value())
 
     def A_dagger(self, y):
-        """argmin_x |A x - y|^2 by conjugate gradient on A^T A x = A^T y."""
-        b = self.A_adjoint(y)
-        x = torch.zeros_like(b)
-        r = b.clone()
-        p = r
-        rs = (r * r).flatten().sum()
-        tol2 = self.tol ** 2
-        for _ in range(int(self.max_iter)):
-            Ap = self.A_adjoint(self.A(p))
-            alpha = rs / (p * Ap).flatten().sum()
-            x = x + p * alpha
-            r = r + Ap * (-alpha)
-            rs_new = (r * r).flatten().sum()
-            if rs_new < tol2:
-                break
-            p = r + p * (rs_new / rs)
-            rs = rs_new
+        """Least-squares pseudo-inverse by conjugate gradient, following deepinv v0.2.0 (restated in
+        tests/golden/deepinv_shim/deepinv/physics/forward.py; upstream is not vendored): when A^T y has fewer
+        elements than y solve A^T A x = A^T y, otherwise (deblurring, super-resolution) solve A A^T z = y and return
+        A^T z.  With the reference's default non-adjoint `A_adjoint` of the SR operator (plain bicubic upsample) the
+        two are different systems, so the branch matters.  The operators run in libsei_b200; the CG vector updates are
+        torch (test-time path only: demo/test.py:122, src/models/__init__.py:28)."""
+        Aty = self.A_adjoint(y)
+        overcomplete = Aty.numel() < y.numel()
+        if not overcomplete:
+            op, b = (lambda v: self.A(self.A_adjoint(v))), y
+        else:
+            op, b = (lambda v: self.A_adjoint(self.A(v))), Aty
+        x = conjugate_gradient(op, b, max_iter=self.max_iter, tol=self.tol)
+        if not overcomplete:
+            x = self.A_adjoint(x)
         return x
+
+
+def conjugate_gradient(A, b, max_iter=1e2, tol=1e-5):
+    """deepinv.optim.utils.conjugate_gradient (v0.2.0): CG from x0 = 0, stops once |r| < tol"""
+    x = torch.zeros_like(b)
+    r = b
+    p = r
+    rsold = (r * r).flatten().sum()
+    for _ in range(int(max_iter)):
+        Ap = A(p)
+        alpha = rsold / (p * Ap).flatten().sum()
+        x = x + p * alpha
+        r = r + Ap * (-alpha)
+        rsnew = (r * r).flatten().sum()
+        if rsnew.sqrt() < tol:
+            break
+        p = r + p * (rsnew / rsold)
+        rsold = rsnew
+    return x
 
 
 def adjoint_function(A, input_size, device="cpu", dtype=torch.float):

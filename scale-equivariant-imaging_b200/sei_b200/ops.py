@@ -286,6 +286,15 @@ def sure_perturb(y, draw, margin, tau):
     return out, b
 
 
+# tensor-core work issued through this module since import (2*M*N*K per product): bench.py reports the step's
+# achieved TFLOP/s from it
+_FLOPS = [0.0]
+
+
+def flop_count():
+    return _FLOPS[0]
+
+
 def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     """D[M,N] = a[M,K] @ b[N,K]^T (+ bias[N]) on the tcgen05 tensor cores; a, b bf16 row-major (last dim
     contiguous, row pitch a multiple of 8 elements); fp32 accumulation; D bf16 or fp32."""
@@ -301,6 +310,7 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     if bias is not None:
         bias = _t(bias, "bias")
     d = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
     with torch.cuda.device(a.device):
         check(_lib.load().sei_gemm_bf16_tn(_ptr(a), _ptr(b), _ptr(d), _ptr(bias), M, N, K, a.stride(0), b.stride(0), N,
                                            int(out_dtype == torch.float32), int(tile_n), _stream(a)))
@@ -318,6 +328,7 @@ def gemm_bf16_tn_gelu_bwd(a, b, h):
     if K != K2 or tuple(h.shape) != (M, N):
         raise SeiError("gemm_bf16_tn_gelu_bwd: shape mismatch")
     d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
     with torch.cuda.device(a.device):
         check(_lib.load().sei_gemm_bf16_tn_gelu_bwd(_ptr(a), _ptr(b), _ptr(d), _ptr(h), M, N, K, a.stride(0), b.stride(0), N,
                                                     h.stride(0), _stream(a)))
@@ -342,6 +353,7 @@ def gemm_bf16_atb(a, b, out=None):
     K2, N = b.shape
     if K != K2:
         raise SeiError(f"gemm_bf16_atb: contraction dimensions differ ({K} vs {K2})")
+    _FLOPS[0] += 2.0 * M * N * K
     if out is not None:
         if out.dtype != torch.float32 or tuple(out.shape) != (M, N) or not out.is_contiguous() or out.device != a.device:
             raise SeiError("gemm_bf16_atb: out must be a contiguous float32 [M, N] tensor on the operands' device")
@@ -367,6 +379,7 @@ def bgemm_bf16(A, x, out, M, K, N, tile_rows, batches, b_inner, x_b, k_inner, x_
     for t, name in ((A, "A"), (x, "x"), (out, "out")):
         if not t.is_cuda or t.dtype != torch.bfloat16:
             raise SeiError(f"bgemm_bf16: {name} must be a CUDA bf16 tensor")
+    _FLOPS[0] += 2.0 * int(M) * int(K) * int(N) * int(batches)
     with torch.cuda.device(x.device):
         check(_lib.load().sei_bgemm_bf16(_ptr(A), _ptr(x), _ptr(out), int(M), int(K), int(N), int(A.shape[1]),
                                          int(tile_rows), int(batches), int(b_inner), int(x_b[0]), int(x_b[1]),

@@ -52,6 +52,21 @@ class Adam(torch.optim.Optimizer):
             st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            return st
+        # State that came through load_state_dict: torch leaves `step` on the CPU (or as a Python number in older
+        # checkpoints) unless the group is capturable / fused, and a map_location="cpu" checkpoint leaves everything
+        # there.  The kernel dereferences these pointers on the device, so they are coerced / checked here.
+        step = st.get("step", 0.0)
+        if not (torch.is_tensor(step) and step.device == p.device and step.dtype == torch.float32 and step.dim() == 0):
+            st["step"] = torch.as_tensor(float(step), dtype=torch.float32).to(p.device)
+        for name in ("exp_avg", "exp_avg_sq"):
+            t = st.get(name)
+            if t is None:
+                raise SeiError(f"sei_b200.optim.Adam: optimizer state lacks '{name}'")
+            if t.device != p.device or t.dtype != torch.float32 or not t.is_contiguous():
+                st[name] = t.to(device=p.device, dtype=torch.float32).contiguous()
+            if st[name].shape != p.shape:
+                raise SeiError(f"sei_b200.optim.Adam: state '{name}' has shape {tuple(st[name].shape)}, parameter {tuple(p.shape)}")
         return st
 
     @torch.no_grad()

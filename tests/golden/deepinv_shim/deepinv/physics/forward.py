@@ -35,22 +35,38 @@ class LinearPhysics(Physics):
         return self.adjoint(y)
 
     def A_dagger(self, y):
-        """Least-squares pseudo-inverse by conjugate gradient on A^T A x = A^T y
-        (deepinv v0.2.0 uses its conjugate_gradient helper with max_iter / tol)."""
-        b = self.A_adjoint(y)
-        x = torch.zeros_like(b)
-        r = b.clone()
-        p = r
-        rs = (r * r).flatten().sum()
-        tol2 = self.tol ** 2
-        for _ in range(int(self.max_iter)):
-            Ap = self.A_adjoint(self.A(p))
-            alpha = rs / (p * Ap).flatten().sum()
-            x = x + p * alpha
-            r = r + Ap * (-alpha)
-            rs_new = (r * r).flatten().sum()
-            if rs_new < tol2:
-                break
-            p = r + p * (rs_new / rs)
-            rs = rs_new
+        """Least-squares pseudo-inverse by conjugate gradient, as deepinv v0.2.0 states it (RECALLED, not vendored):
+        when A^T y is smaller than y (an overcomplete system) solve A^T A x = A^T y; otherwise -- deblurring (equal
+        sizes) and super-resolution -- solve A A^T z = y and return A^T z.  max_iter / tol as attributes."""
+        Aty = self.A_adjoint(y)
+        overcomplete = Aty.numel() < y.numel()
+        if not overcomplete:
+            op, b = (lambda v: self.A(self.A_adjoint(v))), y
+        else:
+            op, b = (lambda v: self.A_adjoint(self.A(v))), Aty
+        x = conjugate_gradient(op, b, max_iter=self.max_iter, tol=self.tol)
+        if not overcomplete:
+            x = self.A_adjoint(x)
         return x
+
+
+def conjugate_gradient(A, b, max_iter=1e2, tol=1e-5):
+    """deepinv.optim.utils.conjugate_gradient (v0.2.0, RECALLED): plain CG from x0 = 0; stops once |r| < tol"""
+    def dot(s1, s2):
+        return (s1.conj() * s2).flatten().sum()
+
+    x = torch.zeros_like(b)
+    r = b
+    p = r
+    rsold = dot(r, r)
+    for _ in range(int(max_iter)):
+        Ap = A(p)
+        alpha = rsold / dot(p, Ap)
+        x = x + p * alpha
+        r = r + Ap * (-alpha)
+        rsnew = torch.real(dot(r, r))
+        if rsnew.sqrt() < tol:
+            break
+        p = r + p * (rsnew / rsold)
+        rsold = rsnew
+    return x

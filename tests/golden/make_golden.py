@@ -281,6 +281,11 @@ def gen_losses():
         ("deblur_gauss2_rotations", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Rotations"), (2, 3, 32, 32)),
         ("deblur_gauss2_rotshift", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ProposedLoss__transforms="Rotations+Shifts"), (2, 3, 32, 32)),
         ("deblur_gauss2_normalT_aa", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", ScalingTransform__kind="normal", ScalingTransform__antialias=True), (2, 3, 32, 32)),
+        # the reference's DEFAULT Loss path (demo/train.py:39,53): one random 48x48 crop of the batch (two CPU randint
+        # draws, src/crop.py:26-27) -- with the 4-D MinSizePadding quirk -- before the method loss
+        ("deblur_gauss2_proposed_crop", dict(task="deblurring", kernel="Gaussian_R2", method="proposed", Loss__crop_training_pairs=True), (2, 3, 64, 64)),
+        ("sr2_proposed_crop", dict(task="sr", kernel=None, sr_factor=2, method="proposed", Loss__crop_training_pairs=True), (2, 3, 56, 56)),
+        ("deblur_gauss2_supervised_crop32", dict(task="deblurring", kernel="Gaussian_R2", method="supervised", Loss__crop_training_pairs=True, Loss__crop_size=32), (2, 3, 40, 48)),
     ]
     only = os.environ.get("GOLDEN_ONLY", "")
     for name, kw, yshape in cases:
@@ -538,7 +543,84 @@ def gen_step():
     save("step_cfg1_cnn", **out)
 
 
+def gen_step_default():
+    """BASELINE configs[0] with the reference's DEFAULT network flags (--ProposedModel__architecture Convolutional:
+    hidden 32, 5 scales, 645 M parameters; src/settings.py:58-60): one proposed step's loss and parameter gradients on
+    synthetic 48x48 crops, batch 8, CPU fp32.  The weights are the seeded initialisation (torch.manual_seed(11); the
+    mirror's constructor consumes the generator identically, checked at small flags), so only digests of the 645 M
+    gradients are stored: every tensor's norm, the full gradient of tensors up to 64 Ki elements, and 16 Ki evenly
+    strided samples of the larger ones."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_convolutional", os.path.join(REF_SRC, "models", "convolutional.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    kw = dict(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+              hidden_channels=32, inout_convs=True, scales=5)
+    torch.set_num_threads(os.cpu_count() or 4)
+    torch.manual_seed(11)
+    net = mod.ConvolutionalModel(**kw)
+
+    class Wrapped(torch.nn.Module):     # Model.forward(x, *args) of src/models/__init__.py:148-149
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, *args):
+            return self.m(x)
+
+    model = Wrapped(net)
+    args = base_args()
+    physics = get_physics(args, device="cpu")
+    loss_fn = ref_losses.get_loss(args=args, physics=physics)
+    gen = torch.Generator().manual_seed(2025)
+    x = torch.rand((8, 3, 48, 48), generator=gen)
+    with torch.no_grad():
+        y = physics.A(x) + (5 / 255) * torch.randn((8, 3, 48, 48), generator=gen)
+    with DrawRecorder() as rec:
+        torch.manual_seed(3)
+        loss = loss_fn(x=x, y=y, model=model)
+    loss.backward()
+    out = {"x": np_(x), "y": np_(y), "loss": np_(loss), "kwargs": np.array(repr(kw)), "init_seed": np.array(11)}
+    out.update(rec.as_dict())
+    with torch.no_grad():
+        out["net_out"] = np_(net(y))
+    for k_, p_ in net.named_parameters():
+        g_ = p_.grad.detach().flatten()
+        out[f"gnorm::{k_}"] = np.array(float(g_.double().norm()))
+        out[f"wsum::{k_}"] = np.array(float(p_.detach().double().sum()))       # pins the seeded initialisation
+        if g_.numel() <= 65536:
+            out[f"grad::{k_}"] = np_(g_)
+        else:
+            idx = torch.linspace(0, g_.numel() - 1, 16384, dtype=torch.float64).long()
+            out[f"gsample::{k_}"] = np_(g_[idx])
+    save("step_cfg1_cnn_default", **out)
+
+
+def gen_dagger():
+    """A_dagger of the reference's physics objects (deepinv LinearPhysics.A_dagger through the shim's statement of
+    upstream's conjugate gradient) for deblurring and SR x2 with both adjoint kinds, a fixed small iteration count."""
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    cases = [("deblur_g1", base_args(kernel="Gaussian_R1"), (2, 3, 24, 24)),
+             ("deblur_box2_v1", base_args(kernel="Box_R2", physics_v2=False), (1, 3, 20, 28)),
+             ("sr2_plain", base_args(task="sr", kernel=None, sr_factor=2), (2, 3, 32, 32)),
+             ("sr2_true", base_args(task="sr", kernel=None, sr_factor=2, physics_true_adjoint=True), (2, 3, 32, 32))]
+    for name, args, shape in cases:
+        for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            if dt == torch.float64 and not getattr(args, "physics_v2", True):
+                continue                      # v1 Blur extends its filter in fp32: float64 inputs raise in the reference
+            phys = get_physics(args, device="cpu")
+            phys.max_iter, phys.tol = 6, 1e-12
+            x = torch.rand(shape, generator=torch.Generator().manual_seed(5), dtype=torch.float64).to(dt)
+            with torch.no_grad():
+                y = phys.A(x)
+                rec = phys.A_dagger(y)
+            out[f"{name}_y_{tag}"], out[f"{name}_dagger_{tag}"] = np_(y), np_(rec)
+        out[f"{name}_x"] = np_(x)
+    save("dagger", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "kernels", "blur", "downsampling", "transform", "losses", "crop", "degrade", "model"]
+    which = sys.argv[1:] or ["step", "step_default", "dagger", "kernels", "blur", "downsampling", "transform", "losses", "crop", "degrade", "model"]
     for w in which:
         globals()[f"gen_{w}"]()

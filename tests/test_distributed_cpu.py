@@ -47,7 +47,36 @@ def _worker(rank, world, port, results):
     same_weights = all(torch.equal(gathered[0], g) for g in gathered)
     with pytest.raises(ValueError):
         parallel.shard_batch(torch.zeros(7, 1), rank, world)
-    results[rank] = (err, same_weights)
+
+    # the overlapped protocol: buckets follow the module tree, each is reduced from inside backward() as soon as the
+    # last of the step's passes through its group has produced its gradients (a `proposed` step runs the network three
+    # times); what the backward pass does not release (the first layer: its input carries no gradient) goes in finish()
+    def tiny():
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3, padding=1), torch.nn.GELU(),
+                                   torch.nn.Sequential(torch.nn.Conv2d(7, 7, 1), torch.nn.GELU(), torch.nn.Conv2d(7, 5, 1)),
+                                   torch.nn.Conv2d(5, 3, 1))
+    torch.manual_seed(3)
+    net = tiny()
+    red = parallel.GradAllReducer(net.parameters(), module=net, group_max_elems=100)
+    assert len(red.buckets) >= 3
+    # odd-sized tensors (9-element kernels, 3- and 7-element biases) must not misalign the views that follow them:
+    # sei_adam_step_f32 and the in-place weight-gradient GEMM require 16-byte aligned gradients
+    assert all(p.grad.data_ptr() % 16 == 0 for p in net.parameters())
+    fired = []
+    orig = red._reduce_bucket
+    red._reduce_bucket = lambda i, async_op: (fired.append((i, red._armed)), orig(i, async_op))[1]
+    for p in net.parameters():
+        p.grad.zero_()
+    loss2 = sum(torch.nn.functional.mse_loss(net(x + 0.1 * k), t) for k in range(3))
+    red.arm()
+    loss2.backward()
+    n_from_backward = len(fired)
+    red.finish()
+    ref2 = tiny()
+    ref2.load_state_dict(net.state_dict())
+    sum(torch.nn.functional.mse_loss(ref2(x_global + 0.1 * k), t_global) for k in range(3)).backward()
+    err2 = max(float((p.grad - q.grad).abs().max()) for p, q in zip(net.parameters(), ref2.parameters()))
+    results[rank] = (err, same_weights, err2, n_from_backward, len(fired), len(red.buckets))
     dist.destroy_process_group()
 
 
@@ -59,9 +88,26 @@ def test_data_parallel_gradient_averaging_gloo():
         mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
         assert len(results) == world
         for rank in range(world):
-            err, same = results[rank]
+            err, same, err2, n_bwd, n_all, n_buckets = results[rank]
             assert err < 1e-6, err
             assert same
+            assert err2 < 1e-6, err2
+            assert n_all == n_buckets                   # every bucket reduced exactly once
+            assert 1 <= n_bwd < n_buckets               # some from inside backward(), the first layer's in finish()
+
+
+def test_sr_model_gradient_views_are_aligned():
+    """the SR network starts with LayerNorm(3) / 9-element kernels; every gradient view of the flat bucket
+    must still start on a 16-byte boundary (checked on the offsets; no process group needed)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scale-equivariant-imaging_b200"))
+    from sei_b200 import parallel
+    sizes = [3, 3, 9 * 3 * 3, 3, 32 * 27, 32, 5, 128 * 32]
+    offs, off = [], 0
+    for n in sizes:
+        offs.append(off)
+        off += -(-n // parallel._ALIGN) * parallel._ALIGN
+    assert all(o % 4 == 0 for o in offs) and parallel._ALIGN % 32 == 0
 
 
 def test_bucket_partition():

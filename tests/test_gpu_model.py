@@ -177,3 +177,69 @@ def test_training_reduces_loss_and_tracks_torch_adam(dev):
     for name, c in curves.items():
         assert c[-1] < 0.7 * c[0], (name, c[0], c[-1])
     assert abs(curves["sei"][-1] - curves["torch"][-1]) < 0.15 * curves["torch"][-1], (curves["sei"][-1], curves["torch"][-1])
+
+
+def test_full_step_cfg1_default_network_matches_reference(golden, dev):
+    """BASELINE configs[0] with the reference's DEFAULT network flags (hidden 32, 5 scales, 645 M parameters): one
+    proposed step (48x48 crops, batch 8) through losses.get_loss + the CNN kernels, the reference's random tensors
+    injected, against the reference's fp32 CPU run (tests/golden/step_cfg1_cnn_default.npz holds the loss, the network
+    output, every gradient tensor's norm, small gradients in full and strided samples of the large ones).
+    Stated bf16 tolerance: loss 2e-2 relative; network output 2e-2 of its range; per gradient tensor cosine > 0.99 on
+    the stored entries and norm within 5 % (tensors with > 16 elements)."""
+    from argparse import Namespace
+    import losses
+    import models.convolutional as mc
+    import physics
+    from sei_b200 import draws
+    g = golden("step_cfg1_cnn_default")
+    torch.manual_seed(int(g["init_seed"]))
+    net = mc.ConvolutionalModel(**eval(str(g["kwargs"])))            # seeded init on the CPU, like the reference's
+    for k, p in net.named_parameters():                              # the same weights as the reference's run
+        assert abs(float(p.detach().double().sum()) - float(g[f"wsum::{k}"])) <= 1e-9 * max(1.0, abs(float(g[f"wsum::{k}"]))), k
+    net = net.to(dev)
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, *args):
+            return self.m(x)
+
+    args = Namespace(task="deblurring", noise_level=5, physics_v2=True, kernel="Gaussian_R2", sr_factor=None,
+                     physics_true_adjoint=False, partial_sure=True, sure_margin=None, partial_sure_sr=False,
+                     Loss__crop_training_pairs=False, Loss__crop_size=48, ProposedLoss__stop_gradient=True,
+                     ProposedLoss__sure_alternative=None, ProposedLoss__alpha_tradeoff=1.0,
+                     ProposedLoss__transforms="Scaling_Transforms", ScalingTransform__kind="padded",
+                     ScalingTransform__antialias=False, method="proposed", sure_cropped_div=True,
+                     sure_averaged_cst=None)
+    phys = physics.get_physics(args, device=dev)
+    loss_fn = losses.get_loss(args, phys)
+    y = torch.from_numpy(g["y"]).to(dev)
+    with torch.no_grad():
+        out = net(y)
+    assert rel_err(out.cpu().numpy(), g["net_out"]) < 2e-2
+    injected = [g[k] for k in sorted((k for k in g if k.startswith("draw")), key=lambda s: int(s[4:].split("_")[0]))]
+    with draws.inject(injected):
+        loss = loss_fn(x=torch.from_numpy(g["x"]).to(dev), y=y, model=Wrapped(net))
+    loss.backward()
+    ref = float(g["loss"])
+    assert abs(float(loss) - ref) < 2e-2 * abs(ref), (float(loss), ref)
+    bad, worst = [], 1.0
+    for k, p in net.named_parameters():
+        got = p.grad.detach().flatten()
+        n_ref = float(g[f"gnorm::{k}"])
+        if got.numel() <= 16 or n_ref < 1e-12:
+            continue
+        ratio = float(got.double().norm()) / n_ref
+        if f"grad::{k}" in g:
+            r, s = np.asarray(g[f"grad::{k}"], dtype=np.float64), got.double().cpu().numpy()
+        else:
+            idx = torch.linspace(0, got.numel() - 1, 16384, dtype=torch.float64).long().to(dev)
+            r, s = np.asarray(g[f"gsample::{k}"], dtype=np.float64), got[idx].double().cpu().numpy()
+        cos = float(r @ s / (np.linalg.norm(r) * np.linalg.norm(s) + 1e-300))
+        worst = min(worst, cos)
+        if cos < 0.99 or not (0.95 < ratio < 1.05):
+            bad.append((k, round(cos, 4), round(ratio, 3)))
+    print(f"default-network step: loss {float(loss):.6f} vs {ref:.6f}; worst gradient cosine {worst:.4f}")
+    assert not bad, bad

@@ -87,3 +87,40 @@ def test_weight_shadows_follow_any_optimizer(dev):
         assert torch.equal(cache, conv.weight.detach().reshape(32, 16).bfloat16())
         if conv._wt_cache is not None and isinstance(opt, SeiAdam):
             assert torch.equal(conv._wt_cache, cache.t())
+
+
+def test_adam_loads_torch_and_cpu_state_dicts(dev, tmp_path):
+    """Optimizer.load_state_dict leaves `step` on the CPU for non-capturable groups, a map_location="cpu"
+    checkpoint leaves the whole state there, and old checkpoints store `step` as a Python number.  The kernel reads
+    these through device pointers, so step() must coerce them (not dereference a host pointer)."""
+    from sei_b200.optim import Adam
+    torch.manual_seed(2)
+    p = torch.nn.Parameter(torch.randn(256, 8, device=dev))
+    q = torch.nn.Parameter(p.detach().clone())
+    grads = [torch.randn_like(p) for _ in range(4)]
+    ref = torch.optim.Adam([q], lr=1e-2)
+    for g in grads[:2]:
+        q.grad = g.clone()
+        ref.step()
+    sd = ref.state_dict()
+    path = tmp_path / "opt.pt"
+    torch.save(sd, path)
+    for variant in ("torch_state", "cpu_checkpoint", "python_step"):
+        p2 = torch.nn.Parameter(q.detach().clone())
+        ours = Adam([p2], lr=1e-2)
+        state = torch.load(path, map_location="cpu") if variant != "torch_state" else ref.state_dict()
+        if variant == "python_step":
+            state["state"][0]["step"] = float(state["state"][0]["step"])
+        ours.load_state_dict(state)
+        q3 = torch.nn.Parameter(q.detach().clone())
+        ref3 = torch.optim.Adam([q3], lr=1e-2)
+        ref3.load_state_dict(ref.state_dict())
+        for g in grads[2:]:
+            p2.grad, q3.grad = g.clone(), g.clone()
+            ours.step()
+            ref3.step()
+        torch.cuda.synchronize()
+        assert float((p2 - q3).abs().max() / q3.abs().max()) < 2e-6, variant
+        st = ours.state[p2]
+        assert st["step"].device == p2.device and float(st["step"]) == 4.0
+        assert st["exp_avg"].is_cuda and st["exp_avg_sq"].is_cuda

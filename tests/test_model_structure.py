@@ -33,9 +33,8 @@ def test_default_parameter_tree_matches_reference(golden):
 def test_network_structure_fp32(golden, name, monkeypatch):
     import models.convolutional as mc
     g, model = _load(golden, name)
-    monkeypatch.setattr(mc, "COMPUTE_DTYPE", torch.float32)
-    monkeypatch.setattr(mc, "_gemm_tn", lambda a, b, bias, out_dtype: (a @ b.t() + (bias if bias is not None else 0)).to(out_dtype))
-    monkeypatch.setattr(mc, "_gemm_atb", lambda a, b, out=None: (a.t() @ b).float())
+    import torch_formulation
+    torch_formulation.install(mc, monkeypatch.setattr)      # fp32 library formulation of the operator hooks: tests only
     y = torch.from_numpy(g["y"])
     out = model(y)
     assert rel_err(out.detach().numpy(), g["out"]) < 2e-5

@@ -278,3 +278,26 @@ def test_oracle_resize_bicubic_matches_reference(golden):
                 assert rel_err(orc.resize_bicubic(x, rate, bool(aa)), g[f"y64_{tag}"]) < 1e-11, tag
                 # the reference's float32 run rounds its source coordinates / weights in fp32 (scale 4/3): 3e-6
                 assert rel_err(orc.resize_bicubic(x.astype(np.float32), rate, bool(aa)), g[f"y32_{tag}"]) < 5e-6, tag
+
+
+@pytest.mark.parametrize("name", ["deblur_g1", "deblur_box2_v1", "sr2_plain", "sr2_true"])
+def test_a_dagger(golden, name):
+    """A_dagger of the reference's physics objects (six CG iterations) against the oracle's conjugate gradient over the
+    oracle's operators: the non-overcomplete branch (A A^T z = y, x = A^T z) with each kind of `A_adjoint`."""
+    g = golden("dagger")
+    if name.startswith("deblur"):
+        kern = orc.named_kernel("Gaussian_R1" if name == "deblur_g1" else "Box_R2")
+        A = lambda v: orc.blur_circular(v, kern)
+        At = lambda v: orc.blur_circular(v, kern, adjoint=True)
+    else:
+        A = lambda v: orc.down_aa(v, 2)
+        At = (lambda v: orc.up_bicubic(v, 2)) if name == "sr2_plain" else (lambda v: orc.down_aa_vjp(v, 2, (2 * v.shape[-2], 2 * v.shape[-1])))
+    for tag, tol in (("f64", 1e-9), ("f32", 1e-5)):
+        if f"{name}_y_{tag}" not in g:
+            continue
+        y = g[f"{name}_y_{tag}"]
+        if name == "sr2_true" and tag == "f64":
+            continue            # the reference's true adjoint evaluates in fp32 whatever the input (DESIGN section 4 quirk)
+        rec = orc.a_dagger(A, At, y, max_iter=6, tol=1e-12)
+        assert rec.dtype == y.dtype
+        assert rel_err(rec, g[f"{name}_dagger_{tag}"]) < tol, (name, tag)
