@@ -81,14 +81,21 @@ def test_resampler_products_layout_and_batching(monkeypatch, kind, B, H, W, C):
     assert resample._Product(torch.zeros(24, 32, dtype=torch.float64), "cpu")._pack_factor(32) == 1
 
 
-def test_mirror_fft_path_matches_reference(golden):
-    """the library (torch.fft) formulation kept for channel counts that are not a multiple of 8"""
+def test_torch_formulation_of_the_resamplers_matches_reference(golden):
+    """tests/torch_formulation.py (the library formulation the CPU structure tests install) against the reference's
+    IdealUpsample / IdealDownsample fixtures; the package itself has no library path: a CPU tensor raises"""
     import models.convolutional as mc
+    import sei_b200
+    import torch_formulation
     g = golden("resample")
     for i in range(N_CASES):
-        for kind, layer in (("down", mc.IdealDownsample(2)), ("up", mc.IdealUpsample(2))):
+        for kind in ("down", "up"):
             x = torch.from_numpy(g[f"{kind}{i}_x"]).float()
-            assert rel_err(layer(x).numpy(), g[f"{kind}{i}_y"]) < 2e-5, (kind, i)
+            assert rel_err(torch_formulation.ideal_resample(x, kind, 2).numpy(), g[f"{kind}{i}_y"]) < 2e-5, (kind, i)
+    with pytest.raises(sei_b200.SeiError):
+        mc.IdealDownsample(2)(torch.rand(1, 8, 16, 16))
+    with pytest.raises(sei_b200.SeiError):
+        mc.LayerNorm(8)(torch.rand(1, 8, 4, 4))
 
 
 @pytest.fixture(scope="module")
