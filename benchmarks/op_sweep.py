@@ -30,11 +30,32 @@ def peak_gbs():
     return 6650.0, "fallback"
 
 
-def time_us(fn, n_rot, reps, warmup=3):
+def time_us(fn, n_rot, reps, warmup=3, graph=True):
+    """device time per call: `reps` back-to-back calls over rotating inputs, captured in a CUDA graph so that the host's
+    per-call cost (ctypes + torch.empty, 15 - 30 us: more than several of these kernels take) is not what is measured"""
     for i in range(warmup):
         fn(i % n_rot)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g):
+                    for i in range(reps):
+                        fn(i % n_rot)
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / reps
+        except Exception:  # noqa: BLE001  (an op that cannot be captured, e.g. torch.fft plans on first use)
+            torch.cuda.synchronize()
     e0.record()
     for i in range(reps):
         fn(i % n_rot)

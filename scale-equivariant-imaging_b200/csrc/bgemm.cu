@@ -52,13 +52,7 @@ struct BgemmParams {
     long long d_bo, d_bi, d_mo, d_mi;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
-{
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// cp_async16 / cp_async_commit / cp_async_wait: sei_common.cuh
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p)
 {

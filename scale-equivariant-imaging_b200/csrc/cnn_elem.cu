@@ -1356,24 +1356,110 @@ __global__ void __launch_bounds__(256) ln_small_bwd_kernel(const __nv_bfloat16* 
 
 static int ln_small_ctas(int sm_count) { return sm_count * 8; }
 
+// ---- any channel count (the widths 3 * 4^s of the network without in / out convolutions: 48, 192, ...): one warp per
+// row, lanes strided over the channels; fp32 two-pass statistics.  A correctness path, not a tuned one.
+__global__ void __launch_bounds__(256) ln_warp_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                          float* __restrict__ mean, float* __restrict__ rstd,
+                                                          long long T, int C, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const float invC = 1.0f / (float)C;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < T; r += nwarps) {
+        const __nv_bfloat16* xr = x + r * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += __bfloat162float(xr[c]);
+        const float mu = warp_sum(s) * invC;
+        float q = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float d = __bfloat162float(xr[c]) - mu;
+            q = fmaf(d, d, q);
+        }
+        const float rs = rsqrtf(warp_sum(q) * invC + eps);
+        for (int c = lane; c < C; c += 32)
+            y[r * C + c] = __float2bfloat16_rn(fmaf((__bfloat162float(xr[c]) - mu) * rs, __ldg(gamma + c), __ldg(beta + c)));
+        if (lane == 0) {
+            mean[r] = mu;
+            rstd[r] = rs;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ln_warp_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                                                             long long T, int C)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const float invC = 1.0f / (float)C;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < T; r += nwarps) {
+        const float mu = mean[r], rs = rstd[r];
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float xh = (__bfloat162float(x[r * C + c]) - mu) * rs;
+            const float g = __bfloat162float(gy[r * C + c]) * __ldg(gamma + c);
+            s1 += g;
+            s2 = fmaf(g, xh, s2);
+        }
+        const float m1 = warp_sum(s1) * invC, m2 = warp_sum(s2) * invC;
+        for (int c = lane; c < C; c += 32) {
+            const float xh = (__bfloat162float(x[r * C + c]) - mu) * rs;
+            const float g = __bfloat162float(gy[r * C + c]) * __ldg(gamma + c);
+            dx[r * C + c] = __float2bfloat16_rn(rs * (g - m1 - xh * m2));
+        }
+    }
+}
+
+// dgamma / dbeta partials: thread = channel, CTA (x: 128-channel group, y: slab of rows) walks its rows in order;
+// partial[slab][2][C], combined in fixed order by colsum_final_kernel (deterministic, no atomics)
+__global__ void __launch_bounds__(128) ln_warp_param_grad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ gy,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 float* __restrict__ partial, long long T, int C)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const long long per = (T + gridDim.y - 1) / gridDim.y;
+    const long long r_lo = per * blockIdx.y, r_hi = min(T, r_lo + per);
+    float dg = 0.f, db = 0.f;
+    for (long long r = r_lo; r < r_hi; ++r) {
+        const float go = __bfloat162float(gy[r * C + c]);
+        dg = fmaf(go, (__bfloat162float(x[r * C + c]) - mean[r]) * rstd[r], dg);
+        db += go;
+    }
+    partial[(size_t)blockIdx.y * 2 * C + c] = dg;
+    partial[(size_t)blockIdx.y * 2 * C + C + c] = db;
+}
+
+static int ln_warp_slabs(long long T, int sm_count) { return (int)std::max<long long>(1, std::min<long long>(T / 64, (long long)sm_count * 4)); }
+
 }  // namespace sei
 
 extern "C" long long sei_ln_small_workspace_bytes(int C)
 {
     DeviceProps dp;
-    if (get_device_props(&dp) || C < 1 || C > kLnSmallMaxC) return -1;
-    return (long long)ln_small_ctas(dp.sm_count) * 2 * C * (long long)sizeof(float);
+    if (get_device_props(&dp) || C < 1 || C > 65536) return -1;
+    // C <= 32: one partial row per CTA of the one-thread-per-row kernel; larger C: one per row slab (at most 4 per SM)
+    return (long long)(C <= kLnSmallMaxC ? ln_small_ctas(dp.sm_count) : dp.sm_count * 4) * 2 * C * (long long)sizeof(float);
 }
 
 extern "C" int sei_ln_small_forward_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                          float* rstd, long long T, int C, float eps, void* stream)
 {
     SEI_REQUIRE(x && gamma && beta && y && mean && rstd, "null pointer argument");
-    SEI_REQUIRE(T >= 0 && C >= 1 && C <= kLnSmallMaxC, "bad shape T=%lld C=%d (1..%d channels)", T, C, kLnSmallMaxC);
+    SEI_REQUIRE(T >= 0 && C >= 1 && C <= 65536, "bad shape T=%lld C=%d", T, C);
     if (T == 0) return 0;
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
+    if (C > kLnSmallMaxC) {
+        const unsigned gridw = (unsigned)std::min<long long>((T + 7) / 8, (long long)dp.sm_count * 8);
+        ln_warp_fwd_kernel<<<gridw, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, T, C, eps);
+        return finish_launch("ln_warp_fwd_kernel");
+    }
     const unsigned grid = (unsigned)std::min<long long>((T + 255) / 256, (long long)ln_small_ctas(dp.sm_count));
     ln_small_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, T, C, eps);
@@ -1385,7 +1471,7 @@ extern "C" int sei_ln_small_backward_bf16(const void* gy, const void* x, const f
                                           long long T, int C, void* stream)
 {
     SEI_REQUIRE(gy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "null pointer argument");
-    SEI_REQUIRE(T >= 0 && C >= 1 && C <= kLnSmallMaxC, "bad shape T=%lld C=%d (1..%d channels)", T, C, kLnSmallMaxC);
+    SEI_REQUIRE(T >= 0 && C >= 1 && C <= 65536, "bad shape T=%lld C=%d", T, C);
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
@@ -1394,6 +1480,20 @@ extern "C" int sei_ln_small_backward_bf16(const void* gy, const void* x, const f
         SEI_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
         SEI_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
         return 0;
+    }
+    if (C > kLnSmallMaxC) {
+        const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+        const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(gy);
+        const unsigned gridw = (unsigned)std::min<long long>((T + 7) / 8, (long long)dp.sm_count * 8);
+        ln_warp_bwd_dx_kernel<<<gridw, 256, 0, st>>>(xb, gb, mean, rstd, gamma, static_cast<__nv_bfloat16*>(dx), T, C);
+        rc = finish_launch("ln_warp_bwd_dx_kernel");
+        if (rc) return rc;
+        const int slabs = ln_warp_slabs(T, dp.sm_count);
+        ln_warp_param_grad_kernel<<<dim3((C + 127) / 128, slabs), 128, 0, st>>>(xb, gb, mean, rstd, static_cast<float*>(workspace), T, C);
+        rc = finish_launch("ln_warp_param_grad_kernel");
+        if (rc) return rc;
+        colsum_final_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), dgamma, dbeta, slabs, 2 * C, C);
+        return finish_launch("colsum_final_kernel");
     }
     const int grid = (int)std::min<long long>((T + 255) / 256, (long long)ln_small_ctas(dp.sm_count));
     ln_small_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gy), mean,

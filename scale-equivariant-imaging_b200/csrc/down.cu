@@ -383,6 +383,596 @@ __global__ void __launch_bounds__(kDownThreads) down_t_band_kernel(const __grid_
     }
 }
 
+
+// ================================================================== round-2 kernels
+// Forward, "rows" form.  The round-1 kernel filtered horizontally first: every input element went through shared
+// memory about 3.7 times (TMA fill, 2x overlapping 128-bit reads of the horizontal windows, the intermediate and its
+// 4R-row vertical windows), which at R = 4 is two thirds of the SM's shared-memory bandwidth at full HBM rate
+// (measured 0.28 of the copy peak).  Here the VERTICAL pass runs first, straight from global memory: a thread owns one
+// 4-column group, walks down the band's input rows with 128-bit read-only loads and keeps the four output rows whose
+// windows cover the current input row in rotating accumulators -- every input element is loaded exactly once and
+// never touches shared memory.  Only the vertically filtered band (1/R of the input) is written to shared memory; the
+// horizontal decimation reads it with 128-bit loads (8 outputs per item, lanes spread over 8 rows of a pitch = 4 mod 32
+// intermediate: conflict-free) into an output tile that leaves through ONE bulk async store (TMA engine); the noise
+// band arrives in that tile by a bulk async load issued at kernel start.
+template <int R> struct DownGeom {
+    static constexpr int T = 4 * R, OFF = aa_off(R);
+    static constexpr int LPAD = 4 * ((OFF + 3) / 4);          // left margin of an intermediate row (>= OFF, multiple of 4)
+    static constexpr int SKIP = LPAD - OFF;
+    static constexpr int NO = 8;                               // outputs per horizontal work item
+    static constexpr int NV = (SKIP + (NO - 1) * R + T + 3) / 4;
+    static constexpr int RING = R <= 2 ? 6 : 4;                // steps of the per-thread input ring (one step = R rows)
+};
+
+__host__ __device__ constexpr int down_v_pitch(int W, int lpad) { return blur_pad_pitch_c(lpad + W + 8); }
+
+struct DownRowsParams {
+    const float* x;
+    float* y;
+    const float* noise;
+    float sigma;
+    int H, W, Ho, Wo, nbands;
+    float wint[kAaMaxTaps];
+    BorderTab colTab, rowTab;
+};
+
+template <int R, int WT, int TH>
+__global__ void __launch_bounds__(kDownThreads, 2) down_rows_kernel(const __grid_constant__ DownRowsParams p)
+{
+    using G = DownGeom<R>;
+    constexpr int T = G::T, OFF = G::OFF, NT = kDownThreads;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+
+    const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R;
+    const int pitch = down_v_pitch(W, G::LPAD);
+    const int opitch = blur_pad_pitch_c(Wo);                           // padded: the 8 rows of a quarter-warp hit 8 bank groups
+    float* sOut = reinterpret_cast<float*>(smem_raw);                  // [TH][opitch]  noise in, result out (in place)
+    float* sV = sOut + TH * opitch;                                    // [TH][pitch]
+    float4* sRing = reinterpret_cast<float4*>(sV + TH * pitch);        // [RING * R][NT] float4, one column per thread
+    const int band = blockIdx.x % p.nbands;
+    const long long plane = blockIdx.x / p.nbands;
+    const int i0 = band * TH, th = min(TH, Ho - i0);
+    const float* __restrict__ xplane = p.x + (size_t)plane * H * W;
+    const size_t oband = ((size_t)plane * Ho + i0) * Wo;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        if (p.noise) {                                                 // one bulk copy per row of the noise band
+            mbar_arrive_expect_tx(&bar, (uint32_t)th * Wo * 4u);
+            for (int r = 0; r < th; ++r) bulk_g2s(sOut + r * opitch, p.noise + oband + (size_t)r * Wo, (uint32_t)Wo * 4u, &bar);
+        }
+    }
+
+    // ---- vertical pass, global -> registers -> sV
+    const int CWin = W >> 2;
+    const int nseg = CWin >= NT ? 1 : min(TH, NT / CWin);            // row segments so that every thread has a column group
+    const int THs = (TH + nseg - 1) / nseg;
+    for (int unit = threadIdx.x; unit < nseg * CWin; unit += NT) {
+        const int seg = unit / CWin, c4 = unit - seg * CWin;
+        const int o_first = seg * THs;
+        const int nout = min(THs, th - o_first);
+        if (nout <= 0) continue;
+        const float* __restrict__ colp = xplane + 4 * c4;
+        const int row0 = R * (i0 + o_first) - OFF;                    // input row of step 0, tap 0
+        const int nsteps = nout + 3;
+        // Input rows reach the thread through a private ring in shared memory filled by per-thread asynchronous 16-byte
+        // copies (cp.async, no registers held while in flight): D - 1 steps of R rows are always outstanding, 160 - 192
+        // bytes per thread, ~90 KB per SM -- what it takes to keep HBM busy (Little's law at ~1 us latency).  A thread
+        // only ever reads what it copied itself, so there is no barrier: cp.async.wait_group is the whole hand-shake.
+        // (Register double-buffering kept 32 - 64 bytes per thread in flight: ncu showed 60 % of the stall samples on the
+        // first FMA of a step, 0.9 eligible warps per scheduler and 39 % of the DRAM bandwidth.)
+        constexpr int D = G::RING;
+        float4* ring = sRing + threadIdx.x;                            // [D * R][NT]
+        auto issue = [&](int s) {
+            if (s < nsteps) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int row = row0 + R * s + k;
+                    const bool ok = (unsigned)row < (unsigned)H;
+                    cp_async16(ring + ((s % D) * R + k) * NT, colp + (size_t)(ok ? row : 0) * W, ok);
+                }
+            }
+            cp_async_commit();                                          // one group per step, empty past the end
+        };
+#pragma unroll
+        for (int q = 0; q < D - 1; ++q) issue(q);
+        float4 acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* vcol = sV + o_first * pitch + G::LPAD + 4 * c4;
+        for (int s0 = 0; s0 < nsteps; s0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = s0 + u;
+                if (s < nsteps) {
+                    issue(s + D - 1);
+                    cp_async_wait<D - 1>();                             // the copies of step s have landed
+                    float4 cur[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cur[k] = ring[((s % D) * R + k) * NT];
+                    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);          // output row o = s starts in slot s % 4
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        float4& a = acc[(u - d) & 3];                   // output row o = s - d
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            const float w = p.wint[R * d + k];
+                            a.x = fmaf(w, cur[k].x, a.x); a.y = fmaf(w, cur[k].y, a.y);
+                            a.z = fmaf(w, cur[k].z, a.z); a.w = fmaf(w, cur[k].w, a.w);
+                        }
+                    }
+                    if (s >= 3) *reinterpret_cast<float4*>(vcol + (s - 3) * pitch) = acc[(u + 1) & 3];   // o = s - 3 is complete
+                }
+            }
+        }
+        cp_async_wait<0>();
+        // the image's first / last two output rows have truncated, renormalised windows: recompute this column group
+        for (int o = 0; o < nout; ++o) {
+            const int i = i0 + o_first + o;
+            const int kb = border_slot(i, Ho);
+            if (kb < 0) continue;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < p.rowTab.xsize[kb]; ++t) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(colp + (size_t)(p.rowTab.xmin[kb] + t) * W));
+                const float w = p.rowTab.w[kb][t];
+                a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+            }
+            *reinterpret_cast<float4*>(vcol + o * pitch) = a;
+        }
+    }
+    __syncthreads();
+    if (p.noise) mbar_wait(&bar, 0);
+
+    // ---- horizontal decimation: sOut[r][j] = sum_t w[t] * sV[r][R*j - OFF + t]  (+ sigma * noise)
+    constexpr int NO = G::NO, NV = G::NV, SKIP = G::SKIP;
+    const int nblk = Wo / NO;                                          // Wo % 8 == 0 is required by the dispatcher
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rgroups = (th + 7) >> 3, bgroups = (nblk + 3) >> 2;
+    for (int wi = warp; wi < rgroups * bgroups; wi += NT / 32) {
+        const int rg = wi % rgroups, bg = wi / rgroups;
+        const int r = 8 * rg + (lane & 7), blk = 4 * bg + (lane >> 3);
+        if (r >= th || blk >= nblk) continue;
+        const float* __restrict__ src = sV + r * pitch + R * NO * blk;   // = row base + LPAD + R*j0 - LPAD
+        float v[4 * NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(src + 4 * q);
+            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+        float out[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            float a = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], v[SKIP + R * o + t], a);
+            out[o] = a;
+        }
+        if (blk == 0 || blk == nblk - 1) {                             // the row's first / last two outputs
+            const float* row = sV + r * pitch + G::LPAD;
+            auto border = [&](int kb) {
+                float a = 0.f;
+                for (int t = 0; t < p.colTab.xsize[kb]; ++t) a = fmaf(p.colTab.w[kb][t], row[p.colTab.xmin[kb] + t], a);
+                return a;
+            };
+            if (blk == 0) { out[0] = border(0); out[1] = border(1); }
+            if (blk == nblk - 1) { out[NO - 2] = border(2); out[NO - 1] = border(3); }
+        }
+        float* dst = sOut + r * opitch + NO * blk;
+#pragma unroll
+        for (int q = 0; q < NO / 4; ++q) {
+            float4 o4 = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+            if (p.noise) {
+                const float4 n4 = *reinterpret_cast<const float4*>(dst + 4 * q);
+                o4.x = fmaf(p.sigma, n4.x, o4.x); o4.y = fmaf(p.sigma, n4.y, o4.y);
+                o4.z = fmaf(p.sigma, n4.z, o4.z); o4.w = fmaf(p.sigma, n4.w, o4.w);
+            }
+            *reinterpret_cast<float4*>(dst + 4 * q) = o4;
+        }
+    }
+    fence_proxy_async();                        // the tile was written by generic stores; the bulk store reads it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < th; ++r) bulk_s2g(p.y + oband + (size_t)r * Wo, sOut + r * opitch, (uint32_t)Wo * 4u);
+        bulk_commit();
+        bulk_wait_read_all();                   // shared memory must stay valid until the engine has read it
+    }
+}
+
+// Persistent form of the kernel above (taken whenever one thread per 4-column group and row segment suffices, i.e.
+// input widths up to 1024): a CTA walks the bands blockIdx.x, blockIdx.x + gridDim.x, ... and its threads' input rings
+// never drain -- the first steps of the NEXT band are already in flight while the current band is decimated
+// horizontally and stored.  A band is only 100 - 180 KB of input, about 4 us at an SM's share of the HBM bandwidth, so a
+// one-band CTA spent a third of its life ramping its loads up and down (the non-persistent kernel: 0.50 - 0.55 of the
+// copy peak with the same inner loops).
+constexpr int kDownStreamDepth = 3;      // ring steps of the persistent kernel: two steps (8 rows at x2 / x4, 128 B per thread) in flight
+
+template <int R, int WT, int TH>
+__global__ void __launch_bounds__(kDownThreads, 2) down_stream_kernel(const __grid_constant__ DownRowsParams p, long long total_items)
+{
+    using G = DownGeom<R>;
+    constexpr int T = G::T, OFF = G::OFF, NT = kDownThreads;
+    // one step = RS = R * JO input rows (four at x2 and x4): JO output rows start per step, JO + 3 are live, each in an
+    // accumulator slot (output index mod NSLOT); the step loop is unrolled by NSLOT / JO so that slots are static
+    constexpr int JO = R == 2 ? 2 : 1, RS = R * JO, NSLOT = JO == 2 ? 6 : 4, UNR = NSLOT / JO, D = kDownStreamDepth;
+    constexpr int JLO = -3;                                    // lowest live output of a step, relative to JO * s
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+
+    const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R;
+    const int pitch = down_v_pitch(W, G::LPAD);
+    const int opitch = blur_pad_pitch_c(Wo);
+    float* sOut = reinterpret_cast<float*>(smem_raw);                  // [TH][opitch]  noise in, result out (in place)
+    float* sV = sOut + TH * opitch;                                    // [TH][pitch]
+    float4* sRing = reinterpret_cast<float4*>(sV + TH * pitch);        // [RING * R][NT] float4, one column per thread
+
+    const int CWin = W >> 2;
+    int nseg = 1;
+    while (2 * nseg <= TH && 2 * nseg * CWin <= NT) nseg *= 2;         // row segments: a power of two that divides TH
+    const int THs = TH / nseg;                                         // output rows per segment and band
+    const int NS = (R * (THs - 1) + T - 1) / RS + 1;                   // steps until the segment's last output row is complete
+    const bool has_unit = (int)threadIdx.x < nseg * CWin;
+    const int seg = threadIdx.x / CWin, c4 = threadIdx.x - seg * CWin;
+    const int o_first = seg * THs;
+    const int n_my = (int)((total_items - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- issue side of the ring: (item, step) advance independently of the consuming loop
+    float4* ring = sRing + threadIdx.x;
+    int is_item = 0, is_step = 0, is_slot = 0, is_row0 = 0;
+    const float* is_col = nullptr;
+    auto is_locate = [&]() {
+        if (is_item < n_my) {
+            const long long w = blockIdx.x + (long long)is_item * gridDim.x;
+            const int band = (int)(w % p.nbands);
+            is_col = p.x + (size_t)(w / p.nbands) * H * W + 4 * c4;
+            is_row0 = R * (band * TH + o_first) - OFF;                  // input row of step 0, row 0
+        }
+    };
+    auto issue = [&]() {
+        if (has_unit && is_item < n_my) {
+#pragma unroll
+            for (int k = 0; k < RS; ++k) {
+                const int row = is_row0 + RS * is_step + k;
+                const bool ok = (unsigned)row < (unsigned)H;
+                cp_async16(ring + (is_slot * RS + k) * NT, is_col + (size_t)(ok ? row : 0) * W, ok);
+            }
+        }
+        cp_async_commit();                                              // one group per step, empty past the end
+        is_slot = is_slot + 1 == D ? 0 : is_slot + 1;
+        if (++is_step == NS) {
+            is_step = 0;
+            ++is_item;
+            is_locate();
+        }
+    };
+    is_locate();
+#pragma unroll
+    for (int q = 0; q < D - 1; ++q) issue();
+
+    int slot = 0;
+    for (int it = 0; it < n_my; ++it) {
+        const long long w = blockIdx.x + (long long)it * gridDim.x;
+        const int band = (int)(w % p.nbands);
+        const long long plane = w / p.nbands;
+        const int i0 = band * TH, th = min(TH, Ho - i0);
+        const size_t oband = ((size_t)plane * Ho + i0) * Wo;
+        if (threadIdx.x == 0 && p.noise) {                              // this band's noise rows -> the output tile
+            bulk_wait_read_all();                                       // the previous band's store has read the tile
+            mbar_arrive_expect_tx(&bar, (uint32_t)th * Wo * 4u);
+            for (int r = 0; r < th; ++r) bulk_g2s(sOut + r * opitch, p.noise + oband + (size_t)r * Wo, (uint32_t)Wo * 4u, &bar);
+        }
+        // ---- vertical pass of this band's segment: NS steps
+        if (has_unit) {
+            float4 acc[NSLOT];
+#pragma unroll
+            for (int q = 0; q < NSLOT; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* vcol = sV + o_first * pitch + G::LPAD + 4 * c4;
+            for (int s0 = 0; s0 < NS; s0 += UNR) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int s = s0 + u;
+                    if (s < NS) {
+                        issue();
+                        cp_async_wait<D - 1>();                         // the copies of this step have landed
+                        float4 cur[RS];
+#pragma unroll
+                        for (int k = 0; k < RS; ++k) cur[k] = ring[(slot * RS + k) * NT];
+                        slot = slot + 1 == D ? 0 : slot + 1;
+#pragma unroll
+                        for (int j = 0; j < JO; ++j) acc[(JO * u + j) % NSLOT] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows that start here
+#pragma unroll
+                        for (int j = JLO; j < JO; ++j) {                // output row o = JO * s + j
+                            float4& a = acc[(JO * u + j + NSLOT) % NSLOT];
+#pragma unroll
+                            for (int k = 0; k < RS; ++k) {
+                                const int t = k - R * j;                // tap of input row k of this step in o's window
+                                if (t >= 0 && t < T) {
+                                    const float wgt = p.wint[t];
+                                    a.x = fmaf(wgt, cur[k].x, a.x); a.y = fmaf(wgt, cur[k].y, a.y);
+                                    a.z = fmaf(wgt, cur[k].z, a.z); a.w = fmaf(wgt, cur[k].w, a.w);
+                                }
+                            }
+                            // o's last input row R * o + T - 1 lies in this step  <=>  0 <= R * j + T - 1 < RS
+                            if (R * j + T - 1 >= 0 && R * j + T - 1 < RS) {
+                                const int o = JO * s + j;
+                                if (o >= 0 && o < THs) *reinterpret_cast<float4*>(vcol + o * pitch) = a;
+                            }
+                        }
+                    }
+                }
+            }
+            // the image's first / last two output rows have truncated, renormalised windows: recompute this column group
+            const float* __restrict__ colp = p.x + (size_t)plane * H * W + 4 * c4;
+            for (int o = 0; o < THs; ++o) {
+                const int i = i0 + o_first + o;
+                const int kb = i < Ho ? border_slot(i, Ho) : -1;
+                if (kb < 0) continue;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < p.rowTab.xsize[kb]; ++t) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(colp + (size_t)(p.rowTab.xmin[kb] + t) * W));
+                    const float wgt = p.rowTab.w[kb][t];
+                    a.x = fmaf(wgt, v.x, a.x); a.y = fmaf(wgt, v.y, a.y); a.z = fmaf(wgt, v.z, a.z); a.w = fmaf(wgt, v.w, a.w);
+                }
+                *reinterpret_cast<float4*>(vcol + o * pitch) = a;
+            }
+        } else {
+            for (int s = 0; s < NS; ++s) issue();                       // keep the group count in step (empty groups)
+        }
+        if (threadIdx.x == 0 && !p.noise) bulk_wait_read_all();         // previous band's store has read the tile
+        __syncthreads();
+        if (p.noise) mbar_wait(&bar, it & 1);
+
+        // ---- horizontal decimation: sOut[r][j] = sum_t w[t] * sV[r][R*j - OFF + t]  (+ sigma * noise)
+        constexpr int NO = G::NO, NV = G::NV, SKIP = G::SKIP;
+        const int nblk = Wo / NO;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int rgroups = (th + 7) >> 3, bgroups = (nblk + 3) >> 2;
+        for (int wi = warp; wi < rgroups * bgroups; wi += NT / 32) {
+            const int rg = wi % rgroups, bg = wi / rgroups;
+            const int r = 8 * rg + (lane & 7), blk = 4 * bg + (lane >> 3);
+            if (r >= th || blk >= nblk) continue;
+            const float* __restrict__ src = sV + r * pitch + R * NO * blk;
+            float v[4 * NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(src + 4 * q);
+                v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+            }
+            float out[NO];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < T; ++t) a = fmaf(p.wint[t], v[SKIP + R * o + t], a);
+                out[o] = a;
+            }
+            if (blk == 0 || blk == nblk - 1) {                         // the row's first / last two outputs
+                const float* row = sV + r * pitch + G::LPAD;
+                auto border = [&](int kb) {
+                    float a = 0.f;
+                    for (int t = 0; t < p.colTab.xsize[kb]; ++t) a = fmaf(p.colTab.w[kb][t], row[p.colTab.xmin[kb] + t], a);
+                    return a;
+                };
+                if (blk == 0) { out[0] = border(0); out[1] = border(1); }
+                if (blk == nblk - 1) { out[NO - 2] = border(2); out[NO - 1] = border(3); }
+            }
+            float* dst = sOut + r * opitch + NO * blk;
+#pragma unroll
+            for (int q = 0; q < NO / 4; ++q) {
+                float4 o4 = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                if (p.noise) {
+                    const float4 n4 = *reinterpret_cast<const float4*>(dst + 4 * q);
+                    o4.x = fmaf(p.sigma, n4.x, o4.x); o4.y = fmaf(p.sigma, n4.y, o4.y);
+                    o4.z = fmaf(p.sigma, n4.z, o4.z); o4.w = fmaf(p.sigma, n4.w, o4.w);
+                }
+                *reinterpret_cast<float4*>(dst + 4 * q) = o4;
+            }
+        }
+        fence_proxy_async();                    // the tile was written by generic stores; the bulk store reads it
+        __syncthreads();                        // ... and sV is free for the next band's vertical pass
+        if (threadIdx.x == 0) {
+            for (int r = 0; r < th; ++r) bulk_s2g(p.y + oband + (size_t)r * Wo, sOut + r * opitch, (uint32_t)Wo * 4u);
+            bulk_commit();
+        }
+    }
+    cp_async_wait<0>();
+    if (threadIdx.x == 0) bulk_wait_read_all(); // shared memory must stay valid until the engine has read it
+}
+
+// Transpose, "rows" form: gx = A^T gy.  The vertical 4-tap polyphase pass walks down the band with the four gradient
+// rows it needs in rotating registers (each gradient row is loaded from global memory once per band segment, 128-bit
+// read-only loads, nothing staged); the horizontal pass produces 16 (12 at R = 3) consecutive outputs per item from
+// three or four 128-bit shared loads (the round-1 kernel issued four scalar shared loads per OUTPUT and sat at 0.28 -
+// 0.40 of the copy peak).  Rows / columns near the image border go through contributor tables.
+template <int R> struct DownTGeom {
+    static constexpr int OFF = aa_off(R);
+    static constexpr int NO = R == 3 ? 12 : 16;                // outputs per horizontal work item
+    static constexpr int NVJ = NO / R;                          // intermediate columns advanced per item
+    static constexpr int NV = R == 2 ? 4 : 3;                   // 128-bit loads per item
+    static constexpr int LP = 4;                                // left margin of an intermediate row
+    static constexpr int SEGROWS = 4 * R;                       // rows after which the register window is back in place
+};
+
+struct DownTRowsParams {
+    const float* gy;
+    float* gx;
+    int H, W, Ho, Wo, TM, nbands;
+    float wint[kAaMaxTaps];
+    Contrib colL[16], colR[16], rowLo[kBorderRows], rowHi[kBorderRows];
+};
+
+template <int R, int WT>
+__global__ void __launch_bounds__(kDownThreads) down_t_rows_kernel(const __grid_constant__ DownTRowsParams p)
+{
+    using G = DownTGeom<R>;
+    constexpr int OFF = G::OFF, NT = kDownThreads, NO = G::NO, NV = G::NV;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int H = p.H, W = WT ? WT : p.W, Ho = p.Ho, Wo = W / R;
+    const int pitch = blur_pad_pitch_c(G::LP + Wo + 8);
+    float* sV = reinterpret_cast<float*>(smem_raw);                    // [TM][pitch]
+    const int band = blockIdx.x % p.nbands;
+    const long long plane = blockIdx.x / p.nbands;
+    const int m0 = band * p.TM, tm = min(p.TM, H - m0);
+    const float* __restrict__ gplane = p.gy + (size_t)plane * Ho * Wo;
+    const int ML = min(H, 5 * R - OFF), MR0 = max(ML, R * (Ho - 2) - OFF);     // rows outside [ML, MR0) are border rows
+
+    // ---- vertical pass: sV[m][j] = sum_q wint[ph + R q] * gy[ib - q][j],  ph = (m + OFF) % R, ib = (m + OFF) / R
+    const int CWo = Wo >> 2;
+    const int nsegmax = p.TM / G::SEGROWS;
+    const int nseg = CWo >= NT ? 1 : min(nsegmax, NT / CWo);
+    const int TMs = ((nsegmax + nseg - 1) / nseg) * G::SEGROWS;        // rows per segment, a multiple of 4R
+    for (int unit = threadIdx.x; unit < nseg * CWo; unit += NT) {
+        const int seg = unit / CWo, j4 = unit - seg * CWo;
+        const int r_first = seg * TMs;
+        const int nrows = min(TMs, tm - r_first);
+        if (nrows <= 0) continue;
+        const float* __restrict__ colp = gplane + 4 * j4;
+        auto load_row = [&](int i) {
+            return (i >= 0 && i < Ho) ? __ldg(reinterpret_cast<const float4*>(colp + (size_t)i * Wo)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // (m0 + r_first) is a multiple of 4R: the first row has phase OFF % R and window top ib0, ib0 % 4 == (OFF / R) % 4
+        const int ib0 = (m0 + r_first + OFF) / R;
+        constexpr int S0 = (OFF / R) & 3;                               // register slot of gradient row ib0
+        float4 g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[(S0 - q) & 3] = load_row(ib0 - q);
+        float4 nxt = load_row(ib0 + 1);
+        float* vcol = sV + r_first * pitch + G::LP + 4 * j4;
+        for (int rb = 0; rb < nrows; rb += G::SEGROWS) {
+#pragma unroll
+            for (int u = 0; u < G::SEGROWS; ++u) {
+                const int e = OFF % R + u;                              // (m + OFF) - R * ib0 - R * (rb / R)  for this row
+                const int ph = e % R, adv = e / R;                      // window top = ib0 + rb / R + adv
+                if (u > 0 && ph == 0) {                                 // the window advanced by one gradient row
+                    g[(S0 + adv) & 3] = nxt;
+                    nxt = load_row(ib0 + rb / R + adv + 1);
+                }
+                if (rb + u < nrows) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float w = p.wint[ph + R * q];
+                        const float4 v = g[(S0 + adv - q) & 3];
+                        a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+                    }
+                    *reinterpret_cast<float4*>(vcol + (rb + u) * pitch) = a;
+                }
+            }
+            // after 4R rows the window has advanced by 4 gradient rows: slot S0 holds row ib0 + rb / R + 4 again
+            {
+                constexpr int e_end = OFF % R + G::SEGROWS;
+                if (e_end % R == 0) {                                   // the advance that falls on the first row of the next block
+                    g[(S0 + e_end / R) & 3] = nxt;
+                    nxt = load_row(ib0 + rb / R + e_end / R + 1);
+                }
+            }
+        }
+        // border rows of the image: contributor tables, straight from global memory
+        for (int r = 0; r < nrows; ++r) {
+            const int m = m0 + r_first + r;
+            if (m >= ML && m < MR0) continue;
+            const Contrib& c = m < ML ? p.rowLo[m] : p.rowHi[m - MR0];
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < kNQ; ++q) {
+                const float w = c.w[q];
+                if (w != 0.f) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(colp + (size_t)c.idx[q] * Wo));
+                    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+                }
+            }
+            *reinterpret_cast<float4*>(vcol + r * pitch) = a;
+        }
+    }
+    // contributor tables of the border columns -> shared memory (per-lane indexing of kernel parameters serialises in
+    // the constant cache: ncu showed 26 % of the stall samples on those loads)
+    Contrib* sCol = reinterpret_cast<Contrib*>(sV + p.TM * pitch);         // [2 * NO]
+    for (int e = threadIdx.x; e < 2 * NO; e += NT) sCol[e] = e < NO ? p.colL[e] : p.colR[e - NO];
+    __syncthreads();
+
+    // ---- horizontal pass: gx[m][n] = sum_q wint[(n + OFF) % R + R q] * sV[m][(n + OFF) / R - q]
+    float* __restrict__ oplane = p.gx + ((size_t)plane * H + m0) * W;
+    const int ngrp = W / NO;
+    if constexpr (R == 3) {
+        // 12 outputs per item (the phase pattern of 4 outputs is not static at R = 3)
+        const int ngi = ngrp - 2;                    // interior groups: 1 .. ngrp - 2
+        for (int item = threadIdx.x; item < tm * ngi; item += NT) {
+            const int u = 1 + item % ngi, r = item / ngi;
+            const float* row = sV + r * pitch + G::LP;
+            float v[4 * NV];
+            const float* src = row + G::NVJ * u - 4;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(src + 4 * q);
+                v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+            }
+            float out[NO];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                const int ph = (o + OFF) % R, jl = (o + OFF) / R + 4;
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a = fmaf(p.wint[ph + R * q], v[jl - q], a);
+                out[o] = a;
+            }
+            float* dst = oplane + (size_t)r * W + NO * u;
+#pragma unroll
+            for (int q = 0; q < NO / 4; ++q) st_stream4(dst + 4 * q, make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
+        }
+    } else {
+        // R = 2, 4: one 128-bit store per item, neighbouring lanes write neighbouring vectors (512 contiguous bytes per
+        // warp instruction; 16-output items left every store instruction touching half sectors: ncu, 45 % excess
+        // sectors).  The 4 outputs of vector g read the intermediate columns (4 / R) g - 2 .. + NVAL - 1 of their row.
+        constexpr int NVAL = R == 2 ? 6 : 5;
+        constexpr int GB = NO / 4;                   // border vectors per side (handled through the tables below)
+        const int ngv = W / 4 - 2 * GB;
+        for (int item = threadIdx.x; item < tm * ngv; item += NT) {
+            const int g = GB + item % ngv, r = item / ngv;
+            const float* src = sV + r * pitch + G::LP + (4 / R) * g - 2;
+            float v[NVAL];
+            if constexpr (R == 2) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float2 t2 = *reinterpret_cast<const float2*>(src + 2 * q);
+                    v[2 * q] = t2.x; v[2 * q + 1] = t2.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NVAL; ++q) v[q] = src[q];
+            }
+            float out[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int ph = (o + OFF) % R, jl = (o + OFF) / R - OFF / R + 3;
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a = fmaf(p.wint[ph + R * q], v[jl - q], a);
+                out[o] = a;
+            }
+            st_stream4(oplane + (size_t)r * W + 4 * g, make_float4(out[0], out[1], out[2], out[3]));
+        }
+    }
+    // the first and the last group of every row contain the border columns: one thread per output, contributor tables
+    for (int item = threadIdx.x; item < tm * 2 * NO; item += NT) {
+        const int r = item / (2 * NO), e = item - r * 2 * NO;
+        const Contrib c = sCol[e];
+        const int n = e < NO ? e : W - 2 * NO + e;
+        const float* row = sV + r * pitch + G::LP;
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q)
+            if (c.w[q] != 0.f) a = fmaf(c.w[q], row[c.idx[q]], a);
+        oplane[(size_t)r * W + n] = a;
+    }
+}
+
 // ------------------------------------------------------------------ direct kernels (any shape)
 struct DownDirectParams {
     const float* x;
@@ -537,6 +1127,77 @@ static int launch_down(const DownParams& p, long long planes, size_t smem, cudaS
     return launch_down_w<R, 0>(p, planes, smem, st, transpose);
 }
 
+
+static size_t down_rows_smem(int th, int W, int Wo, int rate)
+{
+    // ring: the persistent kernel (input widths up to 1024) keeps kDownStreamDepth steps of R * JO rows (JO = 2 at x2),
+    // the one-band kernel RING steps of R rows
+    const int lpad = 4 * ((aa_off(rate) + 3) / 4);
+    const int ring_rows = W / 4 <= kDownThreads ? kDownStreamDepth * (rate == 2 ? 4 : rate) : (rate <= 2 ? 6 * rate : 4 * rate);
+    return ((size_t)th * blur_pad_pitch_c(Wo) + (size_t)th * down_v_pitch(W, lpad)) * 4 + (size_t)ring_rows * kDownThreads * 16;
+}
+
+template <int R, int WT, int TH>
+static int launch_down_rows_inst(const DownRowsParams& q, long long planes, cudaStream_t st)
+{
+    const int W = q.W, Wo = q.Wo;
+    const size_t smem = down_rows_smem(TH, W, Wo, R);
+    if (W / 4 <= kDownThreads) {
+        DeviceProps dp;
+        int rc = get_device_props(&dp);
+        if (rc) return rc;
+        const long long items = planes * q.nbands;
+        const int per_sm = std::max(1, std::min(2, (int)((size_t)227 * 1024 / (smem + 1024))));
+        const unsigned grid = (unsigned)std::min<long long>(items, (long long)dp.sm_count * per_sm);
+        SEI_CUDA(allow_smem(down_stream_kernel<R, WT, TH>, smem));
+        down_stream_kernel<R, WT, TH><<<grid, kDownThreads, smem, st>>>(q, items);
+        return finish_launch(q.noise ? "down_rows_kernel<noise>" : "down_rows_kernel");
+    }
+    SEI_CUDA(allow_smem(down_rows_kernel<R, WT, TH>, smem));
+    down_rows_kernel<R, WT, TH><<<(unsigned)(planes * q.nbands), kDownThreads, smem, st>>>(q);
+    return finish_launch(q.noise ? "down_rows_kernel<noise>" : "down_rows_kernel");
+}
+
+template <int R>
+static int launch_down_rows(DownRowsParams& q, long long planes, int th, cudaStream_t st)
+{
+    q.nbands = (q.Ho + th - 1) / th;
+    if (th == 16) {
+        if (q.W == 256 * R) return launch_down_rows_inst<R, 256 * R, 16>(q, planes, st);
+        return launch_down_rows_inst<R, 0, 16>(q, planes, st);
+    }
+    if (q.W == 256 * R) return launch_down_rows_inst<R, 256 * R, 8>(q, planes, st);
+    return launch_down_rows_inst<R, 0, 8>(q, planes, st);
+}
+
+template <int R>
+static int launch_down_t_rows(DownTRowsParams& q, long long planes, size_t smem, cudaStream_t st)
+{
+    using G = DownTGeom<R>;
+    for (int o = 0; o < G::NO; ++o) {
+        aa_contributors(o, q.W, q.Wo, R, q.colL[o]);
+        aa_contributors(q.W - G::NO + o, q.W, q.Wo, R, q.colR[o]);
+    }
+    const int ML = std::min(q.H, 5 * R - G::OFF), MR0 = std::max(ML, R * (q.Ho - 2) - G::OFF);
+    for (int m = 0; m < ML; ++m) aa_contributors(m, q.H, q.Ho, R, q.rowLo[m]);
+    for (int m = MR0; m < q.H; ++m) aa_contributors(m, q.H, q.Ho, R, q.rowHi[m - MR0]);
+    const unsigned grid = (unsigned)(planes * q.nbands);
+    if (q.W == 256 * R) {
+        SEI_CUDA(allow_smem(down_t_rows_kernel<R, 256 * R>, smem));
+        down_t_rows_kernel<R, 256 * R><<<grid, kDownThreads, smem, st>>>(q);
+    } else {
+        SEI_CUDA(allow_smem(down_t_rows_kernel<R, 0>, smem));
+        down_t_rows_kernel<R, 0><<<grid, kDownThreads, smem, st>>>(q);
+    }
+    return finish_launch("down_t_rows_kernel");
+}
+
+static int env_int_down(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
 static int down_common(const float* in, float* out, long long planes, int H, int W, int rate,
                        const float* noise, float sigma, int path, void* stream, bool transpose)
 {
@@ -558,6 +1219,57 @@ static int down_common(const float* in, float* out, long long planes, int H, int
 
     bool tiled_ok = (W % (4 * rate) == 0) && Wo >= 8 && Ho >= 4 && aligned16(in) && aligned16(out) &&
                     (!noise || aligned16(noise));
+
+    // ---- round-2 "rows" kernels (vertical pass first, straight from global memory); SEI_DOWN_V1=1 selects round 1's
+    const bool v1 = env_int_down("SEI_DOWN_V1", 0) == 1;
+    if (tiled_ok && !v1 && path != SEI_PATH_DIRECT && !transpose && Wo % 8 == 0 && W <= 4096) {
+        DownRowsParams q;
+        q.x = in; q.y = out; q.noise = noise; q.sigma = sigma; q.H = H; q.W = W; q.Ho = Ho; q.Wo = Wo;
+        for (int t = 0; t < kAaMaxTaps; ++t) q.wint[t] = p.wint[t];
+        for (int k = 0; k < 4; ++k) {
+            aa_axis_weights(k < 2 ? k : Wo - 4 + k, W, rate, q.colTab.w[k], q.colTab.xmin[k], q.colTab.xsize[k]);
+            aa_axis_weights(k < 2 ? k : Ho - 4 + k, H, rate, q.rowTab.w[k], q.rowTab.xmin[k], q.rowTab.xsize[k]);
+        }
+        // band height: 16 output rows at x2; 8 at x3 / x4, where the intermediate band is 4 KB per row and four CTAs
+        // per SM (instead of two) hide the global-load latency of the vertical pass better (x4: 33.6 vs 42.2 us)
+        int th = env_int_down("SEI_DOWN_ROWS_TH", rate >= 3 ? 8 : 16);
+        th = th == 8 ? 8 : 16;
+        if (down_rows_smem(th, W, Wo, rate) > (size_t)dp.smem_optin) th = 8;
+        if (down_rows_smem(th, W, Wo, rate) <= (size_t)dp.smem_optin &&
+            planes * ((Ho + th - 1) / th) < (1ll << 31)) {
+            switch (rate) {
+            case 2: return launch_down_rows<2>(q, planes, th, st);
+            case 3: return launch_down_rows<3>(q, planes, th, st);
+            default: return launch_down_rows<4>(q, planes, th, st);
+            }
+        }
+    }
+    if (tiled_ok && !v1 && path != SEI_PATH_DIRECT && transpose && W % (rate == 3 ? 12 : 16) == 0 && Wo >= 16 &&
+        H >= 8 * rate && Ho >= 8) {
+        DownTRowsParams q;
+        q.gy = in; q.gx = out; q.H = H; q.W = W; q.Ho = Ho; q.Wo = Wo;
+        for (int t = 0; t < kAaMaxTaps; ++t) q.wint[t] = p.wint[t];
+        const int segrows = 4 * rate;
+        int tm = env_int_down("SEI_DOWNT_ROWS_TM", 0);
+        if (tm <= 0 || tm % segrows) {
+            // every thread should own a column group: 256 threads / (Wo / 4) groups = segments of 4R rows each
+            const int nseg = std::max(1, kDownThreads / std::max(1, Wo / 4));
+            tm = segrows * nseg;
+            while (tm < 32) tm *= 2;
+        }
+        const size_t smem_t = (size_t)tm * blur_pad_pitch_c(4 + Wo + 8) * 4 + 32 * sizeof(Contrib);
+        const int ML = std::min(H, 5 * rate - aa_off(rate)), MR0 = std::max(ML, rate * (Ho - 2) - aa_off(rate));
+        if (smem_t <= (size_t)dp.smem_optin && ML <= kBorderRows && H - MR0 <= kBorderRows &&
+            planes * ((H + tm - 1) / tm) < (1ll << 31)) {
+            q.TM = tm;
+            q.nbands = (H + tm - 1) / tm;
+            switch (rate) {
+            case 2: return launch_down_t_rows<2>(q, planes, smem_t, st);
+            case 3: return launch_down_t_rows<3>(q, planes, smem_t, st);
+            default: return launch_down_t_rows<4>(q, planes, smem_t, st);
+            }
+        }
+    }
     size_t smem = 0;
     if (tiled_ok) {
         const size_t budget_dflt = getenv("SEI_DOWN_SMEM_KB") ? (size_t)atoi(getenv("SEI_DOWN_SMEM_KB")) * 1024 : (size_t)110 * 1024;

@@ -189,6 +189,126 @@ __global__ void __launch_bounds__(kScaleThreads, 2) scale_band_kernel(const __gr
     }
 }
 
+
+// ------------------------------------------------------------------ rows kernel (round 2)
+// One CTA = one band of TH output rows of ALL C planes of one image (the taps of an image are shared by its planes).
+// Nothing is staged by copies: the vertical 4-tap pass reads its source rows straight from global memory with 128-bit
+// read-only loads (the taps of neighbouring output rows overlap, so about half of them hit L1), 8 independent loads in
+// flight per thread; its result goes to a shared intermediate (double-buffered across planes: one barrier per plane)
+// from which the horizontal 4-tap gather produces coalesced streaming stores.  ~45 KB of shared memory and no mbarrier
+// round trips: four CTAs (1024 threads) per SM hide the gather latency that bound the staged kernel of round 1
+// (ncu: issue slots 35 %, shared pipe 65 %, occupancy 24 %; 75 -> 59 us).
+// The intermediate keeps round 1's even / odd column split (scale_tmp_pos).  A simulation of the gather's bank
+// pattern over the reference's rates and random centres (32 lanes read 32 words spread over 43 - 64 columns) gives 1.24
+// wavefronts per instruction at rate 0.5 and 1.87 at 0.75 for it; no layout of the families (c mod m) * Q + c / m,
+// m = 1, 2, 4, 8, does better on both (a 4-way split with Q = 8 mod 32 was built and measured: 1.51 / 1.89, same time).  A sliding-window vertical pass (only the source rows that enter the 4-row window
+// of the next output row are loaded: 1.5 - 2.2 loads per output vector instead of 4) was built and measured as well:
+// it halves the L1 traffic of the pass but its serial walk and register rotation cost more issue slots than the loads
+// saved (71 us against 59 us), so the independent-loads form stayed.
+struct ScaleRowsParams {
+    const float* x;
+    float* out;
+    const float* rate;
+    const float* center;
+    int C, S, nbands;
+    float two_over_S;
+};
+
+template <int ST, int TH>
+__global__ void __launch_bounds__(kScaleThreads, 4) scale_rows_kernel(const __grid_constant__ ScaleRowsParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int S = ST ? ST : p.S;
+    float* sV = reinterpret_cast<float*>(smem_raw);                              // [2][TH][TP]
+    AxisTap* colT = reinterpret_cast<AxisTap*>(sV + 2 * TH * scale_tmp_pitch(S));   // [S]  (idx = position in a V row)
+    AxisTap* rowT = colT + S;                                                    // [TH] (idx = row offset in elements)
+
+    const int band = blockIdx.x % p.nbands;
+    const int b = blockIdx.x / p.nbands;
+    const int r0 = band * TH, th = min(TH, S - r0);
+    const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
+    const float cx = __ldg(p.center + 2 * b), cy = __ldg(p.center + 2 * b + 1);
+    const int TP = scale_tmp_pitch(S), HALF = scale_tmp_half(S);   // compile-time for the specialised sizes
+
+    for (int j = threadIdx.x; j < S + TH; j += kScaleThreads) {
+        AxisTap t;
+        if (j < S) {
+            scale_axis_tap(j, S, p.two_over_S, inv_rate, cx, t);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) t.idx[a] = scale_tmp_pos(t.idx[a], S);
+            colT[j] = t;
+        } else if (j - S < th) {
+            scale_axis_tap(r0 + j - S, S, p.two_over_S, inv_rate, cy, t);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) t.idx[a] *= S;
+            rowT[j - S] = t;
+        }
+    }
+    __syncthreads();
+
+    const int CW = S >> 2;
+    const size_t plane_elems = (size_t)S * S;
+    for (int c = 0; c < p.C; ++c) {
+        const float* __restrict__ xp = p.x + ((size_t)b * p.C + c) * plane_elems;
+        float* __restrict__ V = sV + (c & 1) * TH * TP;
+        // ---- vertical pass: V[r][pos(col)] = sum_a wy[r][a] * x[iy[r][a]][col]
+        constexpr int kItems = 2;                      // work items per thread whose loads are issued together
+        const int nitems = th * CW;
+        for (int base = threadIdx.x; base < nitems; base += kItems * kScaleThreads) {
+            float4 v[kItems][4];
+            float w[kItems][4];
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const int item = base + k * kScaleThreads;
+                if (item < nitems) {
+                    const int r = item / CW, c4 = item - r * CW;
+                    const AxisTap t = rowT[r];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        v[k][a] = __ldg(reinterpret_cast<const float4*>(xp + t.idx[a] + 4 * c4));
+                        w[k][a] = t.w[a];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const int item = base + k * kScaleThreads;
+                if (item < nitems) {
+                    const int r = item / CW, c4 = item - r * CW;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        acc.x = fmaf(w[k][a], v[k][a].x, acc.x); acc.y = fmaf(w[k][a], v[k][a].y, acc.y);
+                        acc.z = fmaf(w[k][a], v[k][a].z, acc.z); acc.w = fmaf(w[k][a], v[k][a].w, acc.w);
+                    }
+                    float* d = V + r * TP + 2 * c4;
+                    *reinterpret_cast<float2*>(d) = make_float2(acc.x, acc.z);             // columns 4c4, 4c4+2
+                    *reinterpret_cast<float2*>(d + HALF) = make_float2(acc.y, acc.w);      // columns 4c4+1, 4c4+3
+                }
+            }
+        }
+        __syncthreads();
+        // ---- horizontal pass: out[r][j] = sum_b wx[j][b] * V[r][pos(ix[j][b])]
+        float* __restrict__ oplane = p.out + ((size_t)b * p.C + c) * plane_elems + (size_t)r0 * S;
+        for (int j = threadIdx.x; j < S; j += kScaleThreads) {
+            const AxisTap t = colT[j];
+            if (th == TH) {
+#pragma unroll
+                for (int r = 0; r < TH; ++r) __stcs(oplane + r * S + j, scale_hgather(V + r * TP, t));
+            } else {
+                for (int r = 0; r < th; ++r) __stcs(oplane + r * S + j, scale_hgather(V + r * TP, t));
+            }
+        }
+        // no barrier here: the next plane's vertical pass writes the other buffer, and the barrier after it orders
+        // this plane's reads before the writes of the plane after next
+    }
+}
+
+static size_t scale_rows_smem(int th, int S)
+{
+    return (size_t)2 * th * scale_tmp_pitch(S) * 4 + (size_t)(S + th) * sizeof(AxisTap);
+}
+
 struct ScaleDirectParams {
     const float* x;
     float* out;
@@ -323,8 +443,37 @@ extern "C" int sei_scale_transform_f32(const float* x, float* out, int B, int C,
     size_t smem = 0;
     const int TH = (S % 4 == 0 && S >= 8 && aligned16(x) && aligned16(out)) ? scale_pick_band_rows(S, dp.smem_optin, &smem) : 0;
     const bool tiled_ok = TH > 0 && TH <= kScaleThreads && planes * ((S + TH - 1) / TH) < (1ll << 31);
-    SEI_REQUIRE(path != SEI_PATH_TILED || tiled_ok, "tiled scale-transform path not available for S=%d", S);
     const float two_over_S = (float)(2.0 / (double)S);
+    const char* v1 = getenv("SEI_SCALE_V1");              // A/B switch: the staged (TMA) band kernel of round 1
+    const bool rows_ok = S % 4 == 0 && S >= 8 && S <= 2048 && aligned16(x) && aligned16(out) && (long long)B * ((S + 7) / 8) < (1ll << 31);
+    SEI_REQUIRE(path != SEI_PATH_TILED || tiled_ok || rows_ok, "tiled scale-transform path not available for S=%d", S);
+    if (rows_ok && path != SEI_PATH_DIRECT && !(v1 && *v1 == '1' && tiled_ok)) {
+        ScaleRowsParams q;
+        q.x = x; q.out = out; q.rate = rate; q.center = center; q.C = C; q.S = S; q.two_over_S = two_over_S;
+        const int th_env = getenv("SEI_SCALE_ROWS_TH") ? atoi(getenv("SEI_SCALE_ROWS_TH")) : 0;
+        const int THr = th_env == 8 || th_env == 16 ? th_env : (S <= 256 ? 16 : 8);
+        q.nbands = (S + THr - 1) / THr;
+        const size_t sm = scale_rows_smem(THr, S);
+        SEI_REQUIRE(sm <= (size_t)dp.smem_optin, "scale transform: S=%d needs %zu bytes of shared memory", S, sm);
+        const unsigned grid = (unsigned)((long long)B * q.nbands);
+        if (S == 256 && THr == 16) {
+            SEI_CUDA(allow_smem(scale_rows_kernel<256, 16>, sm));
+            scale_rows_kernel<256, 16><<<grid, kScaleThreads, sm, st>>>(q);
+        } else if (S == 256 && THr == 8) {
+            SEI_CUDA(allow_smem(scale_rows_kernel<256, 8>, sm));
+            scale_rows_kernel<256, 8><<<grid, kScaleThreads, sm, st>>>(q);
+        } else if (S == 512 && THr == 8) {
+            SEI_CUDA(allow_smem(scale_rows_kernel<512, 8>, sm));
+            scale_rows_kernel<512, 8><<<grid, kScaleThreads, sm, st>>>(q);
+        } else if (THr == 16) {
+            SEI_CUDA(allow_smem(scale_rows_kernel<0, 16>, sm));
+            scale_rows_kernel<0, 16><<<grid, kScaleThreads, sm, st>>>(q);
+        } else {
+            SEI_CUDA(allow_smem(scale_rows_kernel<0, 8>, sm));
+            scale_rows_kernel<0, 8><<<grid, kScaleThreads, sm, st>>>(q);
+        }
+        return finish_launch("scale_rows_kernel");
+    }
     if (tiled_ok && path != SEI_PATH_DIRECT) {
         ScaleParams p;
         p.x = x; p.out = out; p.rate = rate; p.center = center;

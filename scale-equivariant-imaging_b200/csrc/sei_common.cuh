@@ -122,6 +122,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// per-thread asynchronous 16-byte copy global -> shared (LDGSTS, bypassing L1); !valid: the 16 bytes are zero-filled
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr uint32_t kBulkChunkBytes = 32768;
 
 // Copy `nrows` consecutive rows of a row-major plane (row pitch = row_bytes, a multiple of
@@ -219,6 +228,9 @@ SEI_HD float aa_cubic(float x)
     return 0.0f;
 }
 
+// smallest n' >= n with n' = 4 (mod 32): consecutive rows of such a pitch start one 16-byte bank group apart
+__host__ __device__ constexpr int blur_pad_pitch_c(int n) { return n + ((4 - n % 32) + 32) % 32; }
+
 constexpr int kAaMaxTaps = 16;   // 4 * rate, rate <= 4
 
 // weights of output index i of the antialiased bicubic decimation along one axis
@@ -255,8 +267,14 @@ SEI_HD int reflect_clip(int idx, int S)
     if (S == 1) return 0;
     const int span = S - 1;
     int v = idx < 0 ? -idx : idx;
-    const int flips = v / span, extra = v - flips * span;
-    v = (flips & 1) ? span - extra : extra;
+    if (v > span) {
+        if (v <= 2 * span) {
+            v = 2 * span - v;      // one fold: every tap of the reference's rates (>= 0.5) lands here, no division
+        } else {
+            const int flips = v / span, extra = v - flips * span;
+            v = (flips & 1) ? span - extra : extra;
+        }
+    }
     return v < 0 ? 0 : (v > S - 1 ? S - 1 : v);
 }
 

@@ -59,32 +59,29 @@ def _require_device_rows(t, what):
                        "only -- there is no CPU / library fallback")
 
 
-def _pad_channels(xl):
-    """(B, H, W, C) -> (B, H, W, C8) zero-padded to a multiple of 8 channels (a copy only when C % 8 != 0)"""
+def _pad_channels(xl, to=None):
+    """(..., C) -> (..., C') zero-padded to `to` channels (default: the next multiple of 8); a copy only when C' != C"""
     c = xl.shape[-1]
-    return xl if c % 8 == 0 else F.pad(xl, (0, 8 - c % 8))
+    to = to or -(-c // 8) * 8
+    return xl if to == c else F.pad(xl, (0, to - c))
 
 
 def _op_layer_norm(rows, ln):
     """channel LayerNorm of rows [T, C] (ln_fwd_kernel / ln_small kernels, csrc/cnn_elem.cu)"""
     _require_device_rows(rows, "LayerNorm")
-    if not ops.ln_any_supported(rows):
-        raise SeiError(f"LayerNorm over {rows.shape[1]} channels: the kernels take C <= 32 or C % 8 == 0 up to 8192")
-    return ops.layer_norm_cl(rows, ln.weight, ln.bias, ln.eps)
+    return ops.layer_norm_cl(rows.contiguous(), ln.weight, ln.bias, ln.eps)
 
 
 def _op_dwconv7(xl, conv):
     """depthwise 7x7, padding 3, on a channels-last (B, H, W, C) tensor (dwconv7_kernel)"""
     _require_device_rows(xl, "depthwise 7x7 convolution")
     c = xl.shape[-1]
-    if c % 8 == 0:
-        if not ops.dwconv7_supported(xl):
-            raise SeiError(f"depthwise 7x7 convolution over {c} channels is not built")
-        return ops.dwconv7(xl, conv.weight, conv.bias)
-    pad = 8 - c % 8
-    w = F.pad(conv.weight, (0, 0, 0, 0, 0, 0, 0, pad))
-    b = None if conv.bias is None else F.pad(conv.bias, (0, pad))
-    return ops.dwconv7(_pad_channels(xl).contiguous(), w, b)[..., :c]
+    cp = ops.padded_width(c, "dwconv7")            # channels are independent: zero-padded ones are exact and dropped
+    if cp == c:
+        return ops.dwconv7(xl.contiguous(), conv.weight, conv.bias)
+    w = F.pad(conv.weight, (0, 0, 0, 0, 0, 0, 0, cp - c))
+    b = None if conv.bias is None else F.pad(conv.bias, (0, cp - c))
+    return ops.dwconv7(_pad_channels(xl, cp).contiguous(), w, b)[..., :c]
 
 
 def _op_gelu(x):
@@ -119,10 +116,9 @@ def _op_bias_pattern(out, rows, pat, bias):
     """out[b, c, i, j] += pat[i, j] * bias[c] on the rows view of a channels-last GEMM output (bias_pattern_add_kernel)"""
     _require_device_rows(rows, "Downsample bias")
     c = rows.shape[1]
-    if c % 8 != 0:                                   # edge layers of the no-in/out-conv variant: pad the columns
-        rows, bias = _pad_k(rows), F.pad(bias, (0, 8 - c % 8))
-    if not ops.ln_cl_supported(rows):
-        raise SeiError(f"Downsample bias over {c} channels: the kernel does not tile this width")
+    cp = ops.padded_width(c, "colsum")               # widths of the no-in/out-conv variant: pad the columns
+    if cp != c:
+        rows, bias = _pad_channels(rows, cp).contiguous(), F.pad(bias, (0, cp - c))
     rows = ops.bias_pattern_add(rows, pat.reshape(-1), bias)[:, :c]
     return rows.reshape(out.shape[0], out.shape[2], out.shape[3], c).permute(0, 3, 1, 2)
 
@@ -205,10 +201,7 @@ def _colsum(gy):
     a multiple of 8 for the 3-channel edge layers"""
     n = gy.shape[1]
     _require_device_rows(gy, "bias gradient")
-    g8 = _pad_k(gy)
-    if not ops.ln_cl_supported(g8):
-        raise SeiError(f"bias gradient over {n} channels: the column-sum kernel does not tile this width")
-    return ops.colsum_bf16(g8)[:n]
+    return ops.colsum_bf16(_pad_channels(gy, ops.padded_width(n, "colsum")).contiguous())[:n]
 
 
 def _pad_k(a):

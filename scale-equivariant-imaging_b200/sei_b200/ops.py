@@ -396,10 +396,22 @@ def ln_cl_supported(x_rows):
 
 
 def ln_any_supported(x_rows):
-    """rows the channel LayerNorm kernels take: the vectorised ones (ln_cl_supported) or, for up to 32 channels of any
-    count, the one-thread-per-row ones"""
+    """rows the channel LayerNorm kernels take: the vectorised ones (ln_cl_supported), the one-thread-per-row ones (up to
+    32 channels) or the one-warp-per-row ones (any other count)"""
     return ln_cl_supported(x_rows) or (x_rows.is_cuda and x_rows.dtype == torch.bfloat16 and x_rows.dim() == 2
-                                       and x_rows.is_contiguous() and 1 <= x_rows.shape[1] <= 32)
+                                       and x_rows.is_contiguous() and 1 <= x_rows.shape[1] <= 65536)
+
+
+def padded_width(c, kind):
+    """smallest channel count >= c that the vectorised kernels of `kind` ("colsum": column sums / bias pattern,
+    "dwconv7") tile; zero-padded channels are exact for these per-channel operators"""
+    lib = _lib.load()
+    fn = lib.sei_ln_cl_backward_workspace_bytes if kind == "colsum" else lib.sei_dwconv7_workspace_bytes
+    c8 = -(-int(c) // 8) * 8
+    for cand in range(c8, c8 + 4096, 8):
+        if fn(cand) > 0:
+            return cand
+    raise SeiError(f"no supported channel count at or above {c} for {kind}")
 
 
 class _LayerNormCL(torch.autograd.Function):

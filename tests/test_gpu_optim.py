@@ -1,6 +1,8 @@
 """sei_b200.optim.Adam (csrc/optim.cu) against torch.optim.Adam on identical parameters and gradients: five steps,
 fp32 parameters within 2e-6 relative; the bf16 shadows equal the rounded parameters bit for bit; the transposed
 shadow equals their transpose; a captured CUDA graph of step() keeps advancing the device-side step count."""
+import copy
+
 import pytest
 import torch
 
@@ -108,13 +110,14 @@ def test_adam_loads_torch_and_cpu_state_dicts(dev, tmp_path):
     for variant in ("torch_state", "cpu_checkpoint", "python_step"):
         p2 = torch.nn.Parameter(q.detach().clone())
         ours = Adam([p2], lr=1e-2)
-        state = torch.load(path, map_location="cpu") if variant != "torch_state" else ref.state_dict()
+        # (a live state_dict() shares its tensors with the optimizer it came from: load a deep copy, as a resume would)
+        state = torch.load(path, map_location="cpu") if variant != "torch_state" else copy.deepcopy(ref.state_dict())
         if variant == "python_step":
             state["state"][0]["step"] = float(state["state"][0]["step"])
         ours.load_state_dict(state)
         q3 = torch.nn.Parameter(q.detach().clone())
         ref3 = torch.optim.Adam([q3], lr=1e-2)
-        ref3.load_state_dict(ref.state_dict())
+        ref3.load_state_dict(copy.deepcopy(ref.state_dict()))
         for g in grads[2:]:
             p2.grad, q3.grad = g.clone(), g.clone()
             ours.step()

@@ -72,7 +72,7 @@ def test_argument_validation_needs_no_device():
     # the CNN-side entry points validate before touching a device as well
     assert lib.sei_ln_cl_forward_bf16(None, None, None, None, None, None, 4, 32, 1e-6, None) == -22
     assert lib.sei_ln_cl_forward_bf16(1, 1, 1, 1, 1, 1, 4, 12, 1e-6, None) == -22 and b"multiple of 8" in lib.sei_last_error()
-    assert lib.sei_ln_small_forward_bf16(1, 1, 1, 1, 1, 1, 4, 33, 1e-6, None) == -22
+    assert lib.sei_ln_small_forward_bf16(1, 1, 1, 1, 1, 1, 4, 0, 1e-6, None) == -22          # (any C >= 1 is taken: 1..32 one thread per row, above one warp per row)
     assert lib.sei_dwconv7_cl_bf16(None, None, None, None, 1, 8, 8, 8, None) == -22
     assert lib.sei_dwconv7_cl_bf16(16, 16, None, 16, 1, 8, 8, 12, None) == -22
     assert lib.sei_conv3x3_small_forward_bf16(16, 16, None, 16, 1, 8, 8, 32, 5, None) == -22 and b"Cout" in lib.sei_last_error()
