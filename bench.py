@@ -146,6 +146,7 @@ def bench_config(args, world):
     """`config` of the JSON line; the reference arm prints the B200 arm's config verbatim (same workload, same network)"""
     return {"workload": WORKLOAD.replace("batch 32", f"batch {args.batch}"),
             "network": network_description(args), "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "dp_mode": args.dp_mode if world > 1 else "none",
             "l2": "inputs rotate over 8 resident batches (2 x 8 x 25 MB > 126 MB L2)"}
 
 
@@ -193,19 +194,31 @@ def run_b200(args):
     host_y = [y.cpu().pin_memory() for y in ys[:2]]
     x_static, y_static = torch.empty_like(xs[0]), torch.empty_like(ys[0])
     loss_static = torch.zeros((), device=dev)
-    reducer = parallel.GradAllReducer(params)      # bucketed NCCL all-reduce (average), overlapped with the backward pass
+    # gradient buckets follow the module tree (sei_b200.parallel.completion_groups) so that each can be all-reduced as
+    # soon as the backward pass has produced it
+    reducer = parallel.GradAllReducer(params, module=model if args.dp_mode == "overlap" else None)
 
-    def fwd_bwd():
+    # Data-parallel modes (--dp-mode, only matters for N > 1):
+    #   overlap: forward + backward + the per-group gradient all-reduces (launched from inside backward() on NCCL's
+    #            stream, overlapping the rest of the backward pass) + Adam captured as ONE CUDA graph;
+    #   serial:  round 1's scheme -- graph(forward + backward), one eager all-reduce of every bucket, graph(Adam).
+    overlap = args.dp_mode == "overlap" and world > 1
+
+    def fwd_bwd(reduce_inside):
         opt.zero_grad(set_to_none=False)
         loss = loss_fn(x=x_static, y=y_static, model=model)
-        reducer.arm()
+        if reduce_inside:
+            reducer.arm()
         loss.backward()
-        reducer.finish()
+        if reduce_inside:
+            reducer.finish()
         loss_static.copy_(loss.detach())
 
-    # capture forward+backward (+ the gradient all-reduce) and the optimizer step as ONE CUDA graph
+    # Capturing torch's NCCL collectives in a CUDA graph hangs on this stack (torch 2.11 / NCCL 2.28.9, both from the
+    # autograd thread and deferred to the capturing thread behind events; measured twice on 2 GPUs), so the overlapped
+    # mode runs forward + backward eagerly and only the optimizer step as a graph.
     use_graph = not args.no_graph
-    g_step = None
+    g_step = g_opt = None
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     launches_per_step, flops_per_step = 0, 0.0
@@ -213,7 +226,10 @@ def run_b200(args):
         x_static.copy_(xs[0]); y_static.copy_(ys[0])
         for _ in range(3):
             n_before, f_before = sei_b200.launch_count(), ops.flop_count()
-            fwd_bwd(); opt.step()
+            fwd_bwd(overlap)
+            if not overlap:
+                reducer()
+            opt.step()
             launches_per_step = sei_b200.launch_count() - n_before
             flops_per_step = ops.flop_count() - f_before
     torch.cuda.current_stream().wait_stream(side)
@@ -226,11 +242,22 @@ def run_b200(args):
     if use_graph:
         try:
             g_step = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_step, stream=side):
-                fwd_bwd(); opt.step()
+            # thread_local: NCCL's watchdog thread keeps making CUDA calls while this thread captures
+            mode = dict(capture_error_mode="thread_local") if world > 1 else {}
+            if not overlap:
+                with torch.cuda.graph(g_step, stream=side, **mode):
+                    fwd_bwd(False)
+                    if world == 1:
+                        opt.step()
+            else:
+                g_step = None
+            if world > 1:
+                g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_opt, stream=side, **mode):
+                    opt.step()
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {str(e)[:200]}); running eagerly", file=sys.stderr)
-            g_step = None
+            g_step = g_opt = None
             torch.cuda.synchronize()
             gc.collect()
             torch.cuda.empty_cache()
@@ -241,7 +268,13 @@ def run_b200(args):
         if g_step is not None:
             g_step.replay()
         else:
-            fwd_bwd(); opt.step()
+            fwd_bwd(overlap)
+        if world > 1 and not overlap:
+            reducer()
+        if g_opt is not None:
+            g_opt.replay()
+        elif g_step is None or world > 1:
+            opt.step()
 
     def step_resident(i):
         x_static.copy_(xs[i % NBUF]); y_static.copy_(ys[i % NBUF])
@@ -357,7 +390,7 @@ def run_b200(args):
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 network (fp32 accumulate), f32 operators" if args.network == "cnn" else "f32", "data": "synthetic",
         "config": bench_config(args, world),
-        "n_params": n_params, "cuda_graph": g_step is not None, "final_loss": final_loss,
+        "n_params": n_params, "cuda_graph": g_step is not None or g_opt is not None, "final_loss": final_loss,
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "imgs/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": int(2 * xs[0].numel() * 4), "d2h_bytes_per_step": 4,
                 "how": "losses.get_loss(...)(x, y, model) + backward + Adam from pinned host x,y; loss.item() each step"},
@@ -559,6 +592,8 @@ def main():
     ap.add_argument("--cnn-scales", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dp-mode", default="serial", choices=["overlap", "serial"],
+                    help="N > 1: all-reduce the gradient buckets from inside backward() (one captured graph) or after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=200.0,
                     help="--impl reference: wall-clock budget of the whole K + W step run (sizes the per-step sample)")

@@ -84,6 +84,12 @@ int sei_down_aa_transpose_f32(const float* gy, float* gx, long long planes, int 
 int sei_up_bicubic_f32(const float* y, float* x, long long planes, int h, int w, int rate,
                        void* stream);
 
+/* Paired random crops of a batch (reference src/crop.py:15-39 CropPair, called per dataset item at
+ * src/datasets/__init__.py:78-90 through torchvision TF.crop): out[b, c, i, j] = in[b, c, top[b] + i, left[b] + j],
+ * zero outside the image.  top / left: DEVICE int arrays of B offsets. */
+int sei_crop_batch_f32(const float* in, float* out, int B, int C, int H, int W, int h, int w,
+                       const int* top, const int* left, void* stream);
+
 /* ---- scale transform -----------------------------------------------------------------
  * padded_downsampling_transform (src/transforms.py:60-83) with mode="bicubic",
  * padding_mode="reflection", antialiased=False: builds the grid of

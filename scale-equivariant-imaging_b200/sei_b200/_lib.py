@@ -21,6 +21,7 @@ SIGNATURES = {
     "sei_down_aa_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp, _f, _i, _vp]),
     "sei_down_aa_transpose_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "sei_up_bicubic_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _vp]),
+    "sei_crop_batch_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_transform_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sei_scale_transform_src_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_transform_backward_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -166,6 +166,22 @@ def rotate_nearest(x, angle):
     return y
 
 
+def crop_batch(x, tops, lefts, height, width):
+    """out[b, c] = x[b, c, tops[b] : tops[b] + height, lefts[b] : lefts[b] + width], zero outside the image
+    (sei_crop_batch_f32: one launch for the whole batch, offsets in device memory); no autograd (dataset path)"""
+    x = _t(x, "x")
+    B, Cc, H, W = x.shape
+    tops = torch.as_tensor(tops, dtype=torch.int32).to(x.device).contiguous()
+    lefts = torch.as_tensor(lefts, dtype=torch.int32).to(x.device).contiguous()
+    if tops.numel() != B or lefts.numel() != B:
+        raise SeiError("crop_batch: one (top, left) offset per image is required")
+    out = torch.empty((B, Cc, int(height), int(width)), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sei_crop_batch_f32(_ptr(x), _ptr(out), B, Cc, H, W, int(height), int(width), _ptr(tops), _ptr(lefts),
+                                             _stream(x)))
+    return out
+
+
 def scale_params(u_rate, u_center, rates):
     u_rate, u_center = _t(u_rate, "u_rate"), _t(u_center, "u_center")
     B = u_rate.numel()

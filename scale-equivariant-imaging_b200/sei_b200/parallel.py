@@ -110,8 +110,11 @@ class GradAllReducer:
         the network that go through the group (a `proposed` step runs it three times); when the backward pass has
         produced the group's last contribution its bucket is all-reduced asynchronously (torch runs NCCL collectives on
         the process group's own stream) while the rest of the backward pass keeps the SMs busy.  `finish()` reduces
-        what is left (groups whose input carries no gradient, such as the first layer) and joins the streams.  Works
-        inside CUDA-graph capture (the collectives are captured with the step)."""
+        what is left (groups whose input carries no gradient, such as the first layer) and joins the streams.
+        Under CUDA-graph capture the hooks only record an event per finished group; `finish()` (still capturing, on the
+        capturing thread) then enqueues the collectives on a communication stream that waits for those events.  A graph
+        orders its nodes by dependencies, not by issue order, so on replay every all-reduce starts as soon as its group's
+        gradients exist and runs beside the rest of the backward pass."""
 
     def __init__(self, params, max_elems=2 ** 40, group=None, module=None, group_max_elems=None):
         self.params = [p for p in params if p.requires_grad]
@@ -159,6 +162,9 @@ class GradAllReducer:
         self._bwd = [0] * len(self.buckets)
         self._done = [False] * len(self.buckets)
         self._works = []
+        self._ready = []            # (bucket index, event) recorded by the hooks while a CUDA graph is being captured
+        self._deferred = False
+        self._comm_stream = None
         self._hooks = []
         if self.world > 1:
             for i, m in enumerate(self.modules):
@@ -176,17 +182,42 @@ class GradAllReducer:
     def _group_backward_done(self, index):
         self._bwd[index] += 1
         if self._armed and not self._done[index] and self._bwd[index] >= self._fwd[index]:
-            self._reduce_bucket(index, async_op=True)
+            if self._deferred:
+                self._done[index] = True
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._ready.append((index, ev))
+            else:
+                self._reduce_bucket(index, async_op=True)
 
     def arm(self):
         """call right before loss.backward(): the forward passes since the last finish() are what the backward covers"""
         self._armed = True
         self._bwd = [0] * len(self.buckets)
         self._done = [False] * len(self.buckets)
+        self._ready = []
+        self._deferred = bool(self.world > 1 and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing())
 
     def finish(self):
         """call right after loss.backward(): reduce the buckets the backward pass did not release, wait for all"""
-        if self.world > 1:
+        if self.world > 1 and self._deferred:
+            cur = torch.cuda.current_stream()
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            comm = self._comm_stream
+            for index, ev in self._ready:                      # buckets the backward pass released, in that order
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    self._done[index] = False
+                    self._reduce_bucket(index, async_op=False)
+            comm.wait_stream(cur)                              # the rest needs the whole backward pass
+            with torch.cuda.stream(comm):
+                for i in range(len(self.buckets)):
+                    if not self._done[i]:
+                        self._reduce_bucket(i, async_op=False)
+            cur.wait_stream(comm)
+            self._ready = []
+        elif self.world > 1:
             for i in range(len(self.buckets)):
                 if not self._done[i]:
                     self._reduce_bucket(i, async_op=True)

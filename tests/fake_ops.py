@@ -106,7 +106,29 @@ def sure_loss(y1, y2, y, b, margin_mse, margin_div, tau, sigma2, averaged_cst):
 
 NAMES = ["blur_circular", "blur_padded", "down_aa", "down_aa_transpose", "up_bicubic", "resize_bicubic", "rotate_nearest",
          "roll", "scale_transform", "scale_transform_from", "scale_transform_backward", "ei_remeasure", "add_noise",
-         "sure_perturb", "mse", "mc_div", "sure_loss"]
+         "sure_perturb", "mse", "mc_div", "sure_loss", "crop_batch"]
+
+
+def crop_batch(x, tops, lefts, height, width):
+    xn = _n(x)
+    B, C, H, W = xn.shape
+    out = np.zeros((B, C, int(height), int(width)), dtype=xn.dtype)
+    for b in range(B):
+        t, l = int(tops[b]), int(lefts[b])
+        r1, c1 = min(H, t + height), min(W, l + width)
+        out[b, :, : max(0, r1 - t), : max(0, c1 - l)] = xn[b, :, t:r1, l:c1]
+    return _t(out)
+
+
+def crop_batch(x, tops, lefts, height, width):
+    xn = _n(x)
+    B, C, H, W = xn.shape
+    out = np.zeros((B, C, int(height), int(width)), dtype=xn.dtype)
+    for b in range(B):
+        t, l = int(tops[b]), int(lefts[b])
+        r1, c1 = min(H, t + int(height)), min(W, l + int(width))
+        out[b, :, : max(0, r1 - t), : max(0, c1 - l)] = xn[b, :, t:r1, l:c1]
+    return _t(out)
 
 
 def install(monkeypatch):
