@@ -192,6 +192,14 @@ int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, l
 int sei_gemm_bf16_tn_gelu_bwd(const void* A, const void* B, void* D, const void* H, long long M, int N, int K,
                               long long lda, long long ldb, long long ldd, long long ld_h, void* stream);
 
+/* D (bf16) = A B^T + bias + res_scale * R, the addition done in the GEMM epilogue: a pointwise convolution whose output
+ * is added to a tensor of the same shape -- ConvBlock's `return x + x1` (reference src/models/convolutional.py:43-51),
+ * UNet's inner-residual and skip additions (:203-215: `x = x + xb`, `x = x + skips.pop()`).  R: bf16 [M, N] with row
+ * pitch ld_r (multiple of 8); N % 8 == 0. */
+int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, const float* bias, const void* R, float res_scale,
+                              long long M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_r,
+                              void* stream);
+
 /* D[M, N] (fp32) = A[K, M]^T * B[K, N]: both operands are read with the contraction index as their ROW (UMMA MN-major
  * shared-memory layout), so the weight gradient dL/dW = (dL/dy)^T x of a pointwise convolution needs no transposed
  * copies of the activations.  lda, ldb multiples of 8; K = pixels.  Split-K with fp32 atomics when M*N is small. */
@@ -250,12 +258,24 @@ int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, const float* 
  * order; workspace of sei_dwconv7_workspace_bytes(C) bytes (-1: channel count unsupported). */
 long long sei_dwconv7_workspace_bytes(int C);
 int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, void* stream);
+
+/* y = depthwise7x7(x) (+ bias) + res_scale * res, the addition done in the store of the convolution: the input
+ * gradient of a ConvBlock (reference src/models/convolutional.py:43-51, `return x + x1`: autograd adds the incoming
+ * gradient to the one that went through the block).  res: bf16 [B, H, W, C]. */
+int sei_dwconv7_cl_residual_bf16(const void* x, const float* wt, const float* bias, const void* res, float res_scale,
+                                 void* y, int B, int H, int W, int C, void* stream);
 int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* gw, float* gb, void* workspace,
                               int B, int H, int W, int C, void* stream);
 
 /* Exact (erf-form) GELU of the reference's ConvBlock (src/models/convolutional.py:41, nn.GELU()) on n bf16 elements
  * (n % 8 == 0): out = gelu(x) when gy == NULL, else out = gy * gelu'(x) (the backward of the same layer). */
 int sei_gelu_bf16(const void* x, const void* gy, void* out, long long n, void* stream);
+
+/* gx = gy * gelu'(h) on rows [T, C] and, in the same pass, gb[c] = sum_t gx[t, c]: GELU's backward (reference
+ * src/models/convolutional.py:41) together with the bias gradient of the pointwise convolution in front of it (:40,
+ * ConvBlock.conv2).  workspace: sei_ln_cl_backward_workspace_bytes(C) bytes. */
+int sei_gelu_bwd_colsum_bf16(const void* h, const void* gy, void* gx, float* gb, void* workspace, long long T, int C,
+                             void* stream);
 
 /* One Adam update (torch.optim.Adam semantics without weight decay / amsgrad; reference demo/train.py:167-186,266) of
  * n float32 parameters: m, v updated in place, p <- p - lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps), with the

@@ -813,6 +813,8 @@ struct DwParams {
     const __nv_bfloat16* gy;     // wgrad only
     const float* wt;             // [49][C]
     const float* bias;           // [C] or null
+    const __nv_bfloat16* res;    // [B, H, W, C] or null: y = conv(x) + bias + res_scale * res
+    float res_scale;
     __nv_bfloat16* y;
     float* partial;
     int B, H, W, C, wstrips, hgroups;
@@ -895,6 +897,18 @@ __global__ void __launch_bounds__(128) dwconv7_kernel(const __grid_constant__ Dw
                 }
             }
             __nv_bfloat16* orow = p.y + ((b * H + h) * (long long)W + w0) * C + c0;
+            if (p.res) {
+                const __nv_bfloat16* rrow = p.res + ((b * H + h) * (long long)W + w0) * C + c0;
+#pragma unroll
+                for (int j = 0; j < kDwRW; ++j) {
+                    if (interior || w0 + j < W) {
+                        float rv[4];
+                        unpack4(__ldg(reinterpret_cast<const uint2*>(rrow + j * C)), rv);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(p.res_scale, rv[c], acc[j][c]);
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < kDwRW; ++j) {
                 if (interior || w0 + j < W) {
@@ -1016,9 +1030,28 @@ extern "C" long long sei_dwconv7_workspace_bytes(int C)
     return (long long)gx * C * 50 * (long long)sizeof(float);
 }
 
+static int dwconv7_impl(const void* x, const float* wt, const float* bias, const void* res, float res_scale, void* y,
+                        int B, int H, int W, int C, void* stream);
+
 // y = depthwise7x7(x) (+ bias); wt: taps as [49][C] fp32 (flipped by the caller for the input gradient)
 extern "C" int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C,
                                    void* stream)
+{
+    return dwconv7_impl(x, wt, bias, nullptr, 0.f, y, B, H, W, C, stream);
+}
+
+// y = depthwise7x7(x) (+ bias) + res_scale * res: the input gradient of a ConvBlock, whose residual branch adds the
+// incoming gradient to the gradient that went through the block (autograd's accumulation of `x + x1`, reference
+// src/models/convolutional.py:43-51), in the store of the convolution instead of a separate pass
+extern "C" int sei_dwconv7_cl_residual_bf16(const void* x, const float* wt, const float* bias, const void* res,
+                                            float res_scale, void* y, int B, int H, int W, int C, void* stream)
+{
+    SEI_REQUIRE(res != nullptr && aligned16(res), "res must be a 16-byte aligned [B, H, W, C] bf16 tensor");
+    return dwconv7_impl(x, wt, bias, res, res_scale, y, B, H, W, C, stream);
+}
+
+static int dwconv7_impl(const void* x, const float* wt, const float* bias, const void* res, float res_scale, void* y,
+                        int B, int H, int W, int C, void* stream)
 {
     SEI_REQUIRE(x && wt && y, "null pointer argument");
     SEI_REQUIRE(B >= 0 && H > 0 && W > 0 && C >= 8 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
@@ -1029,6 +1062,7 @@ extern "C" int sei_dwconv7_cl_bf16(const void* x, const float* wt, const float* 
     if (rc) return rc;
     DwParams p = {};
     p.x = static_cast<const __nv_bfloat16*>(x); p.wt = wt; p.bias = bias; p.y = static_cast<__nv_bfloat16*>(y);
+    p.res = static_cast<const __nv_bfloat16*>(res); p.res_scale = res_scale;
     p.B = B; p.H = H; p.W = W; p.C = C; p.wstrips = (W + kDwRW - 1) / kDwRW; p.hgroups = (H + kDwRH - 1) / kDwRH;
     p.items = (long long)B * p.hgroups * p.wstrips * (C / 4);
     const unsigned grid = (unsigned)std::min<long long>((p.items + 127) / 128, (long long)dp.sm_count * 64);
@@ -1195,6 +1229,117 @@ extern "C" int sei_gelu_bf16(const void* x, const void* gy, void* out, long long
     return finish_launch(gy ? "gelu_bwd_kernel" : "gelu_fwd_kernel");
 }
 
+
+// gx = gy * gelu'(h) on rows [T, C] AND the column sums of gx (the bias gradient of the pointwise convolution in front
+// of the GELU: ConvBlock.conv2, reference src/models/convolutional.py:40-41) in the same pass.  colsum_kernel's thread
+// layout (a thread keeps one 8-channel vector and strides down the rows, so the sums stay in registers), the
+// elementwise kernel's prefetch of the next rows.  Saves the separate read of the 4C-wide gradient per ConvBlock.
+namespace sei {
+
+__global__ void __launch_bounds__(kLnThreads) gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ h,
+                                                                      const __nv_bfloat16* __restrict__ gy,
+                                                                      __nv_bfloat16* __restrict__ gx,
+                                                                      float* __restrict__ partial, long long T, int C)
+{
+    __shared__ float red[kLnThreads * 8];
+    constexpr int U = 2;
+    const int nvec = C >> 3;
+    const long long tg = (long long)blockIdx.x * kLnThreads + threadIdx.x;
+    const long long total = (long long)gridDim.x * kLnThreads;
+    const int cv = (int)(tg % nvec);
+    const long long rp = tg / nvec, RP = total / nvec;
+    float db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) db[j] = 0.f;
+    uint4 ch[U], cg[U], nh[U], ng[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (rp + u * RP < T) {
+            ch[u] = __ldcs(reinterpret_cast<const uint4*>(h + (rp + u * RP) * C) + cv);
+            cg[u] = __ldcs(reinterpret_cast<const uint4*>(gy + (rp + u * RP) * C) + cv);
+        }
+    for (long long r = rp; r < T; r += RP * U) {
+        const long long r1 = r + RP * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r1 + u * RP < T) {
+                nh[u] = __ldcs(reinterpret_cast<const uint4*>(h + (r1 + u * RP) * C) + cv);
+                ng[u] = __ldcs(reinterpret_cast<const uint4*>(gy + (r1 + u * RP) * C) + cv);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u * RP < T) {
+                float f[8], g[8];
+                unpack8(ch[u], f);
+                unpack8(cg[u], g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float Phi, phi;
+                    gelu_parts(f[j], Phi, phi);
+                    g[j] *= fmaf(f[j], phi, Phi);
+                }
+                const uint4 packed = pack8(g);
+                __stcs(reinterpret_cast<uint4*>(gx + (r + u * RP) * C) + cv, packed);
+                unpack8(packed, g);                 // the sums are those of the ROUNDED gradient, as a separate pass would see it
+#pragma unroll
+                for (int j = 0; j < 8; ++j) db[j] += g[j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ch[u] = nh[u];
+            cg[u] = ng[u];
+        }
+    }
+    const int per_cta = nvec < kLnThreads ? kLnThreads / nvec : 1;
+    if (per_cta > 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[j * kLnThreads + threadIdx.x] = db[j];
+        __syncthreads();
+        if ((int)threadIdx.x < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float sb = 0.f;
+                for (int k = 0; k < per_cta; ++k) sb += red[j * kLnThreads + threadIdx.x + k * nvec];
+                db[j] = sb;
+            }
+        }
+    }
+    if (per_cta == 1 || (int)threadIdx.x < nvec) {
+        const long long slot = per_cta > 1 ? blockIdx.x : rp;
+        float* o = partial + (size_t)slot * C + 8 * cv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = db[j];
+    }
+}
+
+}  // namespace sei
+
+// gx = gy * gelu'(h) and gb[c] = sum_t gx[t, c]; h, gy, gx: bf16 [T, C]; workspace: sei_ln_cl_backward_workspace_bytes(C)
+extern "C" int sei_gelu_bwd_colsum_bf16(const void* h, const void* gy, void* gx, float* gb, void* workspace, long long T,
+                                        int C, void* stream)
+{
+    SEI_REQUIRE(h && gy && gx && gb && workspace, "null pointer argument");
+    SEI_REQUIRE(T >= 0 && C >= 8 && C % 8 == 0, "bad shape T=%lld C=%d (C must be a multiple of 8)", T, C);
+    SEI_REQUIRE(aligned16(h) && aligned16(gy) && aligned16(gx) && aligned16(workspace), "operands must be 16-byte aligned");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const long long threads = colsum_threads(C, dp.sm_count);
+    SEI_REQUIRE(threads > 0, "channel count %d unsupported by the column-sum kernels", C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (T == 0) {
+        SEI_CUDA(cudaMemsetAsync(gb, 0, (size_t)C * 4, st));
+        return 0;
+    }
+    gelu_bwd_colsum_kernel<<<(unsigned)(threads / kLnThreads), kLnThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(gy), static_cast<__nv_bfloat16*>(gx),
+        static_cast<float*>(workspace), T, C);
+    rc = finish_launch("gelu_bwd_colsum_kernel");
+    if (rc) return rc;
+    colsum_final_kernel<<<(C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), gb, gb, colsum_slots(C, threads), C, C);
+    return finish_launch("colsum_final_kernel");
+}
 
 // ---------------------------------------------------------------- bias behind a resampler
 // Downsample = LayerNorm -> conv1x1 -> ideal resampler; the resampler is applied BEFORE the convolution here (they

@@ -143,145 +143,23 @@ struct GemmParams {
     int accumulate;      // fp32 output: add to D instead of overwriting it (weight gradients accumulated in place)
     const __nv_bfloat16* gelu_h;   // optional [M, N] (row pitch ld_h): D = (A B^T) * gelu'(gelu_h)  (TMA-store epilogue only)
     int ld_h;
+    const __nv_bfloat16* res;      // optional [M, N] (row pitch ld_r): D = A B^T + bias + res_scale * res  (bf16 output)
+    int ld_r;
+    float res_scale;
 };
-
-// first version: one output tile per CTA (kept for A/B measurements: SEI_GEMM_V1=1)
-template <int BN, int STAGES, bool OUT_F32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel_v1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ GemmParams p)
-{
-    constexpr int BM = kGemmBM, BK = kGemmBK;
-    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32 for BN in {32, 64, 128, 256}
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
-    __shared__ uint32_t tmem_base_slot;
-
-    // SWIZZLE_128B tiles must start on a 1024-byte boundary
-    const uint32_t raw = smem_u32(smem_raw);
-    unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int nk_total = (p.K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;      // k-blocks of this split (>= 1 by construction)
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a);
-        tma_prefetch_desc(&map_b);
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(&tmem_full_bar, 1);
-        mbar_fence_init();
-    }
-    if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t use = kb / STAGES;
-                if (kb >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
-                tma_load_2d(a_dst, &map_a, (kb0 + kb) * BK, m0, &full_bar[s]);
-                tma_load_2d(a_dst + A_BYTES, &map_b, (kb0 + kb) * BK, n0, &full_bar[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                }
-                umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
-            }
-            umma_commit(&tmem_full_bar);             // accumulator complete
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-        const int q = warp & 3;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            tmem_ld_wait();
-            const int col0 = n0 + c;
-            if (row < p.M && col0 < p.N) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias && blockIdx.z == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-                }
-                if (OUT_F32 && (p.splits > 1 || p.accumulate)) {
-                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
-                } else if (OUT_F32) {
-                    float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
-                    if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = v[j];
-                    }
-                } else {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
-                    if (col0 + 32 <= p.N && (p.ldd & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]),
-                                           t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(dst + j) = pk;
-                        }
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
+// 128-bit read-only load that does not allocate in L1 (operands every lane reads exactly once)
+__device__ __forceinline__ uint4 ld_nc_na(const uint4* ptr)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
 }
 
 // The GELU backward fused into the input-gradient GEMM of the layer that follows it (reference ConvBlock: conv2 -> GELU
@@ -329,6 +207,24 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
         for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
     }
+    if (!OUT_F32 && p.res) {
+        const __nv_bfloat16* rp = p.res + (size_t)row * p.ld_r + col0;
+        if (col0 + 32 <= p.N && (p.ld_r & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 raw = ld_nc_na(reinterpret_cast<const uint4*>(rp + j));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[j + 2 * e] = fmaf(p.res_scale, f.x, v[j + 2 * e]);
+                    v[j + 2 * e + 1] = fmaf(p.res_scale, f.y, v[j + 2 * e + 1]);
+                }
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) v[j] = fmaf(p.res_scale, __bfloat162float(rp[j]), v[j]);
+        }
+    }
     if (OUT_F32 && (p.splits > 1 || p.accumulate)) {
         float* dst = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
         if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
@@ -367,14 +263,88 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
     }
 }
 
+
+// Epilogue of one 32-row x 64-column chunk of the accumulator on the bulk-tensor-store path (one warp): tcgen05.ld the
+// chunk, add bias / residual, convert to bf16, stage it in the warp's SWIZZLE_128B slab (16-byte chunk j of row r at
+// position j ^ (r & 7): conflict-free) and hand the slab to the TMA engine.  The bias row of the chunk is staged once in
+// shared memory by the warp (two coalesced loads, then 16 broadcast LDS.128 per lane) -- the first version issued 64
+// predicated scalar loads + compares + adds per lane and chunk, three times the instructions of the conversion itself
+// -- and the residual row chunk (128 contiguous bytes per lane) is requested BEFORE the accumulator wait so that the two
+// latencies overlap.
+template <int NSLAB>
+__device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const CUtensorMap* map_d, uint32_t taddr, int row0,
+                                                      int col0, int lane, bool add_bias, unsigned char* slab, float* sb)
+{
+    const int row = row0 + lane;
+    uint4 rr[8];
+    const bool has_res = p.res != nullptr;
+    if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ld_r + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            rr[j] = (row < p.M && col0 + 8 * j + 8 <= p.N) ? ld_nc_na(rp + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    add_bias = add_bias && p.bias != nullptr;
+    if (add_bias) {
+        sb[lane] = col0 + lane < p.N ? __ldg(p.bias + col0 + lane) : 0.f;
+        sb[lane + 32] = col0 + 32 + lane < p.N ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
+    }
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(taddr, r0);
+    tmem_ld_32x32(taddr + 32u, r1);
+    tmem_ld_wait();
+    if (p.gelu_h) epilogue_gelu_bwd(p, row, col0, r0, r1);
+    if (lane == 0) bulk_wait_read<NSLAB - 1>();   // the store that last read this slab has finished reading
+    __syncwarp();                            // (also: the bias row is visible to every lane)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {            // 8 chunks of 8 bf16
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cc = 8 * j + e;
+            v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
+        }
+        if (add_bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + 8 * j), b1 = *reinterpret_cast<const float4*>(sb + 8 * j + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (has_res) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                v[2 * e] = fmaf(p.res_scale, f.x, v[2 * e]);
+                v[2 * e + 1] = fmaf(p.res_scale, f.y, v[2 * e + 1]);
+            }
+        }
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
+                       t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+    }
+    fence_proxy_async();                     // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0 && col0 < p.N && row0 < p.M) {
+        tma_store_2d(map_d, slab, col0, row0);
+        bulk_commit();
+    }
+}
+
 // Persistent kernel: gridDim.x CTAs (one per SM) walk the work items (output tile x K-split), m fastest so that the
 // CTAs running together share the B (weight) tile through L2.  The shared-memory ring and its mbarrier phases
 // run continuously across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue
 // warps drain tile i (tcgen05.ld -> bias -> store) while the MMA thread is already accumulating tile i+1.
 // MN = false: A[M,K], B[N,K] row-major (K contiguous).  MN = true: A[K,M], B[K,N] row-major (the contraction index is
 // the row: D = A^T B), used by the weight gradient so that gy and x are read in place (no transposed copies).
-template <int BN, int STAGES, bool OUT_F32, bool MN = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// EW epilogue warps (4 or 8): warp 2 + i owns TMEM lane quarter (2 + i) % 4 and every (EW / 4)-th column chunk.  A
+// short-K tile finishes its MMAs in a few hundred clocks and then waits for 32 - 64 KB of output to leave: with four
+// warps that drain (tcgen05.ld -> convert -> slab -> bulk store, each step waiting on the one before) bounded the
+// expanding pointwise convolutions of the shallow levels at half of the HBM rate.
+template <int BN, int STAGES, bool OUT_F32, bool MN = false, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
 {
@@ -385,6 +355,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float bias_s[EW * 64];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B tiles: 1024-byte aligned
@@ -406,7 +377,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 128);           // every epilogue thread arrives
+            mbar_init(&tmem_empty_bar[a], 32 * EW);       // every epilogue thread arrives
         }
         mbar_fence_init();
     }
@@ -482,9 +453,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-        const int q = warp & 3;
+        // ===== epilogue: warps 2.. own TMEM lane quarters (warp % 4) and interleaved column chunks =====
+        const int q = warp & 3, sub = (warp - 2) >> 2;
+        constexpr int NSUB = EW / 4;
         uint32_t tcount = 0, chunk_count = 0;
+        constexpr int NSLAB = EW == 4 ? 2 : 1;     // staging slabs per warp (with eight warps the other warps provide the overlap)
+        unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * NSLAB * SLAB_BYTES;
+        float* sb = bias_s + (warp - 2) * 64;
         for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
             const int split = (int)(w / tiles_mn);
             const long long rem = w - split * tiles_mn;
@@ -493,50 +468,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             if (!OUT_F32 && p.tma_store && BN >= 64) {
-                // coalesced path: each warp converts its 32 x 64 sub-tile to bf16, writes it to its own SWIZZLE_128B
-                // staging slab (16-byte chunk j of row r at position j ^ (r & 7): conflict-free) and one lane hands
-                // the slab to the TMA engine; two slabs per warp so the next chunk is staged while the store drains
-                unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * 2 * SLAB_BYTES;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 64) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
-                    tmem_ld_wait();
-                    if (p.gelu_h) epilogue_gelu_bwd(p, row, n0 + c, r0, r1);
-                    unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;   // alternates across tiles too
-                    if (lane == 0) bulk_wait_read<1>();      // the store that last read this slab has finished reading
-                    __syncwarp();
-                    const int col0 = n0 + c;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {            // 8 chunks of 8 bf16
-                        float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int cc = 8 * j + e;
-                            v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
-                            if (p.bias && split == 0 && col0 + cc < p.N) v[e] += __ldg(p.bias + col0 + cc);
-                        }
-                        uint4 pk;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
-                                       t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
-                    }
-                    fence_proxy_async();                     // generic-proxy writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
-                        tma_store_2d(&map_d, slab, col0, m0 + q * 32);
-                        bulk_commit();
-                    }
-                }
+                for (int c = 64 * sub; c < BN; c += 64 * NSUB)
+                    gemm_epilogue_chunk64<NSLAB>(p, &map_d, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, split == 0,
+                                                 slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = 32 * sub; c < BN; c += 32 * NSUB) {
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r);
+                    tmem_ld_32x32(taddr + (uint32_t)c, r);
                     tmem_ld_wait();
                     gemm_store_chunk<OUT_F32>(p, r, row, n0 + c, split == 0);
                 }
@@ -618,8 +560,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int STAGES, int EW = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
 {
@@ -630,6 +572,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float bias_s[EW * 64];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -653,7 +596,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 256);           // the epilogue threads of both CTAs
+            mbar_init(&tmem_empty_bar[a], 64 * EW);       // the epilogue threads of both CTAs
         }
         mbar_fence_init();
     }
@@ -705,48 +648,22 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
     } else {
         // ===== epilogue (both CTAs): own 128 rows of the accumulator =====
-        const int q = warp & 3;
+        const int q = warp & 3, sub = (warp - 2) >> 2;
+        constexpr int NSUB = EW / 4;
         uint32_t tcount = 0, chunk_count = 0;
-        unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * 2 * SLAB_BYTES;
+        constexpr int NSLAB = EW == 4 ? 2 : 1;
+        unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * NSLAB * SLAB_BYTES;
+        float* sb = bias_s + (warp - 2) * 64;
         for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
             const int m0 = (int)(w % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(w / tiles_m) * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 64) {
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c, r0);
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c + 32), r1);
-                tmem_ld_wait();
-                if (p.gelu_h) epilogue_gelu_bwd(p, m0 + q * 32 + lane, n0 + c, r0, r1);
-                unsigned char* slab = slabs + (size_t)(chunk_count++ & 1) * SLAB_BYTES;
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
-                const int col0 = n0 + c;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int cc = 8 * j + e;
-                        v[e] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
-                        if (p.bias && col0 + cc < p.N) v[e] += __ldg(p.bias + col0 + cc);
-                    }
-                    uint4 pk;
-                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
-                                   t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-                    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                    *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
-                    tma_store_2d(&map_d, slab, col0, m0 + q * 32);
-                    bulk_commit();
-                }
-            }
+            for (int c = 64 * sub; c < BN; c += 64 * NSUB)
+                gemm_epilogue_chunk64<NSLAB>(p, &map_d, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, true,
+                                             slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
             tc_fence_before();
             mbar_arrive_leader(&tmem_empty_bar[acc]);       // this thread is done reading the accumulator stage
         }
@@ -1159,33 +1076,39 @@ static int launch_gemm_mn(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
     return finish_launch("gemm_bf16_mn_kernel");
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p, bool out_f32,
-                       int sm_count, cudaStream_t st)
+// shared memory of gemm_bf16_tn_kernel: operand ring + alignment slack + (bf16 TMA-store path only) two 4 KB slabs per
+// epilogue warp
+template <int BN, int STAGES, int EW>
+constexpr size_t gemm_smem_bytes(bool out_f32)
 {
-    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
+    return (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024 + ((out_f32 || BN < 64) ? 0 : (size_t)8 * 32 * 128);
+}
+
+template <int BN, int STAGES, int EW>
+static int launch_gemm_ew(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p, bool out_f32,
+                          int sm_count, cudaStream_t st)
+{
     const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
-    const char* v1 = getenv("SEI_GEMM_V1");
-    if (v1 && *v1 == '1') {
-        dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN, p.splits);
-        if (out_f32) {
-            SEI_CUDA(allow_smem(gemm_bf16_tn_kernel_v1<BN, STAGES, true>, smem));
-            gemm_bf16_tn_kernel_v1<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
-        } else {
-            SEI_CUDA(allow_smem(gemm_bf16_tn_kernel_v1<BN, STAGES, false>, smem));
-            gemm_bf16_tn_kernel_v1<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, p);
-        }
-        return finish_launch("gemm_bf16_tn_kernel");
-    }
     const unsigned grid = (unsigned)std::min<long long>(tiles * p.splits, sm_count);
+    constexpr int threads = 64 + 32 * EW;
     if (out_f32) {
-        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, md, p);
+        constexpr size_t smem = gemm_smem_bytes<BN, STAGES, EW>(true);
+        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true, false, EW>, smem));
+        gemm_bf16_tn_kernel<BN, STAGES, true, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, p);
     } else {
-        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, false><<<grid, kGemmThreads, smem, st>>>(ma, mb, md, p);
+        constexpr size_t smem = gemm_smem_bytes<BN, STAGES, EW>(false);
+        static_assert(smem + 4096 <= 227 * 1024, "operand ring + epilogue slabs + static barriers / bias strips exceed the shared memory of an SM");
+        SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false, false, EW>, smem));
+        gemm_bf16_tn_kernel<BN, STAGES, false, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, p);
     }
     return finish_launch("gemm_bf16_tn_kernel");
+}
+
+// epilogue warps per CTA (SEI_GEMM_EW=4 restores the round-1 shape for A/B measurements)
+static int gemm_epilogue_warps()
+{
+    const char* e = getenv("SEI_GEMM_EW");
+    return (e && *e == '4') ? 4 : 8;
 }
 
 // 5-D bf16 tensor map {n, ri, ro, bi, bo}: element (n, r = ro * r_inner + ri, batch = bo * b_inner + bi) of a tensor whose
@@ -1312,14 +1235,36 @@ static void choose_splits(long long tiles, int units, int nk, int* splits, int* 
     }
 }
 
+struct GemmEpilogueExtra {
+    const void* gelu_h = nullptr;      // multiply by gelu'(gelu_h)
+    long long ld_h = 0;
+    const void* res = nullptr;         // add res_scale * res
+    long long ld_r = 0;
+    float res_scale = 1.0f;
+};
+
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                             long long lda, long long ldb, long long ldd, int out_f32, int tile_n,
-                            const void* gelu_h, long long ld_h, void* stream);
+                            const GemmEpilogueExtra& ex, void* stream);
 
 extern "C" int sei_gemm_bf16_tn(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                                 long long lda, long long ldb, long long ldd, int out_f32, int tile_n, void* stream)
 {
-    return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, out_f32, tile_n, nullptr, 0, stream);
+    return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, out_f32, tile_n, GemmEpilogueExtra(), stream);
+}
+
+// D (bf16) = A B^T + bias + res_scale * R: a pointwise convolution whose output is added to a tensor of the same shape in
+// the GEMM epilogue (ConvBlock's `x + x1`, reference src/models/convolutional.py:51; UNet's skip / inner-residual
+// additions :206-215) instead of a separate pass over both tensors.  R: bf16 [M, N] with row pitch ld_r (multiple of 8).
+extern "C" int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, const float* bias, const void* R,
+                                         float res_scale, long long M, int N, int K, long long lda, long long ldb,
+                                         long long ldd, long long ld_r, void* stream)
+{
+    SEI_REQUIRE(R != nullptr && aligned16(R) && ld_r % 8 == 0 && ld_r >= N, "R must be 16-byte aligned with a row pitch >= N that is a multiple of 8");
+    SEI_REQUIRE(N % 8 == 0, "the fused residual needs N %% 8 == 0 (N=%d)", N);
+    GemmEpilogueExtra ex;
+    ex.res = R; ex.ld_r = ld_r; ex.res_scale = res_scale;
+    return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
 }
 
 // D (bf16) = (A B^T) * gelu'(H): the input gradient of `conv3` with the GELU backward applied in the epilogue.
@@ -1329,13 +1274,17 @@ extern "C" int sei_gemm_bf16_tn_gelu_bwd(const void* A, const void* B, void* D, 
 {
     SEI_REQUIRE(H != nullptr && aligned16(H) && ld_h % 8 == 0 && ld_h >= N, "H must be 16-byte aligned with a row pitch >= N that is a multiple of 8");
     SEI_REQUIRE(N % 64 == 0 && ldd % 8 == 0, "the fused GELU backward needs N %% 64 == 0 and ldd %% 8 == 0 (N=%d)", N);
-    return gemm_bf16_tn_impl(A, B, D, nullptr, M, N, K, lda, ldb, ldd, 0, 0, H, ld_h, stream);
+    GemmEpilogueExtra ex;
+    ex.gelu_h = H; ex.ld_h = ld_h;
+    return gemm_bf16_tn_impl(A, B, D, nullptr, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
 }
 
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
                             long long lda, long long ldb, long long ldd, int out_f32, int tile_n,
-                            const void* gelu_h, long long ld_h, void* stream)
+                            const GemmEpilogueExtra& ex, void* stream)
 {
+    const void* gelu_h = ex.gelu_h;
+    const long long ld_h = ex.ld_h;
     SEI_REQUIRE(A && B && D, "null pointer argument");
     SEI_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "bad shape M=%lld N=%d K=%d", M, N, K);
     SEI_REQUIRE(lda >= K && ldb >= K && ldd >= N, "leading dimensions smaller than the rows");
@@ -1357,6 +1306,8 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     GemmParams p;
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
     p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
+    p.res = static_cast<const __nv_bfloat16*>(ex.res); p.ld_r = (int)ex.ld_r; p.res_scale = ex.res_scale;
+    SEI_REQUIRE(!ex.res || !out_f32, "the fused residual is a bf16-output epilogue");
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
     p.tma_store = (!out_f32 && bn >= 64 && ldd % 8 == 0 && !(nts && *nts == '1')) ? 1 : 0;
@@ -1383,18 +1334,33 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
         CUtensorMap mb2;
         rc = make_map_bf16(&mb2, B, N, K, ldb, 128);
         if (rc) return rc;
-        constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
         const long long ctiles = ((M + 255) / 256) * (long long)((N + 255) / 256);
         const unsigned grid = 2u * (unsigned)std::min<long long>(ctiles, dp.sm_count / 2);
-        SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2>, smem2));
-        gemm_bf16_tn_2cta_kernel<ST2><<<grid, kGemmThreads, smem2, st>>>(ma, mb2, md, p);
+        if (gemm_epilogue_warps() == 8) {
+            constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 8 * 32 * 128;
+            static_assert(smem2 + 4096 <= 227 * 1024, "CTA-pair kernel: ring + slabs + barriers exceed the shared memory of an SM");
+            SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 8>, smem2));
+            gemm_bf16_tn_2cta_kernel<ST2, 8><<<grid, 64 + 32 * 8, smem2, st>>>(ma, mb2, md, p);
+        } else {
+            constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
+            SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 4>, smem2));
+            gemm_bf16_tn_2cta_kernel<ST2, 4><<<grid, 64 + 32 * 4, smem2, st>>>(ma, mb2, md, p);
+        }
         return finish_launch("gemm_bf16_tn_2cta_kernel");
     }
+    if (gemm_epilogue_warps() == 8) {        // eight epilogue warps; one operand stage fewer where the slabs need the room
+        switch (bn) {
+        case 32: return launch_gemm_ew<32, 8, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+        case 64: return launch_gemm_ew<64, 7, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+        case 128: return launch_gemm_ew<128, 5, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+        default: return launch_gemm_ew<256, 3, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+        }
+    }
     switch (bn) {
-    case 32: return launch_gemm<32, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    case 64: return launch_gemm<64, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    case 128: return launch_gemm<128, 6>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    default: return launch_gemm<256, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 32: return launch_gemm_ew<32, 8, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 64: return launch_gemm_ew<64, 7, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 128: return launch_gemm_ew<128, 5, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    default: return launch_gemm_ew<256, 3, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
     }
 }
 
@@ -1438,7 +1404,7 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
-    p.gelu_h = nullptr; p.ld_h = 0;
+    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);

@@ -40,6 +40,9 @@ _NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"    
 # 9 ms GELU-backward pass but the four epilogue warps then spend longer on the erf arithmetic than the tensor cores
 # on the tile (CTA-pair GEMMs 76 -> 93 ms, N = 128 GEMMs 6 -> 13 ms per step): off by default.
 _GELU_FUSION = __import__("os").environ.get("SEI_GELU_FUSION", "0") == "1"
+# ConvBlock as one autograd node with its additions fused into the neighbouring kernels (SEI_CONVBLOCK_NODE=0: the
+# op-by-op path, for A/B measurements)
+_CONVBLOCK_NODE = __import__("os").environ.get("SEI_CONVBLOCK_NODE", "1") == "1"
 
 
 def _gemm_tn(a, b, bias, out_dtype):
@@ -127,11 +130,13 @@ class _GemmTN(torch.autograd.Function):
     """out[T, N] = x[T, K] @ w[N, K]^T + bias[N]; all three passes on sei_gemm_bf16_tn."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, wt_getter, param=None):
+    def forward(ctx, x, weight, bias, w_bf16, wt_getter, param=None, res=None):
         ctx.save_for_backward(x, w_bf16)
         ctx.has_bias = bias is not None
         ctx.wt_getter = wt_getter
         ctx.param = param                      # nn.Parameter whose .grad may receive the weight gradient in place
+        if res is not None:                    # out = x w^T + bias + res, the addition in the GEMM epilogue
+            return ops.gemm_bf16_tn_residual(x, w_bf16, bias, res, 1.0)
         return _gemm_tn(x, w_bf16, bias, COMPUTE_DTYPE)
 
     @staticmethod
@@ -160,7 +165,7 @@ class _GemmTN(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             # one pass, fp32 accumulation, fixed order (csrc/cnn_elem.cu); library reduction for odd channel counts
             gb = _colsum(gy)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, (gy if len(ctx.needs_input_grad) > 6 and ctx.needs_input_grad[6] else None)
 
 
 class _GeluGemmTN(torch.autograd.Function):
@@ -209,6 +214,79 @@ def _pad_k(a):
     a = a.contiguous()
     k = a.shape[1]
     return a if k % 8 == 0 else F.pad(a, (0, 8 - k % 8))
+
+
+
+def _wgrad_into(param, gy, x):
+    """dL/dW = gy^T x of a pointwise convolution: accumulated straight into param.grad when that buffer exists (returns
+    None), otherwise returned as a new fp32 matrix"""
+    g = None if _NO_WGRAD_ACC else param.grad
+    if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.is_cuda
+            and g.numel() == gy.shape[1] * x.shape[1]):
+        _gemm_atb(gy, x, out=g.view(gy.shape[1], x.shape[1]))
+        return None
+    return _gemm_atb(gy, x).view(param.shape)
+
+
+class _ConvBlockFn(torch.autograd.Function):
+    """A whole ConvBlock (reference src/models/convolutional.py:33-51) as ONE autograd node:
+
+        out = res_scale * x + conv3(gelu(conv2(LayerNorm(dwconv7(x)))))
+
+    (res_scale = 1 is the block itself; 2 folds UNet's inner residual `x + xb` when the block is alone in its sequence).
+    The residual is added in the epilogue of conv3's GEMM (sei_gemm_bf16_tn_residual); in the backward pass the
+    incoming gradient is added in the store of the depthwise input-gradient convolution (sei_dwconv7_cl_residual_bf16)
+    and conv2's bias gradient is summed inside the GELU-backward pass (sei_gelu_bwd_colsum_bf16).  As separate autograd
+    nodes these were three extra passes over C-wide tensors and one over the 4C-wide gradient per block and direction
+    (library additions: 6 ms of a 233 ms step; the extra column sum: 2.4 ms)."""
+
+    @staticmethod
+    def forward(ctx, xl, res_scale, block, dw_w, dw_b, ln_g, ln_b, w2, b2, w3, b3):
+        B, H, W, C = xl.shape
+        T = B * H * W
+        dw32 = dw_w.detach().float().reshape(C, 49)
+        dwb32 = None if dw_b is None else dw_b.detach().float().contiguous()
+        g32, be32 = ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous()
+        _, w2_bf = block.conv2._weight_matrix()
+        _, w3_bf = block.conv3._weight_matrix()
+        t1 = ops._dwconv7_raw(xl, dw32.t().contiguous(), dwb32)
+        t2, mean, rstd, small = ops.ln_forward_raw(t1.view(T, C), g32, be32, block.ln.ln.eps)
+        h = _gemm_tn(t2, w2_bf, b2, COMPUTE_DTYPE)
+        a = ops.gelu_raw(h)
+        out = ops.gemm_bf16_tn_residual(a, w3_bf, b3, xl.view(T, C), res_scale)
+        ctx.save_for_backward(xl, t1, mean, rstd, t2, h, a, dw32, g32)
+        ctx.block, ctx.res_scale, ctx.small = block, float(res_scale), small
+        ctx.dtypes = (dw_w.dtype, None if dw_b is None else dw_b.dtype, ln_g.dtype, ln_b.dtype)
+        ctx.has_bias = (b2 is not None, b3 is not None)
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        xl, t1, mean, rstd, t2, h, a, dw32, g32 = ctx.saved_tensors
+        block = ctx.block
+        B, H, W, C = xl.shape
+        T = B * H * W
+        g = g.contiguous()
+        g2 = g.view(T, C)
+        need = ctx.needs_input_grad
+        gb3 = _colsum(g2) if (ctx.has_bias[1] and need[10]) else None
+        gw3 = _wgrad_into(block.conv3.weight, g2, a) if need[9] else None
+        ga = _gemm_tn(g2, block.conv3._weight_matrix_t(), None, COMPUTE_DTYPE)          # [T, 4C]
+        gh, gb2 = ops.gelu_bwd_colsum(h, ga)
+        del ga
+        gw2 = _wgrad_into(block.conv2.weight, gh, t2) if need[7] else None
+        gt2 = _gemm_tn(gh, block.conv2._weight_matrix_t(), None, COMPUTE_DTYPE)         # [T, C]
+        del gh
+        gt1, dgam, dbet = ops.ln_backward_raw(gt2, t1.view(T, C), mean, rstd, g32, ctx.small)
+        del gt2
+        gt1 = gt1.view(B, H, W, C)
+        gdw, gdwb = ops.dwconv7_wgrad_raw(gt1, xl)
+        gx = None
+        if need[0]:
+            gx = ops._dwconv7_raw(gt1, dw32.flip(1).t().contiguous(), None, res=g, res_scale=ctx.res_scale)
+        dt = ctx.dtypes
+        return (gx, None, None, gdw.view(C, 1, 7, 7).to(dt[0]), None if dt[1] is None else gdwb.to(dt[1]),
+                dgam.to(dt[2]), dbet.to(dt[3]), gw2, gb2 if ctx.has_bias[0] else None, gw3, gb3)
 
 
 class _GemmConv2d(Conv2d):
@@ -267,9 +345,20 @@ class _GemmConv2d(Conv2d):
         out = _GeluGemmTN.apply(h2, w2, self.bias, w_bf16, self._weight_matrix_t, self.weight)
         return out.view(B, H, W, -1).permute(0, 3, 1, 2)
 
-    def forward(self, x, use_bias=True):
+    def forward(self, x, use_bias=True, residual=None):
+        """residual: a tensor of the output's shape added to it -- in the GEMM epilogue when the shapes allow"""
         B, C, H, W = x.shape
         xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)      # (B, H, W, C) view
+        if residual is not None:
+            rl = residual.contiguous(memory_format=CL).permute(0, 2, 3, 1)
+            if (self.kernel_size == (1, 1) and self.out_channels % 8 == 0 and self.in_channels % 8 == 0 and rl.is_cuda
+                    and rl.dtype == torch.bfloat16 == COMPUTE_DTYPE and tuple(rl.shape) == (B, H, W, self.out_channels)):
+                w2, w_bf16 = self._weight_matrix()
+                out = _GemmTN.apply(xl.reshape(B * H * W, C), w2, self.bias if use_bias else None, w_bf16,
+                                    self._weight_matrix_t, self.weight if w_bf16.shape == w2.shape else None,
+                                    rl.reshape(B * H * W, self.out_channels))
+                return out.view(B, H, W, -1).permute(0, 3, 1, 2)
+            return self.forward(x, use_bias=use_bias) + residual
         if self.kernel_size == (3, 3):
             # the network's output layer (hidden -> 3 channels): direct kernel, no unfolded copy (csrc/cnn_elem.cu)
             out = _op_conv3x3_small(xl, self)
@@ -321,8 +410,19 @@ class ConvBlock(Module):
         self.gelu = GELU()
         self.conv3 = _conv(4 * dim, dim, 1)
 
-    def forward(self, x):
+    def fused_node_ok(self, xl):
+        """the block runs as one autograd node (_ConvBlockFn): bf16 CUDA activations and channel counts the vectorised
+        kernels tile (every width of the default network); other widths take the op-by-op path below"""
+        return (_CONVBLOCK_NODE and xl.is_cuda and xl.dtype == torch.bfloat16 == COMPUTE_DTYPE and xl.shape[-1] % 8 == 0
+                and ops.dwconv7_supported(xl) and ops.ln_cl_supported(xl.reshape(-1, xl.shape[-1])))
+
+    def forward(self, x, res_scale=1.0):
+        """x + block(x) for res_scale = 1 (the reference's forward); res_scale * x + block(x) in general"""
         xl = x.contiguous(memory_format=CL).permute(0, 2, 3, 1)
+        if self.fused_node_ok(xl):
+            out = _ConvBlockFn.apply(xl.contiguous(), res_scale, self, self.conv1.weight, self.conv1.bias, self.ln.ln.weight,
+                                     self.ln.ln.bias, self.conv2.weight, self.conv2.bias, self.conv3.weight, self.conv3.bias)
+            return out.permute(0, 3, 1, 2)
         x1 = _op_dwconv7(xl, self.conv1).permute(0, 3, 1, 2)      # hand-written channels-last kernels (csrc/cnn_elem.cu)
         x1 = self.ln(x1)
         x1 = self.conv2(x1)
@@ -331,7 +431,7 @@ class ConvBlock(Module):
         else:
             x1 = _op_gelu(x1)
             x1 = self.conv3(x1)
-        return x + x1
+        return (x if res_scale == 1.0 else res_scale * x) + x1
 
 
 class IdealUpsample(Module):
@@ -356,8 +456,11 @@ class Upsample(Module):
         self.seq.append(LayerNorm(self.in_channels, eps=1e-6))
         self.seq.append(_conv(self.in_channels, self.out_channels, 1, stride=1))
 
-    def forward(self, x):
-        return self.seq(x)
+    def forward(self, x, skip=None):
+        if skip is None:
+            return self.seq(x)
+        x = self.seq[1](self.seq[0](x))
+        return self.seq[2](x, residual=skip)
 
 
 class IdealDownsample(Module):
@@ -398,6 +501,16 @@ class Downsample(Module):
         return self.ideal_downsample(self.conv(x))
 
 
+def _run_sequence(seq, x, inner_residual):
+    """`xb = x; x = seq(x); if inner_residual: x = x + xb` (reference UNet.forward).  A sequence of one ConvBlock (the
+    default) returns 2 x + block(x) from the block's own node: no separate addition."""
+    if inner_residual and len(seq) == 1 and isinstance(seq[0], ConvBlock):
+        return seq[0](x, res_scale=2.0)
+    xb = x
+    x = seq(x)
+    return x + xb if inner_residual else x
+
+
 class UNet(Module):
     def __init__(self, in_channels, hidden_channels, inout_convs, scales, num_conv_blocks, rate, residual,
                  inner_residual):
@@ -436,16 +549,12 @@ class UNet(Module):
         if hasattr(self, "in_conv"):
             x = self.in_conv(x)
         for _ in range(self.scales - 1):
-            xb = x
-            x = next(convs)(x)
-            if self.inner_residual:
-                x = x + xb
+            x = _run_sequence(next(convs), x, self.inner_residual)
             skips.append(x)
             x = next(downs)(x)
         x = next(convs)(x)
         for _ in range(self.scales - 1):
-            x = next(ups)(x)
-            x = x + skips.pop()
+            x = next(ups)(x, skip=skips.pop())       # `x = ups(x); x = x + skip` with the addition in the GEMM epilogue
             x = next(convs)(x)
         if hasattr(self, "out_conv"):
             x = self.out_conv(x)

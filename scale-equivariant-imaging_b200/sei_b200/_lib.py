@@ -40,6 +40,7 @@ SIGNATURES = {
     "sei_gemm_bf16_tn_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_gemm_bf16_atb_accumulate": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _vp]),
     "sei_gemm_bf16_tn": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _vp]),
+    "sei_gemm_bf16_tn_residual": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_ln_cl_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "sei_ln_cl_backward_workspace_bytes": (C.c_longlong, [_i]),
     "sei_ln_cl_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
@@ -49,8 +50,10 @@ SIGNATURES = {
     "sei_conv3x3_small_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sei_dwconv7_workspace_bytes": (C.c_longlong, [_i]),
     "sei_dwconv7_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sei_dwconv7_cl_residual_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "sei_dwconv7_wgrad_cl_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sei_gelu_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
+    "sei_gelu_bwd_colsum_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "sei_adam_step_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "sei_transpose_bf16": (C.c_int, [_vp, _vp, _i, _i, _vp]),
     "sei_bias_pattern_add_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _vp]),

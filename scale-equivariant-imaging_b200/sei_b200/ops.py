@@ -333,6 +333,26 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     return d
 
 
+def gemm_bf16_tn_residual(a, b, bias, res, res_scale=1.0):
+    """D[M,N] (bf16) = a[M,K] @ b[N,K]^T + bias[N] + res_scale * res[M,N]: a pointwise convolution added to a tensor of its
+    output's shape in the GEMM epilogue (sei_gemm_bf16_tn_residual)"""
+    for t, name in ((a, "a"), (b, "b"), (res, "res")):
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise SeiError(f"gemm_bf16_tn_residual: {name} must be a 2-D CUDA bf16 tensor with a contiguous last dimension")
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2 or tuple(res.shape) != (M, N):
+        raise SeiError("gemm_bf16_tn_residual: shape mismatch")
+    if bias is not None:
+        bias = _t(bias, "bias")
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn_residual(_ptr(a), _ptr(b), _ptr(d), _ptr(bias), _ptr(res), float(res_scale), M, N, K,
+                                                    a.stride(0), b.stride(0), N, res.stride(0), _stream(a)))
+    return d
+
+
 def gemm_bf16_tn_gelu_bwd(a, b, h):
     """D[M,N] (bf16) = (a[M,K] @ b[N,K]^T) * gelu'(h[M,N]): dgrad of the layer after a GELU with the GELU backward in the
     GEMM epilogue (sei_gemm_bf16_tn_gelu_bwd)"""
@@ -430,20 +450,42 @@ def padded_width(c, kind):
     raise SeiError(f"no supported channel count at or above {c} for {kind}")
 
 
+def ln_forward_raw(x, g32, b32, eps):
+    """(y, mean, rstd, small) of the channel LayerNorm of rows [T, C] (no autograd bookkeeping); g32 / b32: fp32 [C]"""
+    T, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(T, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+    small = not ln_cl_supported(x)
+    fwd = _lib.load().sei_ln_small_forward_bf16 if small else _lib.load().sei_ln_cl_forward_bf16
+    with torch.cuda.device(x.device):
+        check(fwd(_ptr(x), _ptr(g32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), T, Cc, float(eps), _stream(x)))
+    return y, mean, rstd, small
+
+
+def ln_backward_raw(gy, x, mean, rstd, g32, small):
+    """(dx, dgamma, dbeta) of the channel LayerNorm; gy, x: bf16 rows [T, C]"""
+    T, Cc = x.shape
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws_bytes = lib.sei_ln_small_workspace_bytes(Cc) if small else lib.sei_ln_cl_backward_workspace_bytes(Cc)
+    ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
+    bwd = lib.sei_ln_small_backward_bf16 if small else lib.sei_ln_cl_backward_bf16
+    with torch.cuda.device(x.device):
+        check(bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(dx), _ptr(dg), _ptr(db), _ptr(ws), T, Cc,
+                  _stream(x)))
+    return dx, dg, db
+
+
 class _LayerNormCL(torch.autograd.Function):
     """y = LayerNorm_C(x) on rows [T, C] (bf16), fp32 affine parameters; backward by the hand-written kernels"""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):
-        T, Cc = x.shape
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        y = torch.empty_like(x)
-        mean = torch.empty(T, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(T, dtype=torch.float32, device=x.device)
-        ctx.small = not ln_cl_supported(x)
-        fwd = _lib.load().sei_ln_small_forward_bf16 if ctx.small else _lib.load().sei_ln_cl_forward_bf16
-        with torch.cuda.device(x.device):
-            check(fwd(_ptr(x), _ptr(g32), _ptr(b32), _ptr(y), _ptr(mean), _ptr(rstd), T, Cc, float(eps), _stream(x)))
+        y, mean, rstd, ctx.small = ln_forward_raw(x, g32, b32, eps)
         ctx.save_for_backward(x, mean, rstd, g32)
         ctx.param_dtypes = (gamma.dtype, beta.dtype)
         return y
@@ -451,18 +493,7 @@ class _LayerNormCL(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, mean, rstd, g32 = ctx.saved_tensors
-        T, Cc = x.shape
-        gy = gy.contiguous()
-        lib = _lib.load()
-        dx = torch.empty_like(x)
-        dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        db = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        ws_bytes = lib.sei_ln_small_workspace_bytes(Cc) if ctx.small else lib.sei_ln_cl_backward_workspace_bytes(Cc)
-        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=x.device)
-        bwd = lib.sei_ln_small_backward_bf16 if ctx.small else lib.sei_ln_cl_backward_bf16
-        with torch.cuda.device(x.device):
-            check(bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g32), _ptr(dx), _ptr(dg), _ptr(db), _ptr(ws), T, Cc,
-                      _stream(x)))
+        dx, dg, db = ln_backward_raw(gy.contiguous(), x, mean, rstd, g32, ctx.small)
         return dx, dg.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]), None
 
 
@@ -526,12 +557,43 @@ def dwconv7_supported(x_bhwc):
             and x_bhwc.shape[3] % 8 == 0 and _lib.load().sei_dwconv7_workspace_bytes(int(x_bhwc.shape[3])) > 0)
 
 
-def _dwconv7_raw(x, wt, bias):
+def _dwconv7_raw(x, wt, bias, res=None, res_scale=1.0):
+    """depthwise 7x7 of x [B, H, W, C] with taps wt [49, C] (+ bias) (+ res_scale * res, added in the kernel's store)"""
     B, H, W, Cc = x.shape
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        check(_lib.load().sei_dwconv7_cl_bf16(_ptr(x), _ptr(wt), _ptr(bias), _ptr(y), B, H, W, Cc, _stream(x)))
+        if res is None:
+            check(_lib.load().sei_dwconv7_cl_bf16(_ptr(x), _ptr(wt), _ptr(bias), _ptr(y), B, H, W, Cc, _stream(x)))
+        else:
+            if res.shape != x.shape or res.dtype != x.dtype or not res.is_contiguous():
+                raise SeiError("dwconv7: the residual must be a contiguous tensor of the input's shape and dtype")
+            check(_lib.load().sei_dwconv7_cl_residual_bf16(_ptr(x), _ptr(wt), _ptr(bias), _ptr(res), float(res_scale), _ptr(y),
+                                                           B, H, W, Cc, _stream(x)))
     return y
+
+
+def dwconv7_wgrad_raw(gy, x):
+    """(gw [C, 49], gb [C]) fp32 of the depthwise 7x7 convolution; gy, x: bf16 [B, H, W, C]"""
+    B, H, W, Cc = x.shape
+    lib = _lib.load()
+    gw = torch.empty((Cc, 49), dtype=torch.float32, device=x.device)
+    gb = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.sei_dwconv7_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sei_dwconv7_wgrad_cl_bf16(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(ws), B, H, W, Cc, _stream(x)))
+    return gw, gb
+
+
+def gelu_bwd_colsum(h_rows, gy_rows):
+    """(gy * gelu'(h), fp32 column sums of that product) in one pass over bf16 rows [T, C] (sei_gelu_bwd_colsum_bf16)"""
+    T, Cc = h_rows.shape
+    lib = _lib.load()
+    gx = torch.empty_like(h_rows)
+    gb = torch.empty(Cc, dtype=torch.float32, device=h_rows.device)
+    ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=h_rows.device)
+    with torch.cuda.device(h_rows.device):
+        check(lib.sei_gelu_bwd_colsum_bf16(_ptr(h_rows), _ptr(gy_rows), _ptr(gx), _ptr(gb), _ptr(ws), T, Cc, _stream(h_rows)))
+    return gx, gb
 
 
 class _DwConv7(torch.autograd.Function):
@@ -556,12 +618,7 @@ class _DwConv7(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = _dwconv7_raw(gy, w32.flip(1).t().contiguous(), None)      # the same convolution with the taps flipped
-        lib = _lib.load()
-        gw = torch.empty((Cc, 49), dtype=torch.float32, device=x.device)
-        gb = torch.empty(Cc, dtype=torch.float32, device=x.device)
-        ws = torch.empty(int(lib.sei_dwconv7_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
-        with torch.cuda.device(x.device):
-            check(lib.sei_dwconv7_wgrad_cl_bf16(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(ws), B, H, W, Cc, _stream(x)))
+        gw, gb = dwconv7_wgrad_raw(gy, x)
         return gx, gw.view(ctx.wshape).to(ctx.dtypes[0]), (gb.to(ctx.dtypes[1]) if ctx.has_bias else None)
 
 

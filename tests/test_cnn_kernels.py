@@ -324,3 +324,82 @@ def test_gelu_matches_torch(dev):
     y4 = ops.gelu(x4)
     assert y4.stride() == x4.stride()
     assert rel_err(y4.float().cpu().numpy(), F.gelu(x4.float()).cpu().numpy()) < 4e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(256, 128, 512), (1000, 32, 128), (4096, 512, 2048), (130, 40, 72), (300, 264, 72),
+                                   (2048, 64, 256)])
+def test_gemm_residual_epilogue(dev, M, N, K):
+    """D = A B^T + bias + s R with the addition in the GEMM epilogue (single-CTA TMA-store path, direct-store path for
+    narrow outputs, CTA-pair kernel) vs the fp32 formulation"""
+    from sei_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).bfloat16()
+    for s in (1.0, 2.0):
+        ref = a.float() @ b.float().t() + bias + s * r.float()
+        d = ops.gemm_bf16_tn_residual(a, b, bias, r, s)
+        assert d.dtype == torch.bfloat16 and d.shape == (M, N)
+        assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
+    d0 = ops.gemm_bf16_tn_residual(a, b, None, r, 1.0)
+    assert rel_err(d0.float().cpu().numpy(), (a.float() @ b.float().t() + r.float()).cpu().numpy()) < 6e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8)])
+def test_dwconv7_residual_store(dev, B, H, W, C):
+    """y = dwconv7(x) + s * res with the addition in the kernel's store"""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(C)
+    x = torch.randn(B, H, W, C, device=dev).bfloat16()
+    res = torch.randn(B, H, W, C, device=dev).bfloat16()
+    w = torch.randn(C, 49, device=dev) / 7
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.view(C, 1, 7, 7), None, padding=3, groups=C).permute(0, 2, 3, 1)
+    for s in (1.0, 2.0):
+        y = ops._dwconv7_raw(x, w.t().contiguous(), None, res=res, res_scale=s)
+        assert rel_err(y.float().cpu().numpy(), (ref + s * res.float()).cpu().numpy()) < 6e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,C", [(1000, 128), (4096, 512), (333, 2048), (77, 8), (5000, 32)])
+def test_gelu_bwd_colsum(dev, T, C):
+    """gy * gelu'(h) and its column sums in one pass vs the two separate kernels (bit-identical products; sums within
+    fp32 reordering)"""
+    from sei_b200 import ops
+    torch.manual_seed(T + C)
+    h = (2 * torch.randn(T, C, device=dev)).bfloat16()
+    gy = torch.randn(T, C, device=dev).bfloat16()
+    gx, gb = ops.gelu_bwd_colsum(h, gy)
+    ha = h.clone().requires_grad_(True)
+    ops.gelu(ha).backward(gy)
+    assert torch.equal(gx, ha.grad)
+    ref = ha.grad.float().sum(0)
+    assert rel_err(gb.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,res_scale", [(32, 1.0), (128, 2.0), (512, 1.0)])
+def test_convblock_single_node_matches_op_by_op(dev, C, res_scale, monkeypatch):
+    """ConvBlock as one autograd node (additions fused into the GEMM epilogue / depthwise store, bias gradient inside
+    the GELU backward) against the op-by-op autograd graph of the same kernels"""
+    import models.convolutional as mc
+    torch.manual_seed(C)
+    blk = mc.ConvBlock(C).to(dev)
+    x = torch.randn(2, C, 24, 16, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(2, C, 24, 16, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for node in (True, False):
+        monkeypatch.setattr(mc, "_CONVBLOCK_NODE", node)
+        blk.zero_grad(set_to_none=True)
+        xa = x.clone().requires_grad_(True)
+        y = blk(xa, res_scale=res_scale)
+        y.backward(gy)
+        outs.append((y.detach().float(), xa.grad.float(), {n: p.grad.detach().float().clone() for n, p in blk.named_parameters()}))
+    (y1, gx1, g1), (y0, gx0, g0) = outs
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 8e-3          # one bf16 rounding instead of two
+    assert rel_err(gx1.cpu().numpy(), gx0.cpu().numpy()) < 8e-3
+    for n in g0:
+        assert rel_err(g1[n].cpu().numpy(), g0[n].cpu().numpy()) < 2e-3, n
