@@ -200,6 +200,18 @@ int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, const float
                               long long M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_r,
                               void* stream);
 
+/* Aout (bf16) = gelu(A B^T + bias) and Dout (bf16) = gelu'(A B^T + bias), both written from the GEMM epilogue:
+ * ConvBlock.conv2 followed by ConvBlock.gelu (reference src/models/convolutional.py:40-41, 46-47) without the
+ * pre-activation ever reaching memory.  The pre-activation is rounded to bf16 before the GELU (the value an unfused
+ * bf16 pipeline would store), erf-form GELU.  N > 32; Aout / Dout: row pitch ldo (multiple of 8). */
+int sei_gemm_bf16_tn_gelu_dual(const void* A, const void* B, const float* bias, void* Aout, void* Dout, long long M, int N,
+                               int K, long long lda, long long ldb, long long ldo, void* stream);
+
+/* D (bf16) = (A B^T) * Mult element-wise in the epilogue: the input gradient of ConvBlock.conv3 (:42) times the stored
+ * gelu' -- the backward of ConvBlock.gelu without a pass of its own.  Mult: bf16 [M, N], row pitch ld_m. */
+int sei_gemm_bf16_tn_mul(const void* A, const void* B, const void* Mult, void* D, long long M, int N, int K,
+                         long long lda, long long ldb, long long ldd, long long ld_m, void* stream);
+
 /* D[M, N] (fp32) = A[K, M]^T * B[K, N]: both operands are read with the contraction index as their ROW (UMMA MN-major
  * shared-memory layout), so the weight gradient dL/dW = (dL/dy)^T x of a pointwise convolution needs no transposed
  * copies of the activations.  lda, ldb multiples of 8; K = pixels.  Split-K with fp32 atomics when M*N is small. */

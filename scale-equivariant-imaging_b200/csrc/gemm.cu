@@ -143,9 +143,11 @@ struct GemmParams {
     int accumulate;      // fp32 output: add to D instead of overwriting it (weight gradients accumulated in place)
     const __nv_bfloat16* gelu_h;   // optional [M, N] (row pitch ld_h): D = (A B^T) * gelu'(gelu_h)  (TMA-store epilogue only)
     int ld_h;
-    const __nv_bfloat16* res;      // optional [M, N] (row pitch ld_r): D = A B^T + bias + res_scale * res  (bf16 output)
-    int ld_r;
+    const __nv_bfloat16* res;      // optional [M, N] (row pitch ld_r): D = A B^T + bias + res_scale * res  (bf16 output),
+    int ld_r;                      //   or, with res_mul, D = (A B^T + bias) * res
     float res_scale;
+    int res_mul;
+    int gelu_dual;                 // D = gelu(A B^T + bias) and D2 (second tensor map) = gelu'(A B^T + bias)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
@@ -154,12 +156,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 }
 
 
-// 128-bit read-only load that does not allocate in L1 (operands every lane reads exactly once)
-__device__ __forceinline__ uint4 ld_nc_na(const uint4* ptr)
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8])
 {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
-    return v;
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
+                   t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    return pk;
 }
 
 // The GELU backward fused into the input-gradient GEMM of the layer that follows it (reference ConvBlock: conv2 -> GELU
@@ -212,7 +216,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
         if (col0 + 32 <= p.N && (p.ld_r & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                const uint4 raw = ld_nc_na(reinterpret_cast<const uint4*>(rp + j));
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp + j));
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -272,17 +276,30 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
 // -- and the residual row chunk (128 contiguous bytes per lane) is requested BEFORE the accumulator wait so that the two
 // latencies overlap.
 template <int NSLAB>
-__device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const CUtensorMap* map_d, uint32_t taddr, int row0,
-                                                      int col0, int lane, bool add_bias, unsigned char* slab, float* sb)
+__device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const CUtensorMap* map_d, const CUtensorMap* map_d2,
+                                                      uint32_t taddr, int row0, int col0, int lane, bool add_bias,
+                                                      unsigned char* slab, float* sb)
 {
     const int row = row0 + lane;
     uint4 rr[8];
     const bool has_res = p.res != nullptr;
     if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + (size_t)row * p.ld_r + col0);
+        // The residual / multiplier chunk (32 rows x 128 B) is copied into the warp's own slab with coalesced 16-byte
+        // asynchronous copies (a lane moves chunk lane % 8 of rows lane / 8 + 4 i: four whole rows per instruction, the
+        // slab's swizzled layout) while the accumulator is fetched; each lane then reads ITS row back.  Per-lane row
+        // loads straight from global memory touch 32 sectors per instruction and re-fetch every sector (the kernel
+        // leaves no room for L1): the input-gradient GEMM with the multiplier took 598 us against 162 us without.
+        if (lane == 0) bulk_wait_read<0>();      // the slab is free (the previous store has read it)
+        __syncwarp();
+        const int ch = lane & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            rr[j] = (row < p.M && col0 + 8 * j + 8 <= p.N) ? ld_nc_na(rp + j) : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 8; ++i) {
+            const int rl = (lane >> 3) + 4 * i;
+            const bool ok = row0 + rl < p.M && col0 + 8 * ch + 8 <= p.N;
+            cp_async16(slab + rl * 128 + ((ch ^ (rl & 7)) << 4),
+                       p.res + (ok ? (size_t)(row0 + rl) * p.ld_r + col0 + 8 * ch : 0), ok);
+        }
+        cp_async_commit();
     }
     add_bias = add_bias && p.bias != nullptr;
     if (add_bias) {
@@ -294,8 +311,16 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
     tmem_ld_32x32(taddr + 32u, r1);
     tmem_ld_wait();
     if (p.gelu_h) epilogue_gelu_bwd(p, row, col0, r0, r1);
+    if (has_res) {
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4));
+    }
     if (lane == 0) bulk_wait_read<NSLAB - 1>();   // the store that last read this slab has finished reading
     __syncwarp();                            // (also: the bias row is visible to every lane)
+    const bool dual = p.gelu_dual != 0;
+    uint4 dpk[8];                            // gelu'(h) of the chunk (dual mode), stored after the activations
 #pragma unroll
     for (int j = 0; j < 8; ++j) {            // 8 chunks of 8 bf16
         float v[8];
@@ -311,25 +336,56 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
         }
         if (has_res) {
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+            if (p.res_mul) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                v[2 * e] = fmaf(p.res_scale, f.x, v[2 * e]);
-                v[2 * e + 1] = fmaf(p.res_scale, f.y, v[2 * e + 1]);
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[2 * e] *= f.x;
+                    v[2 * e + 1] *= f.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[2 * e] = fmaf(p.res_scale, f.x, v[2 * e]);
+                    v[2 * e + 1] = fmaf(p.res_scale, f.y, v[2 * e + 1]);
+                }
             }
         }
-        uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]),
-                       t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk;
+        if (dual) {
+            float dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // the pre-activation is rounded to bf16 first: that is the value the unfused path stores and both of its
+                // passes read
+                const float hq = __bfloat162float(__float2bfloat16_rn(v[e]));
+                float Phi, phi;
+                gelu_parts(hq, Phi, phi);
+                dv[e] = fmaf(hq, phi, Phi);
+                v[e] = hq * Phi;
+            }
+            dpk[j] = pack8_bf16(dv);
+        }
+        *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8_bf16(v);
     }
     fence_proxy_async();                     // generic-proxy writes -> visible to the TMA engine
     __syncwarp();
-    if (lane == 0 && col0 < p.N && row0 < p.M) {
+    const bool in_range = col0 < p.N && row0 < p.M;
+    if (lane == 0 && in_range) {
         tma_store_2d(map_d, slab, col0, row0);
         bulk_commit();
+    }
+    if (dual) {
+        if (lane == 0) bulk_wait_read<0>();  // the activations have left the slab
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = dpk[j];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && in_range) {
+            tma_store_2d(map_d2, slab, col0, row0);
+            bulk_commit();
+        }
     }
 }
 
@@ -346,7 +402,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
 template <int BN, int STAGES, bool OUT_F32, bool MN = false, int EW = 4>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
+                    const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_d2,
+                    const __grid_constant__ GemmParams p)
 {
     constexpr int BM = kGemmBM, BK = kGemmBK;
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -472,7 +529,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (!OUT_F32 && p.tma_store && BN >= 64) {
 #pragma unroll 1
                 for (int c = 64 * sub; c < BN; c += 64 * NSUB)
-                    gemm_epilogue_chunk64<NSLAB>(p, &map_d, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, split == 0,
+                    gemm_epilogue_chunk64<NSLAB>(p, &map_d, &map_d2, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, split == 0,
                                                  slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
             } else {
 #pragma unroll 1
@@ -563,7 +620,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
 template <int STAGES, int EW = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p)
+                         const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_d2,
+                         const __grid_constant__ GemmParams p)
 {
     constexpr int BM = kGemmBM, BK = kGemmBK, BN = 256, BNH = 128;      // per CTA: 128 rows of A, 128 columns of B
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -662,7 +720,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
             for (int c = 64 * sub; c < BN; c += 64 * NSUB)
-                gemm_epilogue_chunk64<NSLAB>(p, &map_d, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, true,
+                gemm_epilogue_chunk64<NSLAB>(p, &map_d, &map_d2, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, true,
                                              slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
             tc_fence_before();
             mbar_arrive_leader(&tmem_empty_bar[acc]);       // this thread is done reading the accumulator stage
@@ -1072,7 +1130,7 @@ static int launch_gemm_mn(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
     const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
     const unsigned grid = (unsigned)std::min<long long>(tiles * p.splits, sm_count);
     SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true, true>, smem));
-    gemm_bf16_tn_kernel<BN, STAGES, true, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, ma, p);
+    gemm_bf16_tn_kernel<BN, STAGES, true, true><<<grid, kGemmThreads, smem, st>>>(ma, mb, ma, ma, p);
     return finish_launch("gemm_bf16_mn_kernel");
 }
 
@@ -1085,8 +1143,8 @@ constexpr size_t gemm_smem_bytes(bool out_f32)
 }
 
 template <int BN, int STAGES, int EW>
-static int launch_gemm_ew(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmParams& p, bool out_f32,
-                          int sm_count, cudaStream_t st)
+static int launch_gemm_ew(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& md2,
+                          const GemmParams& p, bool out_f32, int sm_count, cudaStream_t st)
 {
     const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
     const unsigned grid = (unsigned)std::min<long long>(tiles * p.splits, sm_count);
@@ -1094,12 +1152,12 @@ static int launch_gemm_ew(const CUtensorMap& ma, const CUtensorMap& mb, const CU
     if (out_f32) {
         constexpr size_t smem = gemm_smem_bytes<BN, STAGES, EW>(true);
         SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, true, false, EW>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, true, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, p);
+        gemm_bf16_tn_kernel<BN, STAGES, true, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, md2, p);
     } else {
         constexpr size_t smem = gemm_smem_bytes<BN, STAGES, EW>(false);
         static_assert(smem + 4096 <= 227 * 1024, "operand ring + epilogue slabs + static barriers / bias strips exceed the shared memory of an SM");
         SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false, false, EW>, smem));
-        gemm_bf16_tn_kernel<BN, STAGES, false, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, p);
+        gemm_bf16_tn_kernel<BN, STAGES, false, false, EW><<<grid, threads, smem, st>>>(ma, mb, md, md2, p);
     }
     return finish_launch("gemm_bf16_tn_kernel");
 }
@@ -1238,9 +1296,11 @@ static void choose_splits(long long tiles, int units, int nk, int* splits, int* 
 struct GemmEpilogueExtra {
     const void* gelu_h = nullptr;      // multiply by gelu'(gelu_h)
     long long ld_h = 0;
-    const void* res = nullptr;         // add res_scale * res
+    const void* res = nullptr;         // add res_scale * res (or multiply by res: res_mul)
     long long ld_r = 0;
     float res_scale = 1.0f;
+    int res_mul = 0;
+    void* d2 = nullptr;                // gelu_dual: second output gelu'(.) (same shape and pitch as D)
 };
 
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
@@ -1265,6 +1325,31 @@ extern "C" int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, 
     GemmEpilogueExtra ex;
     ex.res = R; ex.ld_r = ld_r; ex.res_scale = res_scale;
     return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
+}
+
+// Aout (bf16) = gelu(A B^T + bias), Dout (bf16) = gelu'(A B^T + bias): ConvBlock.conv2 and ConvBlock.gelu (reference
+// src/models/convolutional.py:40-41) as one kernel -- the pre-activation never reaches memory; the stored derivative
+// turns the GELU backward into the multiplier epilogue below (one erf evaluation per element and step instead of two).
+extern "C" int sei_gemm_bf16_tn_gelu_dual(const void* A, const void* B, const float* bias, void* Aout, void* Dout,
+                                          long long M, int N, int K, long long lda, long long ldb, long long ldo, void* stream)
+{
+    SEI_REQUIRE(Aout && Dout && aligned16(Dout), "null / misaligned output");
+    SEI_REQUIRE(N > 32 && ldo % 8 == 0, "the fused GELU needs N > 32 and an output pitch that is a multiple of 8 (N=%d)", N);
+    GemmEpilogueExtra ex;
+    ex.d2 = Dout;
+    return gemm_bf16_tn_impl(A, B, Aout, bias, M, N, K, lda, ldb, ldo, 0, 0, ex, stream);
+}
+
+// D (bf16) = (A B^T) * Mult, element-wise in the epilogue: the input gradient of ConvBlock.conv3 multiplied by the stored
+// gelu' (the GELU backward without a pass of its own).  Mult: bf16 [M, N] with row pitch ld_m (multiple of 8).
+extern "C" int sei_gemm_bf16_tn_mul(const void* A, const void* B, const void* Mult, void* D, long long M, int N, int K,
+                                    long long lda, long long ldb, long long ldd, long long ld_m, void* stream)
+{
+    SEI_REQUIRE(Mult != nullptr && aligned16(Mult) && ld_m % 8 == 0 && ld_m >= N, "Mult must be 16-byte aligned with a row pitch >= N that is a multiple of 8");
+    SEI_REQUIRE(N > 32 && N % 8 == 0 && ldd % 8 == 0, "the multiplier epilogue needs N > 32, N %% 8 == 0 and ldd %% 8 == 0 (N=%d)", N);
+    GemmEpilogueExtra ex;
+    ex.res = Mult; ex.ld_r = ld_m; ex.res_mul = 1;
+    return gemm_bf16_tn_impl(A, B, D, nullptr, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
 }
 
 // D (bf16) = (A B^T) * gelu'(H): the input gradient of `conv3` with the GELU backward applied in the epilogue.
@@ -1307,15 +1392,21 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
     p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
     p.res = static_cast<const __nv_bfloat16*>(ex.res); p.ld_r = (int)ex.ld_r; p.res_scale = ex.res_scale;
+    p.res_mul = ex.res_mul; p.gelu_dual = ex.d2 ? 1 : 0;
     SEI_REQUIRE(!ex.res || !out_f32, "the fused residual is a bf16-output epilogue");
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
     p.tma_store = (!out_f32 && bn >= 64 && ldd % 8 == 0 && !(nts && *nts == '1')) ? 1 : 0;
     SEI_REQUIRE(!gelu_h || p.tma_store, "the fused GELU backward needs the TMA-store epilogue (N >= 64, ldd %% 8 == 0)");
-    CUtensorMap md = ma;
+    SEI_REQUIRE(!(ex.d2 || ex.res_mul) || p.tma_store, "the fused GELU / multiplier epilogues need the TMA-store path (N > 32, ldd %% 8 == 0)");
+    CUtensorMap md = ma, md2 = ma;
     if (p.tma_store) {
         rc = make_map_bf16(&md, D, M, N, ldd, 32);
         if (rc) return rc;
+        if (ex.d2) {
+            rc = make_map_bf16(&md2, ex.d2, M, N, ldd, 32);
+            if (rc) return rc;
+        }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // split-K for the weight-gradient shapes (few output tiles, very long K = pixels): fp32 output only
@@ -1340,27 +1431,27 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
             constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 8 * 32 * 128;
             static_assert(smem2 + 4096 <= 227 * 1024, "CTA-pair kernel: ring + slabs + barriers exceed the shared memory of an SM");
             SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 8>, smem2));
-            gemm_bf16_tn_2cta_kernel<ST2, 8><<<grid, 64 + 32 * 8, smem2, st>>>(ma, mb2, md, p);
+            gemm_bf16_tn_2cta_kernel<ST2, 8><<<grid, 64 + 32 * 8, smem2, st>>>(ma, mb2, md, md2, p);
         } else {
             constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 4 * 2 * 32 * 128;
             SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 4>, smem2));
-            gemm_bf16_tn_2cta_kernel<ST2, 4><<<grid, 64 + 32 * 4, smem2, st>>>(ma, mb2, md, p);
+            gemm_bf16_tn_2cta_kernel<ST2, 4><<<grid, 64 + 32 * 4, smem2, st>>>(ma, mb2, md, md2, p);
         }
         return finish_launch("gemm_bf16_tn_2cta_kernel");
     }
     if (gemm_epilogue_warps() == 8) {        // eight epilogue warps; one operand stage fewer where the slabs need the room
         switch (bn) {
-        case 32: return launch_gemm_ew<32, 8, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-        case 64: return launch_gemm_ew<64, 7, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-        case 128: return launch_gemm_ew<128, 5, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-        default: return launch_gemm_ew<256, 3, 8>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+        case 32: return launch_gemm_ew<32, 8, 8>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+        case 64: return launch_gemm_ew<64, 7, 8>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+        case 128: return launch_gemm_ew<128, 5, 8>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+        default: return launch_gemm_ew<256, 3, 8>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
         }
     }
     switch (bn) {
-    case 32: return launch_gemm_ew<32, 8, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    case 64: return launch_gemm_ew<64, 7, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    case 128: return launch_gemm_ew<128, 5, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
-    default: return launch_gemm_ew<256, 3, 4>(ma, mb, md, p, out_f32 != 0, dp.sm_count, st);
+    case 32: return launch_gemm_ew<32, 8, 4>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+    case 64: return launch_gemm_ew<64, 7, 4>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+    case 128: return launch_gemm_ew<128, 5, 4>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
+    default: return launch_gemm_ew<256, 3, 4>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
     }
 }
 
@@ -1404,7 +1495,7 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
-    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f;
+    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f; p.res_mul = 0; p.gelu_dual = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);

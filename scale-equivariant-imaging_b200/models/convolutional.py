@@ -43,6 +43,13 @@ _GELU_FUSION = __import__("os").environ.get("SEI_GELU_FUSION", "0") == "1"
 # ConvBlock as one autograd node with its additions fused into the neighbouring kernels (SEI_CONVBLOCK_NODE=0: the
 # op-by-op path, for A/B measurements)
 _CONVBLOCK_NODE = __import__("os").environ.get("SEI_CONVBLOCK_NODE", "1") == "1"
+# GELU and its derivative written from conv2's GEMM epilogue, GELU backward as a multiplier in conv3's input-gradient
+# epilogue (SEI_GELU_EPILOGUE=0: separate GELU kernels, for A/B measurements)
+# -- from this channel count on (0 = never).  Measured per level (benchmarks/mlp_bench.py, profiles/r02_mlp_bench*.md):
+# the erf arithmetic of 268 M elements costs the same at every level, but only the deep levels' tiles spend long enough
+# in the tensor core for eight epilogue warps to hide it; at the shallow levels the separate, full-occupancy GELU
+# kernels are faster.
+_GELU_EPILOGUE_MIN_C = int(__import__("os").environ.get("SEI_GELU_EPILOGUE_MIN_C", "512"))
 
 
 def _gemm_tn(a, b, bias, out_dtype):
@@ -251,9 +258,15 @@ class _ConvBlockFn(torch.autograd.Function):
         _, w3_bf = block.conv3._weight_matrix()
         t1 = ops._dwconv7_raw(xl, dw32.t().contiguous(), dwb32)
         t2, mean, rstd, small = ops.ln_forward_raw(t1.view(T, C), g32, be32, block.ln.ln.eps)
-        h = _gemm_tn(t2, w2_bf, b2, COMPUTE_DTYPE)
-        a = ops.gelu_raw(h)
+        gelu_epilogue = 0 < _GELU_EPILOGUE_MIN_C <= C
+        if gelu_epilogue:
+            # conv2 + GELU in one kernel: gelu(h) and gelu'(h) leave the GEMM epilogue, h itself is never stored
+            a, h = ops.gemm_bf16_tn_gelu_dual(t2, w2_bf, b2)          # (`h` holds gelu'(h) on this path)
+        else:
+            h = _gemm_tn(t2, w2_bf, b2, COMPUTE_DTYPE)
+            a = ops.gelu_raw(h)
         out = ops.gemm_bf16_tn_residual(a, w3_bf, b3, xl.view(T, C), res_scale)
+        ctx.gelu_epilogue = gelu_epilogue
         ctx.save_for_backward(xl, t1, mean, rstd, t2, h, a, dw32, g32)
         ctx.block, ctx.res_scale, ctx.small = block, float(res_scale), small
         ctx.dtypes = (dw_w.dtype, None if dw_b is None else dw_b.dtype, ln_g.dtype, ln_b.dtype)
@@ -271,9 +284,13 @@ class _ConvBlockFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gb3 = _colsum(g2) if (ctx.has_bias[1] and need[10]) else None
         gw3 = _wgrad_into(block.conv3.weight, g2, a) if need[9] else None
-        ga = _gemm_tn(g2, block.conv3._weight_matrix_t(), None, COMPUTE_DTYPE)          # [T, 4C]
-        gh, gb2 = ops.gelu_bwd_colsum(h, ga)
-        del ga
+        if ctx.gelu_epilogue:
+            gh = ops.gemm_bf16_tn_mul(g2, block.conv3._weight_matrix_t(), h)            # (g W3) * gelu'(h): [T, 4C]
+            gb2 = _colsum(gh) if (ctx.has_bias[0] and need[8]) else None
+        else:
+            ga = _gemm_tn(g2, block.conv3._weight_matrix_t(), None, COMPUTE_DTYPE)      # [T, 4C]
+            gh, gb2 = ops.gelu_bwd_colsum(h, ga)
+            del ga
         gw2 = _wgrad_into(block.conv2.weight, gh, t2) if need[7] else None
         gt2 = _gemm_tn(gh, block.conv2._weight_matrix_t(), None, COMPUTE_DTYPE)         # [T, C]
         del gh

@@ -353,6 +353,46 @@ def gemm_bf16_tn_residual(a, b, bias, res, res_scale=1.0):
     return d
 
 
+def _check_2d_bf16(fn, **tensors):
+    for name, t in tensors.items():
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise SeiError(f"{fn}: {name} must be a 2-D CUDA bf16 tensor with a contiguous last dimension")
+
+
+def gemm_bf16_tn_gelu_dual(a, b, bias):
+    """(gelu(h), gelu'(h)) with h = a[M,K] @ b[N,K]^T + bias, both bf16 [M, N], written from the GEMM epilogue
+    (sei_gemm_bf16_tn_gelu_dual): the pre-activation never reaches memory"""
+    _check_2d_bf16("gemm_bf16_tn_gelu_dual", a=a, b=b)
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2:
+        raise SeiError("gemm_bf16_tn_gelu_dual: inner dimensions differ")
+    if bias is not None:
+        bias = _t(bias, "bias")
+    act = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    der = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn_gelu_dual(_ptr(a), _ptr(b), _ptr(bias), _ptr(act), _ptr(der), M, N, K,
+                                                     a.stride(0), b.stride(0), N, _stream(a)))
+    return act, der
+
+
+def gemm_bf16_tn_mul(a, b, mult):
+    """D[M,N] (bf16) = (a[M,K] @ b[N,K]^T) * mult[M,N] with the product applied in the GEMM epilogue (sei_gemm_bf16_tn_mul)"""
+    _check_2d_bf16("gemm_bf16_tn_mul", a=a, b=b, mult=mult)
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2 or tuple(mult.shape) != (M, N):
+        raise SeiError("gemm_bf16_tn_mul: shape mismatch")
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn_mul(_ptr(a), _ptr(b), _ptr(mult), _ptr(d), M, N, K, a.stride(0), b.stride(0), N,
+                                               mult.stride(0), _stream(a)))
+    return d
+
+
 def gemm_bf16_tn_gelu_bwd(a, b, h):
     """D[M,N] (bf16) = (a[M,K] @ b[N,K]^T) * gelu'(h[M,N]): dgrad of the layer after a GELU with the GELU backward in the
     GEMM epilogue (sei_gemm_bf16_tn_gelu_bwd)"""

@@ -387,6 +387,7 @@ def test_convblock_single_node_matches_op_by_op(dev, C, res_scale, monkeypatch):
     the GELU backward) against the op-by-op autograd graph of the same kernels"""
     import models.convolutional as mc
     torch.manual_seed(C)
+    monkeypatch.setattr(mc, "_GELU_EPILOGUE_MIN_C", 128)       # C = 32: separate GELU kernels; 128, 512: GEMM epilogues
     blk = mc.ConvBlock(C).to(dev)
     x = torch.randn(2, C, 24, 16, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
     gy = torch.randn(2, C, 24, 16, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
@@ -401,5 +402,31 @@ def test_convblock_single_node_matches_op_by_op(dev, C, res_scale, monkeypatch):
     (y1, gx1, g1), (y0, gx0, g0) = outs
     assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 8e-3          # one bf16 rounding instead of two
     assert rel_err(gx1.cpu().numpy(), gx0.cpu().numpy()) < 8e-3
-    for n in g0:
-        assert rel_err(g1[n].cpu().numpy(), g0[n].cpu().numpy()) < 2e-3, n
+    for n in g0:       # (the stored gelu' is rounded to bf16 on the epilogue path: 2^-9 relative per element)
+        assert rel_err(g1[n].cpu().numpy(), g0[n].cpu().numpy()) < 6e-3, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(256, 128, 32), (1000, 512, 128), (4096, 2048, 512), (130, 72, 40), (300, 264, 72)])
+def test_gemm_gelu_dual_and_multiplier_epilogues(dev, M, N, K):
+    """conv2 + GELU as one kernel (gelu and gelu' written from the GEMM epilogue) and the multiplier epilogue of conv3's
+    input gradient, vs the fp32 formulation on the same bf16 operands"""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bias = 0.3 * torch.randn(N, device=dev)
+    act, der = ops.gemm_bf16_tn_gelu_dual(a, b, bias)
+    h = (a.float() @ b.float().t() + bias).bfloat16().float().requires_grad_(True)     # the rounded pre-activation
+    ref_act = F.gelu(h)
+    ref_act.sum().backward()
+    assert rel_err(act.float().cpu().numpy(), ref_act.detach().cpu().numpy()) < 8e-3
+    assert rel_err(der.float().cpu().numpy(), h.grad.cpu().numpy()) < 8e-3
+    # away from roundings of h that flip with the accumulation order, the values are those of the separate GELU kernel
+    h_sei = ops.gemm_bf16_tn(a, b, bias)
+    assert torch.equal(act, ops.gelu_raw(h_sei))
+    mult = torch.randn(M, N, device=dev).bfloat16()
+    d = ops.gemm_bf16_tn_mul(a, b, mult)
+    ref = (a.float() @ b.float().t()) * mult.float()
+    assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
