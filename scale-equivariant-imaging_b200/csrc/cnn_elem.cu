@@ -15,6 +15,7 @@
 #include "gelu.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sei {
 
@@ -1019,15 +1020,33 @@ static void dw_wgrad_shape(int C, int sm_count, int* CQB, int* NG, int* gx, int*
 
 }  // namespace sei
 
+namespace sei {      // csrc/dwconv_tile.cu: shared-memory tile kernels for channel counts that are multiples of 64
+bool dwconv7_tile_supported(int C);
+int dwconv7_tile_wgrad_slots(int C, int sm_count);
+int dwconv7_tile_forward(const void* x, const float* wt, const float* bias, const void* res, float res_scale, void* y, int B,
+                         int H, int W, int C, cudaStream_t st);
+int dwconv7_tile_wgrad(const void* gy, const void* x, float* partial, int slots, int B, int H, int W, int C, cudaStream_t st);
+}
+static bool dwconv7_use_tiles(int C)
+{
+    const char* e = getenv("SEI_DWCONV_TILE");           // A/B switch: 0 = the register-window kernels of round 1
+    return dwconv7_tile_supported(C) && !(e && *e == '0');
+}
+
 extern "C" long long sei_dwconv7_workspace_bytes(int C)
 {
     DeviceProps dp;
     if (get_device_props(&dp) || C < 8 || C % 8) return -1;
     const int cqn = C / 4;
-    if (!(cqn % 32 == 0 || 32 % cqn == 0)) return -1;
-    int CQB, NG, gx, gy;
-    dw_wgrad_shape(C, dp.sm_count, &CQB, &NG, &gx, &gy);
-    return (long long)gx * C * 50 * (long long)sizeof(float);
+    long long bytes = -1;
+    if (cqn % 32 == 0 || 32 % cqn == 0) {
+        int CQB, NG, gx, gy;
+        dw_wgrad_shape(C, dp.sm_count, &CQB, &NG, &gx, &gy);
+        bytes = (long long)gx * C * 50 * (long long)sizeof(float);
+    }
+    if (dwconv7_tile_supported(C))
+        bytes = std::max(bytes, (long long)dwconv7_tile_wgrad_slots(C, dp.sm_count) * C * 50 * (long long)sizeof(float));
+    return bytes;
 }
 
 static int dwconv7_impl(const void* x, const float* wt, const float* bias, const void* res, float res_scale, void* y,
@@ -1060,6 +1079,7 @@ static int dwconv7_impl(const void* x, const float* wt, const float* bias, const
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
+    if (dwconv7_use_tiles(C)) return dwconv7_tile_forward(x, wt, bias, res, res_scale, y, B, H, W, C, reinterpret_cast<cudaStream_t>(stream));
     DwParams p = {};
     p.x = static_cast<const __nv_bfloat16*>(x); p.wt = wt; p.bias = bias; p.y = static_cast<__nv_bfloat16*>(y);
     p.res = static_cast<const __nv_bfloat16*>(res); p.res_scale = res_scale;
@@ -1084,7 +1104,8 @@ extern "C" int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* g
 {
     SEI_REQUIRE(gy && x && gw && gb && workspace, "null pointer argument");
     SEI_REQUIRE(B >= 0 && H > 0 && W > 0 && C >= 8 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
-    SEI_REQUIRE(sei_dwconv7_workspace_bytes(C) > 0, "channel count %d unsupported by the depthwise weight-gradient kernel", C);
+    SEI_REQUIRE(sei_dwconv7_workspace_bytes(C) > 0 && (dwconv7_use_tiles(C) || (C / 4) % 32 == 0 || 32 % (C / 4) == 0),
+                "channel count %d unsupported by the depthwise weight-gradient kernel", C);
     SEI_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(workspace), "operands must be 16-byte aligned");
     DeviceProps dp;
     int rc = get_device_props(&dp);
@@ -1094,6 +1115,13 @@ extern "C" int sei_dwconv7_wgrad_cl_bf16(const void* gy, const void* x, float* g
         SEI_CUDA(cudaMemsetAsync(gw, 0, (size_t)C * 49 * 4, st));
         SEI_CUDA(cudaMemsetAsync(gb, 0, (size_t)C * 4, st));
         return 0;
+    }
+    if (dwconv7_use_tiles(C)) {
+        const int slots = dwconv7_tile_wgrad_slots(C, dp.sm_count);
+        rc = dwconv7_tile_wgrad(gy, x, static_cast<float*>(workspace), slots, B, H, W, C, st);
+        if (rc) return rc;
+        colsum_final_kernel<<<(C * 50 + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), gw, gb, slots, C * 50, C * 49);
+        return finish_launch("colsum_final_kernel");
     }
     DwParams p = {};
     p.x = static_cast<const __nv_bfloat16*>(x); p.gy = static_cast<const __nv_bfloat16*>(gy);

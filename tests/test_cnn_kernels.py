@@ -276,7 +276,8 @@ def test_conv3x3_small_matches_torch(dev, B, H, W, Cin, Cout, need_gx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8), (1, 5, 9, 256), (2, 33, 8, 16)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8), (1, 5, 9, 256), (2, 33, 8, 16),
+                                     (2, 40, 37, 64), (1, 33, 50, 192), (3, 16, 16, 512)])
 def test_dwconv7_matches_torch(dev, B, H, W, C):
     """depthwise 7x7 (ConvBlock.conv1) vs F.conv2d(groups=C) in fp32 on the same bf16 input"""
     import torch.nn.functional as F
@@ -348,7 +349,7 @@ def test_gemm_residual_epilogue(dev, M, N, K):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 19, 21, 32), (1, 16, 16, 128), (1, 7, 40, 8), (2, 40, 37, 64)])
 def test_dwconv7_residual_store(dev, B, H, W, C):
     """y = dwconv7(x) + s * res with the addition in the kernel's store"""
     import torch.nn.functional as F
