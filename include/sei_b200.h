@@ -251,6 +251,17 @@ int sei_ln_cl_backward_bf16(const void* gy, const void* x, const float* mean, co
  * reference's pointwise convolutions (autograd of nn.Conv2d bias).  workspace: sei_ln_cl_backward_workspace_bytes(C). */
 int sei_colsum_bf16(const void* x, float* out, void* workspace, long long T, int C, void* stream);
 
+/* 3x3 'same' convolution as an IMPLICIT GEMM on the tcgen05 tensor cores: UNet.in_conv / UNet.out_conv of the reference
+ * (src/models/convolutional.py:175-176) and their input gradients.  x: bf16 [B, H, W, Cin] channels-last with Cin = 8
+ * (3 image channels zero-padded) or 32; the nine shifted windows of a 16 x 8 pixel tile are bulk tensor copies whose
+ * out-of-image coordinates are zero-filled (the 'same' padding) and are read in place as the K-chunks of the A operand.
+ * wg: the weights in chunk form, bf16 [NCHP][N][8] with N = 32 (Cin = 8: NCHP = 10) or N = 16 (Cin = 32: NCHP = 36),
+ * element [tap * (Cin / 8) + block][n][j] = w[n][8 * block + j][ky][kx], tap = 3 ky + kx, zero where padded.
+ * out: bf16 [B, H, W, out_stride], out_stride = 32 (Cin = 8) or 4 (Cin = 32; channels >= out_valid are written as zero).
+ * bias: fp32 [out_valid] or NULL. */
+int sei_conv3x3_igemm_bf16(const void* x, const void* wg, const float* bias, void* out, int B, int H, int W, int Cin,
+                           int out_stride, int out_valid, void* stream);
+
 /* 3x3 convolution, stride 1, zero "same" padding, with 1..4 output channels, on a channels-last bf16 input
  * [B, H, W, Cin] (Cin a multiple of 8, <= 64): the reference's UNet.out_conv (src/models/convolutional.py:176,
  * Conv2d(hidden, in_channels, kernel_size=3, padding="same")).  w: [Cout, Cin, 3, 3] fp32, bias: [Cout] fp32 or NULL.

@@ -40,6 +40,8 @@ _NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"    
 # 9 ms GELU-backward pass but the four epilogue warps then spend longer on the erf arithmetic than the tensor cores
 # on the tile (CTA-pair GEMMs 76 -> 93 ms, N = 128 GEMMs 6 -> 13 ms per step): off by default.
 _GELU_FUSION = __import__("os").environ.get("SEI_GELU_FUSION", "0") == "1"
+# 3x3 in / out convolutions as implicit GEMMs on tcgen05 (SEI_IGEMM_CONV=0: unfold + GEMM / direct kernels of round 1)
+_IGEMM_CONV = __import__("os").environ.get("SEI_IGEMM_CONV", "1") == "1"
 # ConvBlock as one autograd node with its additions fused into the neighbouring kernels (SEI_CONVBLOCK_NODE=0: the
 # op-by-op path, for A/B measurements)
 _CONVBLOCK_NODE = __import__("os").environ.get("SEI_CONVBLOCK_NODE", "1") == "1"
@@ -306,6 +308,50 @@ class _ConvBlockFn(torch.autograd.Function):
                 dgam.to(dt[2]), dbet.to(dt[3]), gw2, gb2 if ctx.has_bias[0] else None, gw3, gb3)
 
 
+
+class _Conv3x3Igemm(torch.autograd.Function):
+    """3x3 'same' convolution of the network's edge layers as an implicit GEMM on tcgen05 (csrc/conv_igemm.cu):
+    x [B, H, W, 8] (3 image channels zero-padded) -> [B, H, W, 32]   (in_conv; weight [32, <= 4, 3, 3]), or
+    x [B, H, W, 32] -> [B, H, W, 4]                                  (out_conv; weight [<= 4, 32, 3, 3]).
+    The input gradient is the other instantiation with the taps flipped and the channel roles exchanged; the weight
+    gradient (864 numbers summed over all pixels) is the direct kernel of csrc/cnn_elem.cu, for in_conv with the roles of
+    the image and the gradient exchanged."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        N = weight.shape[0]
+        ctx.in_type = x.shape[-1] == 8
+        if ctx.in_type:
+            out = ops.conv3x3_igemm(x, ops.igemm_weight_chunks(weight, 8, 32), bias, 32, N)
+        else:
+            out = ops.conv3x3_igemm(x, ops.igemm_weight_chunks(weight, 32, 16), bias, 4, N)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        N, Cr = weight.shape[0], weight.shape[1]
+        wt = weight.detach().transpose(0, 1).flip(2, 3)                       # [C, N, 3, 3]: the transposed convolution
+        gx = gw = gb = None
+        if ctx.in_type:
+            if ctx.needs_input_grad[0]:
+                gx4 = ops.conv3x3_igemm(g, ops.igemm_weight_chunks(wt, 32, 16), None, 4, Cr)
+                gx = F.pad(gx4, (0, 4))
+            gwt, _ = ops.conv3x3_small_wgrad(x[..., :4].contiguous(), g, Cr)        # roles exchanged: [Cr, 32, 3, 3]
+            gw = gwt.permute(1, 0, 2, 3).flip(2, 3).contiguous()
+            if ctx.has_bias:
+                gb = _colsum(g.view(-1, g.shape[-1]))[:N]
+        else:
+            if ctx.needs_input_grad[0]:
+                gx = ops.conv3x3_igemm(F.pad(g, (0, 4)), ops.igemm_weight_chunks(wt, 8, 32), None, 32, 32)
+            gw, gb = ops.conv3x3_small_wgrad(g, x, N)
+        return gx, gw.to(weight.dtype), (gb.to(ctx.bias_dtype) if ctx.has_bias else None)
+
+
 class _GemmConv2d(Conv2d):
     """nn.Conv2d whose forward/backward contractions run on the tcgen05 GEMM.  Supports what the reference's
     network uses: 1x1 stride 1, and 3x3 stride 1 with 'same' zero padding; groups = 1."""
@@ -376,6 +422,16 @@ class _GemmConv2d(Conv2d):
                                     rl.reshape(B * H * W, self.out_channels))
                 return out.view(B, H, W, -1).permute(0, 3, 1, 2)
             return self.forward(x, use_bias=use_bias) + residual
+        if (self.kernel_size == (3, 3) and _IGEMM_CONV and xl.is_cuda and xl.dtype == torch.bfloat16 == COMPUTE_DTYPE
+                and self.padding in ("same", (1, 1))):
+            # the network's edge layers as implicit GEMMs on tcgen05 (csrc/conv_igemm.cu): no unfolded copy
+            bias = self.bias if use_bias else None
+            if self.out_channels == 32 and self.in_channels <= 4:
+                out = _Conv3x3Igemm.apply(_pad_channels(xl, 8).contiguous(), self.weight, bias)
+                return out.permute(0, 3, 1, 2)
+            if self.in_channels == 32 and self.out_channels <= 4:
+                out = _Conv3x3Igemm.apply(xl.contiguous(), self.weight, bias)
+                return out[..., : self.out_channels].permute(0, 3, 1, 2)
         if self.kernel_size == (3, 3):
             # the network's output layer (hidden -> 3 channels): direct kernel, no unfolded copy (csrc/cnn_elem.cu)
             out = _op_conv3x3_small(xl, self)

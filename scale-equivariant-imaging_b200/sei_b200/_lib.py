@@ -47,6 +47,7 @@ SIGNATURES = {
     "sei_ln_cl_backward_workspace_bytes": (C.c_longlong, [_i]),
     "sei_ln_cl_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "sei_colsum_bf16": (C.c_int, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "sei_conv3x3_igemm_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sei_conv3x3_small_workspace_bytes": (C.c_longlong, [_i, _i]),
     "sei_conv3x3_small_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sei_conv3x3_small_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

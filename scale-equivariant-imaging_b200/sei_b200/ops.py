@@ -548,6 +548,51 @@ def colsum_bf16(x_rows):
     return out
 
 
+def igemm_weight_chunks(w, cinp, nout):
+    """w [N, C, 3, 3] -> the chunk form sei_conv3x3_igemm_bf16 reads: bf16 [NCHP][nout][8], chunk = tap * (cinp / 8) + block,
+    element [chunk][n][j] = w[n][8 * block + j][ky][kx] (zero where N < nout, C < cinp or the chunk count is padded to even)"""
+    N, Cc = int(w.shape[0]), int(w.shape[1])
+    cch = cinp // 8
+    nchp = (9 * cch + 1) & ~1
+    wp = torch.zeros((nout, cinp, 3, 3), dtype=torch.float32, device=w.device)
+    wp[:N, :Cc] = w.detach().float()
+    t = wp.permute(2, 3, 1, 0).reshape(9, cch, 8, nout).permute(0, 1, 3, 2).reshape(9 * cch, nout, 8)
+    out = torch.zeros((nchp, nout, 8), dtype=torch.bfloat16, device=w.device)
+    out[: 9 * cch] = t.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def conv3x3_igemm(x_bhwc, wg, bias, out_stride, out_valid):
+    """3x3 'same' convolution of a channels-last bf16 tensor (8 or 32 channels) as an implicit GEMM on tcgen05
+    (sei_conv3x3_igemm_bf16); wg from igemm_weight_chunks; returns bf16 [B, H, W, out_stride]"""
+    if not x_bhwc.is_cuda or x_bhwc.dtype != torch.bfloat16 or x_bhwc.dim() != 4 or not x_bhwc.is_contiguous():
+        raise SeiError("conv3x3_igemm: x must be a contiguous CUDA bf16 [B, H, W, C] tensor")
+    B, H, W, Cin = x_bhwc.shape
+    if bias is not None:
+        bias = _t(bias, "bias")
+    out = torch.empty((B, H, W, out_stride), dtype=torch.bfloat16, device=x_bhwc.device)
+    nout = 32 if Cin == 8 else 16
+    _FLOPS[0] += 2.0 * B * H * W * nout * 9 * Cin
+    with torch.cuda.device(x_bhwc.device):
+        check(_lib.load().sei_conv3x3_igemm_bf16(_ptr(x_bhwc), _ptr(wg), _ptr(bias), _ptr(out), B, H, W, Cin, out_stride,
+                                                 out_valid, _stream(x_bhwc)))
+    return out
+
+
+def conv3x3_small_wgrad(gy4, x, cout):
+    """(gw [cout, Cin, 3, 3], gb [cout]) fp32 of a 3x3 'same' convolution with <= 4 output channels: gy4 bf16 [B, H, W, 4],
+    x bf16 [B, H, W, Cin] (sei_conv3x3_small_backward_bf16 without the input gradient)"""
+    B, H, W, Cin = x.shape
+    lib = _lib.load()
+    gw = torch.empty((cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    gb = torch.empty(cout, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.sei_conv3x3_small_workspace_bytes(Cin, cout)), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sei_conv3x3_small_backward_bf16(_ptr(gy4), _ptr(x), _ptr(gw), None, _ptr(gw), _ptr(gb), _ptr(ws),
+                                                  B, H, W, Cin, cout, _stream(x)))
+    return gw, gb
+
+
 def conv3x3_small_supported(x_bhwc, out_channels):
     return (x_bhwc.is_cuda and x_bhwc.dtype == torch.bfloat16 and x_bhwc.dim() == 4 and x_bhwc.is_contiguous()
             and x_bhwc.shape[3] in (8, 16, 32, 64) and 1 <= out_channels <= 4)

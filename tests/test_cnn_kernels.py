@@ -431,3 +431,31 @@ def test_gemm_gelu_dual_and_multiplier_epilogues(dev, M, N, K):
     d = ops.gemm_bf16_tn_mul(a, b, mult)
     ref = (a.float() @ b.float().t()) * mult.float()
     assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 24, 40), (3, 19, 21), (2, 64, 48)])
+@pytest.mark.parametrize("kind", ["in", "out"])
+def test_conv3x3_implicit_gemm_matches_torch(dev, B, H, W, kind):
+    """the 3x3 'same' edge convolutions as implicit GEMMs on tcgen05 (nine TMA windows with zero fill as K-chunks) vs
+    F.conv2d in fp32 on the same bf16 operands: forward, input gradient, weight and bias gradients"""
+    import torch.nn.functional as F
+    import models.convolutional as mc
+    torch.manual_seed(B * 100 + H + W)
+    cin, cout = (3, 32) if kind == "in" else (32, 3)
+    conv = mc._conv(cin, cout, 3, padding="same").to(dev)
+    x = torch.randn(B, cin, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(B, cout, H, W, device=dev).bfloat16()
+    xa = x.clone().requires_grad_(True)
+    y = conv(xa)
+    y.backward(gy)
+    wq = conv.weight.detach().bfloat16().float().requires_grad_(True)           # the tensor cores read bf16 weights
+    bq = conv.bias.detach().clone().requires_grad_(True)
+    xr = x.float().requires_grad_(True)
+    yr = F.conv2d(xr, wq, bq, padding=1)
+    yr.backward(gy.float())
+    assert y.shape == yr.shape
+    assert rel_err(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) < 6e-3
+    assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.cpu().numpy()) < 8e-3
+    assert rel_err(conv.weight.grad.cpu().numpy(), wq.grad.cpu().numpy()) < 3e-3
+    assert rel_err(conv.bias.grad.cpu().numpy(), bq.grad.cpu().numpy()) < 3e-3
