@@ -105,6 +105,11 @@ int sei_scale_transform_f32(const float* x, float* out, int B, int C, int S,
  * antialias), out is B x C x S x S, the grid is the one of an S x S image. */
 int sei_scale_transform_src_f32(const float* x, float* out, int B, int C, int Ssrc, int S,
                                 const float* rate, const float* center, void* stream);
+
+/* gx [B, C, Ssrc, Ssrc] = the transpose of sei_scale_transform_src_f32 applied to gout [B, C, S, S] (autograd through
+ * grid_sample in the anti-aliased padded transform, reference src/transforms.py:60-83). */
+int sei_scale_transform_src_backward_f32(const float* gout, float* gx, int B, int C, int Ssrc, int S, const float* rate,
+                                         const float* center, void* stream);
 /* transpose of the above w.r.t. x (autograd through grid_sample; only reached with
  * --no-ProposedLoss__stop_gradient).  gx is overwritten. */
 int sei_scale_transform_backward_f32(const float* gout, float* gx, int B, int C, int S,
@@ -330,12 +335,23 @@ int sei_ln_small_backward_bf16(const void* gy, const void* x, const float* mean,
  * normal_downsampling_transform (src/transforms.py:112-124); antialias selects ATen's _upsample_bicubic2d_aa weights. */
 int sei_resize_bicubic_f32(const float* x, float* y, long long planes, int H, int W, int Ho, int Wo,
                            float scale_h, float scale_w, int antialias, void* stream);
+
+/* gx[planes, H, W] = the transpose of sei_resize_bicubic_f32 applied to gy[planes, Ho, Wo]: autograd through
+ * F.interpolate in normal_downsampling_transform / alias_free_interpolate (reference src/transforms.py:44-57,112-124)
+ * when the EI branch keeps its gradient (src/losses/__init__.py:84-96, --no-ProposedLoss__stop_gradient). */
+int sei_resize_bicubic_backward_f32(const float* gy, float* gx, long long planes, int H, int W, int Ho, int Wo,
+                                    float scale_h, float scale_w, int antialias, void* stream);
 /* deepinv.transform.Rotate (third-party, v0.2.0; used at src/losses/__init__.py:86-91): torchvision
  * transforms.functional.rotate(x, angle) with its defaults = grid_sample(mode="nearest", padding_mode="zeros",
  * align_corners=False) on torchvision's affine grid.  rescaled_theta: HOST pointer to the 3 x 2 fp32 matrix
  * theta^T / [W/2, H/2] torchvision builds (row-major). */
 int sei_rotate_nearest_f32(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
                            void* stream);
+
+/* gx = the transpose of sei_rotate_nearest_f32 applied to gy (autograd through deepinv's Rotate -> torchvision rotate ->
+ * grid_sample(nearest) when the EI branch keeps its gradient). */
+int sei_rotate_nearest_backward_f32(const float* gy, float* gx, long long planes, int H, int W, const float* rescaled_theta,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

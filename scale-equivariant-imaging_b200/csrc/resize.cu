@@ -87,6 +87,49 @@ __global__ void __launch_bounds__(256) resize_bicubic_kernel(const __grid_consta
     }
 }
 
+
+// Transposes (autograd through the transforms when the EI branch keeps its gradient, --no-ProposedLoss__stop_gradient:
+// reference src/losses/__init__.py:84-96 with no_grad=False): every output gradient is scattered to the taps its
+// forward value was read from, with the forward kernel's weights, by fp32 atomics into a zeroed buffer.  Not on the
+// default path, so direct kernels.
+__global__ void __launch_bounds__(256) resize_bicubic_backward_kernel(const __grid_constant__ ResizeParams p)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % p.Wo);
+        const long long t = idx / p.Wo;
+        const int i = (int)(t % p.Ho);
+        float* gx = p.y + (t / p.Ho) * (long long)p.H * p.W;          // (p.x: output gradient, p.y: input gradient)
+        const float g = __ldg(p.x + idx);
+        if (!p.aa) {
+            const float ry = p.sh * ((float)i + 0.5f) - 0.5f, rx = p.sw * ((float)j + 0.5f) - 0.5f;
+            const float fy = floorf(ry), fx = floorf(rx);
+            float cy[4], cx[4];
+            keys_coeffs(ry - fy, cy);
+            keys_coeffs(rx - fx, cx);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int r = min(max((int)fy - 1 + a, 0), p.H - 1);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int c = min(max((int)fx - 1 + b, 0), p.W - 1);
+                    atomicAdd(gx + (size_t)r * p.W + c, g * cy[a] * cx[b]);
+                }
+            }
+        } else {
+            float wy[kAaMaxTaps], wx[kAaMaxTaps];
+            int ymin, ysize, xmin, xsize;
+            aa_axis_weights_f(i, p.H, p.sh, wy, ymin, ysize);
+            aa_axis_weights_f(j, p.W, p.sw, wx, xmin, xsize);
+            for (int a = 0; a < ysize; ++a) {
+                float* row = gx + (size_t)(ymin + a) * p.W + xmin;
+                const float ga = g * wy[a];
+                for (int b = 0; b < xsize; ++b) atomicAdd(row + b, ga * wx[b]);
+            }
+        }
+    }
+}
+
 // Rotation by nearest-neighbour resampling: deepinv.transform.Rotate -> torchvision.transforms.functional.rotate(x, angle)
 // with its defaults (NEAREST, expand=False, zero fill), i.e. F.grid_sample(x, grid, mode="nearest", padding_mode="zeros",
 // align_corners=False) on the grid of torchvision's _gen_affine_grid.  The fp32 operation order of that grid (linspace
@@ -107,6 +150,7 @@ __device__ __forceinline__ float linspace_at(int i, int steps, float start, floa
     return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(steps - 1 - i)));
 }
 
+template <bool BACKWARD>
 __global__ void __launch_bounds__(256) rotate_nearest_kernel(const __grid_constant__ RotateParams p)
 {
     const int H = p.H, W = p.W;
@@ -122,10 +166,13 @@ __global__ void __launch_bounds__(256) rotate_nearest_kernel(const __grid_consta
         // grid_sample, align_corners=False: ((g + 1) * size - 1) / 2, then nearbyint
         const float fx = rintf(__fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 2.0f));
         const float fy = rintf(__fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 2.0f));
-        float v = 0.0f;
-        if (fx >= 0.0f && fx <= (float)(W - 1) && fy >= 0.0f && fy <= (float)(H - 1))
-            v = __ldg(p.x + plane * (long long)H * W + (long long)(int)fy * W + (int)fx);
-        p.y[idx] = v;
+        const bool inside = fx >= 0.0f && fx <= (float)(W - 1) && fy >= 0.0f && fy <= (float)(H - 1);
+        const long long src = plane * (long long)H * W + (long long)(int)fy * W + (int)fx;
+        if (BACKWARD) {                    // p.x: output gradient, p.y: zeroed input gradient (several outputs may pick one pixel)
+            if (inside) atomicAdd(p.y + src, __ldg(p.x + idx));
+        } else {
+            p.y[idx] = inside ? __ldg(p.x + src) : 0.0f;
+        }
     }
 }
 
@@ -154,8 +201,47 @@ extern "C" int sei_resize_bicubic_f32(const float* x, float* y, long long planes
     return finish_launch("resize_bicubic_kernel");
 }
 
+// gx[planes, H, W] = transpose of sei_resize_bicubic_f32 applied to gy[planes, Ho, Wo] (same scales / antialias flag)
+extern "C" int sei_resize_bicubic_backward_f32(const float* gy, float* gx, long long planes, int H, int W, int Ho, int Wo,
+                                               float scale_h, float scale_w, int antialias, void* stream)
+{
+    SEI_REQUIRE(gy && gx, "null pointer argument");
+    SEI_REQUIRE(planes >= 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "bad shape planes=%lld %dx%d -> %dx%d", planes, H, W, Ho, Wo);
+    SEI_REQUIRE(scale_h > 0.f && scale_w > 0.f, "scales must be positive");
+    SEI_REQUIRE(!antialias || (4.0f * std::max(scale_h, scale_w) + 2.0f <= (float)kAaMaxTaps),
+                "antialiased resize supports scale factors down to 0.29 (%d taps per axis)", kAaMaxTaps);
+    if (planes == 0) return 0;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SEI_CUDA(cudaMemsetAsync(gx, 0, (size_t)planes * H * W * sizeof(float), st));
+    ResizeParams p;
+    p.x = gy; p.y = gx; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.aa = antialias ? 1 : 0; p.sh = scale_h; p.sw = scale_w;
+    p.total = planes * (long long)Ho * Wo;
+    const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
+    resize_bicubic_backward_kernel<<<grid, 256, 0, st>>>(p);
+    return finish_launch("resize_bicubic_backward_kernel");
+}
+
+static int rotate_nearest_impl(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
+                               bool backward, void* stream);
+
 extern "C" int sei_rotate_nearest_f32(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
                                       void* stream)
+{
+    return rotate_nearest_impl(x, y, planes, H, W, rescaled_theta, false, stream);
+}
+
+// gx = transpose of sei_rotate_nearest_f32 applied to gy (every output gradient goes to the source pixel it was read from)
+extern "C" int sei_rotate_nearest_backward_f32(const float* gy, float* gx, long long planes, int H, int W,
+                                               const float* rescaled_theta, void* stream)
+{
+    return rotate_nearest_impl(gy, gx, planes, H, W, rescaled_theta, true, stream);
+}
+
+static int rotate_nearest_impl(const float* x, float* y, long long planes, int H, int W, const float* rescaled_theta,
+                               bool backward, void* stream)
 {
     SEI_REQUIRE(x && y && rescaled_theta, "null pointer argument");
     SEI_REQUIRE(planes >= 0 && H > 0 && W > 0, "bad shape planes=%lld %dx%d", planes, H, W);
@@ -175,6 +261,12 @@ extern "C" int sei_rotate_nearest_f32(const float* x, float* y, long long planes
     p.y_step = H > 1 ? (p.y_end - p.y_start) / (float)(H - 1) : 0.0f;
     p.total = planes * (long long)H * W;
     const unsigned grid = (unsigned)std::min<long long>((p.total + 255) / 256, (long long)dp.sm_count * 32);
-    rotate_nearest_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (backward) {
+        SEI_CUDA(cudaMemsetAsync(y, 0, (size_t)p.total * sizeof(float), st));
+        rotate_nearest_kernel<true><<<grid, 256, 0, st>>>(p);
+    } else {
+        rotate_nearest_kernel<false><<<grid, 256, 0, st>>>(p);
+    }
     return finish_launch("rotate_nearest_kernel");
 }

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const __grid_constant
 // fp32 atomics into a zeroed buffer.  Not on the default path (stop_gradient=True), so a direct kernel.
 __global__ void __launch_bounds__(256) scale_backward_kernel(const __grid_constant__ ScaleDirectParams p)
 {
-    const int S = p.S;
+    const int S = p.S, Ss = p.Ssrc;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(idx % S);
@@ -364,15 +364,15 @@ __global__ void __launch_bounds__(256) scale_backward_kernel(const __grid_consta
         const int b = (int)(plane / p.C);
         const float inv_rate = __fdiv_rn(1.0f, __ldg(p.rate + b));
         AxisTap ty, tx;
-        scale_axis_tap(i, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b + 1), ty);
-        scale_axis_tap(j, S, p.two_over_S, inv_rate, __ldg(p.center + 2 * b), tx);
-        float* gx = p.out + plane * (long long)S * S;
+        scale_axis_tap(i, Ss, p.two_over_S, inv_rate, __ldg(p.center + 2 * b + 1), ty);
+        scale_axis_tap(j, Ss, p.two_over_S, inv_rate, __ldg(p.center + 2 * b), tx);
+        float* gx = p.out + plane * (long long)Ss * Ss;
         const float g = __ldg(p.x + idx);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const float ga = g * ty.w[a];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) atomicAdd(gx + (size_t)ty.idx[a] * S + tx.idx[c], ga * tx.w[c]);
+            for (int c = 0; c < 4; ++c) atomicAdd(gx + (size_t)ty.idx[a] * Ss + tx.idx[c], ga * tx.w[c]);
         }
     }
 }
@@ -539,6 +539,27 @@ extern "C" int sei_scale_transform_backward_f32(const float* gout, float* gx, in
     d.two_over_S = (float)(2.0 / (double)S);
     d.total = (long long)B * C * S * S;
     SEI_CUDA(cudaMemsetAsync(gx, 0, (size_t)d.total * sizeof(float), st));
+    const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
+    scale_backward_kernel<<<grid, 256, 0, st>>>(d);
+    return finish_launch("scale_backward_kernel");
+}
+
+// transpose of sei_scale_transform_src_f32: gout [B, C, S, S] -> gx [B, C, Ssrc, Ssrc]
+extern "C" int sei_scale_transform_src_backward_f32(const float* gout, float* gx, int B, int C, int Ssrc, int S,
+                                                    const float* rate, const float* center, void* stream)
+{
+    SEI_REQUIRE(gout && gx && rate && center, "null pointer argument");
+    SEI_REQUIRE(B >= 0 && C > 0 && S > 0 && Ssrc > 0, "bad shape B=%d C=%d Ssrc=%d S=%d", B, C, Ssrc, S);
+    if (B == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    ScaleDirectParams d;
+    d.x = gout; d.out = gx; d.rate = rate; d.center = center; d.C = C; d.S = S; d.Ssrc = Ssrc;
+    d.two_over_S = (float)(2.0 / (double)S);
+    d.total = (long long)B * C * S * S;
+    SEI_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * C * Ssrc * Ssrc * sizeof(float), st));
     const unsigned grid = (unsigned)std::min<long long>((d.total + 255) / 256, (long long)dp.sm_count * 32);
     scale_backward_kernel<<<grid, 256, 0, st>>>(d);
     return finish_launch("scale_backward_kernel");

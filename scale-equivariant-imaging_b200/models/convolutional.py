@@ -475,6 +475,8 @@ class LayerNorm(Module):
 
 
 class ConvBlock(Module):
+    _sei_atomic_group = True       # one autograd node: its gradients become final together (sei_b200.parallel.completion_groups)
+
     def __init__(self, dim):
         super().__init__()
         self.conv1 = Conv2d(in_channels=dim, out_channels=dim, kernel_size=7, padding=3, groups=dim)

@@ -24,6 +24,7 @@ SIGNATURES = {
     "sei_crop_batch_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_transform_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sei_scale_transform_src_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sei_scale_transform_src_backward_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_transform_backward_f32": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sei_scale_params_f32": (C.c_int, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "sei_ei_workspace_bytes": (C.c_longlong, [_i, _i]),
@@ -65,7 +66,9 @@ SIGNATURES = {
     "sei_ln_small_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "sei_ln_small_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "sei_resize_bicubic_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "sei_resize_bicubic_backward_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "sei_rotate_nearest_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "sei_rotate_nearest_backward_f32": (C.c_int, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "sei_bgemm_tile_rows": (C.c_int, [_i, _i]),
     "sei_bgemm_bf16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _ll, _ll, _i, _ll, _ll, _ll, _ll, _i, _ll, _ll,
                                  _vp]),

@@ -204,8 +204,5 @@ class Rotate(nn.Module):
         self.n_trans, self.group_size = n_trans, degrees
 
     def forward(self, x):
-        if x.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("Rotate has no backward here: the reference uses it under the EI loss's "
-                                      "stop-gradient (ProposedLoss__stop_gradient=True, the default)")
         theta = torch.arange(0, 360)[1:][draws.randperm(359)][: self.n_trans]
         return ops.rotate_nearest(x, float(theta[0]))

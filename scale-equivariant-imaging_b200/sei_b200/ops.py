@@ -129,8 +129,14 @@ def up_bicubic(y, rate):
 
 
 def resize_bicubic(x, scale_factor, antialias):
-    """F.interpolate(x, scale_factor=scale_factor, mode='bicubic', antialias=antialias) (sei_resize_bicubic_f32);
-    no autograd: the reference only uses it under the EI loss's stop-gradient"""
+    """F.interpolate(x, scale_factor=scale_factor, mode='bicubic', antialias=antialias) (sei_resize_bicubic_f32), with the
+    hand-written transpose as its backward (sei_resize_bicubic_backward_f32)"""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _ResizeBicubic.apply(x, float(scale_factor), bool(antialias))
+    return _resize_bicubic_raw(x, scale_factor, antialias)
+
+
+def _resize_bicubic_raw(x, scale_factor, antialias):
     import math
     x = _t(x, "x")
     B, Cc, H, W = x.shape
@@ -156,14 +162,51 @@ def rotate_rescaled_theta(angle, H, W):
 
 def rotate_nearest(x, angle):
     """torchvision.transforms.functional.rotate(x, angle) with its defaults (nearest, same size, zero fill), the call
-    deepinv's Rotate makes (sei_rotate_nearest_f32); no autograd"""
+    deepinv's Rotate makes (sei_rotate_nearest_f32); backward: every output gradient returns to the pixel it was read
+    from (sei_rotate_nearest_backward_f32)"""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _RotateNearest.apply(x, float(angle))
+    return _rotate_nearest_raw(x, angle, False)
+
+
+def _rotate_nearest_raw(x, angle, backward):
     x = _t(x, "x")
     B, Cc, H, W = x.shape
     y = torch.empty_like(x)
     r = rotate_rescaled_theta(angle, H, W)
+    fn = _lib.load().sei_rotate_nearest_backward_f32 if backward else _lib.load().sei_rotate_nearest_f32
     with torch.cuda.device(x.device):
-        check(_lib.load().sei_rotate_nearest_f32(_ptr(x), _ptr(y), B * Cc, H, W, C.c_void_p(r.ctypes.data), _stream(x)))
+        check(fn(_ptr(x), _ptr(y), B * Cc, H, W, C.c_void_p(r.ctypes.data), _stream(x)))
     return y
+
+
+class _RotateNearest(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, angle):
+        ctx.angle = angle
+        return _rotate_nearest_raw(x, angle, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _rotate_nearest_raw(g.contiguous(), ctx.angle, True), None
+
+
+class _ResizeBicubic(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale_factor, antialias):
+        ctx.args = (tuple(x.shape), scale_factor, antialias)
+        return _resize_bicubic_raw(x, scale_factor, antialias)
+
+    @staticmethod
+    def backward(ctx, g):
+        (B, Cc, H, W), scale_factor, antialias = ctx.args
+        g = _t(g, "g")
+        gx = torch.empty((B, Cc, H, W), dtype=g.dtype, device=g.device)
+        s = 1.0 / float(scale_factor)
+        with torch.cuda.device(g.device):
+            check(_lib.load().sei_resize_bicubic_backward_f32(_ptr(g), _ptr(gx), B * Cc, H, W, g.shape[2], g.shape[3], s, s,
+                                                              int(antialias), _stream(g)))
+        return gx, None, None
 
 
 def crop_batch(x, tops, lefts, height, width):
@@ -212,7 +255,34 @@ def scale_transform(x, rate, center, path=PATH_AUTO):
 
 def scale_transform_from(x_src, out_size, rate, center):
     """grid_sample step of the scale transform reading a source of another (square) size: x_src [B, C, Ssrc, Ssrc]
-    -> [B, C, out_size, out_size] (sei_scale_transform_src_f32; the anti-aliased variant, no autograd)"""
+    -> [B, C, out_size, out_size] (sei_scale_transform_src_f32; the anti-aliased variant); backward by
+    sei_scale_transform_src_backward_f32"""
+    if x_src.requires_grad and torch.is_grad_enabled():
+        return _ScaleTransformFrom.apply(x_src, int(out_size), rate, center)
+    return _scale_transform_from_raw(x_src, out_size, rate, center)
+
+
+class _ScaleTransformFrom(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_src, out_size, rate, center):
+        ctx.save_for_backward(rate, center)
+        ctx.src_shape = tuple(x_src.shape)
+        return _scale_transform_from_raw(x_src, out_size, rate, center)
+
+    @staticmethod
+    def backward(ctx, g):
+        rate, center = ctx.saved_tensors
+        B, Cc, Ss, _ = ctx.src_shape
+        g = _t(g, "g")
+        rate_c, center_c = _t(rate, "downsampling_rate").reshape(-1), _t(center, "center").reshape(-1)
+        gx = torch.empty(ctx.src_shape, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            check(_lib.load().sei_scale_transform_src_backward_f32(_ptr(g), _ptr(gx), B, Cc, Ss, g.shape[-1], _ptr(rate_c),
+                                                                   _ptr(center_c), _stream(g)))
+        return gx, None, None, None
+
+
+def _scale_transform_from_raw(x_src, out_size, rate, center):
     x_src = _t(x_src, "x")
     B, Cc, H, W = x_src.shape
     if H != W:

@@ -57,9 +57,11 @@ def make_buckets(params, max_elems=64 * 2 ** 20):
 
 def completion_groups(module, max_elems):
     """Partition a module tree into the sub-modules whose parameter gradients become final together: descend from the
-    root until a sub-module holds at most `max_elems` parameters (or has parameters of its own).  For the restoration
-    CNN at its default flags this yields the two 268 M-parameter pointwise convolutions of the deepest ConvBlock as
-    buckets of their own and one bucket per shallower block / resampling layer."""
+    root until a sub-module holds at most `max_elems` parameters, has parameters of its own, or declares itself atomic
+    (`_sei_atomic_group = True`: a module that runs as ONE autograd node, whose children are never called -- the
+    restoration CNN's ConvBlock).  For the CNN at its default flags this yields the deepest ConvBlock (537 M parameters,
+    83 % of the gradient bytes, final half-way through the last backward pass) as a bucket of its own and one bucket per
+    shallower block / resampling layer."""
     out = []
 
     def walk(m):
@@ -67,7 +69,7 @@ def completion_groups(module, max_elems):
         if n == 0:
             return
         own = any(True for _ in m.parameters(recurse=False))
-        if own or n <= max_elems or not any(True for _ in m.children()):
+        if own or n <= max_elems or getattr(m, "_sei_atomic_group", False) or not any(True for _ in m.children()):
             out.append(m)
             return
         for c in m.children():

@@ -57,9 +57,6 @@ def _antialiased_padded_transform(x, downsampling_rate, center):
     torch.stack) followed by grid_sample of the SMALLER image with the grid of the original shape (:63-82).  Like the
     reference it reads the rates on the host, and like the reference it only works when every image of the batch drew
     the same rate: torch.stack of differently sized images raises a RuntimeError there, and so does this."""
-    if x.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("the anti-aliased scale transform has no backward here: the reference uses it under "
-                                  "the EI loss's stop-gradient (ProposedLoss__stop_gradient=True, the default)")
     rates = [float(r) for r in downsampling_rate.reshape(-1).tolist()]
     if len(set(rates)) > 1:
         raise RuntimeError("stack expects each tensor to be equal size: the anti-aliasing pre-filter resizes every image by "
@@ -102,9 +99,6 @@ def normal_downsampling_transform(x, downsampling_rate, mode, antialiased):
     """Every image resized by the same factor (reference :112-124: a per-image F.interpolate loop); one kernel here."""
     if mode != "bicubic":
         raise NotImplementedError("only mode='bicubic' (the only one the reference passes, src/transforms.py:139) is built")
-    if x.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("normal_downsampling_transform has no backward here: the reference uses it under the EI "
-                                  "loss's stop-gradient (ProposedLoss__stop_gradient=True, the default)")
     return ops.resize_bicubic(x, float(downsampling_rate), antialiased)
 
 

@@ -593,9 +593,18 @@ def test_antialiased_padded_transform_vs_reference(golden, dev):
     with pytest.raises(RuntimeError, match="equal size"):          # the reference fails the same way (torch.stack)
         transforms.padded_downsampling_transform(x, torch.tensor([0.75, 0.5], device=dev), torch.zeros(2, 1, 1, 2, device=dev),
                                                  "bicubic", "reflection", True)
-    with pytest.raises(NotImplementedError):
-        transforms.padded_downsampling_transform(x.clone().requires_grad_(True), torch.full((2,), 0.5, device=dev),
-                                                 torch.zeros(2, 1, 1, 2, device=dev), "bicubic", "reflection", True)
+    # gradient through the anti-aliased transform (hand-written transposes of both steps) against torch's CPU autograd
+    # of the same composition: F.interpolate(antialias=True) then grid_sample on the reference's grid
+    import torch.nn.functional as F
+    rate, center = torch.full((2,), 0.5), torch.tensor([[0.2, -0.3], [-0.5, 0.4]]).view(2, 1, 1, 2)
+    xa = x.clone().requires_grad_(True)
+    gy = torch.rand(2, 3, 32, 32, device=dev)
+    transforms.padded_downsampling_transform(xa, rate.to(dev), center.to(dev), "bicubic", "reflection", True).backward(gy)
+    xr = x.cpu().clone().requires_grad_(True)
+    small = F.interpolate(xr, scale_factor=0.5, mode="bicubic", antialias=True)
+    grid = transforms.get_downsampling_grid((2, 3, 32, 32), rate, center, torch.float32, "cpu")
+    F.grid_sample(small, grid, mode="bicubic", padding_mode="reflection", align_corners=True).backward(gy.cpu())
+    assert rel_err(npy(xa.grad), xr.grad.numpy()) < 1e-5
     # module form: EI re-measurement goes through the unfused composition
     import physics
     phys = physics.get_physics(base_args(), device=dev)
@@ -630,8 +639,14 @@ def test_rotate_vs_torchvision(golden, dev):
     with draws.inject([g["module_draw0_randperm"]]):
         y = Rotate()(cu(g["module_x"], dev))
     assert int((npy(y) != g["module_y"]).sum()) <= 2
-    with pytest.raises(NotImplementedError):
-        Rotate()(cu(g["module_x"], dev).requires_grad_(True))
+    # backward: the transpose of the pixel selection (adjointness against the forward kernel: <R x, y> = <x, R^T y>)
+    xa = cu(g["module_x"], dev).requires_grad_(True)
+    with draws.inject([g["module_draw0_randperm"]]):
+        ya = Rotate()(xa)
+    w = torch.rand_like(ya)
+    ya.backward(w)
+    lhs, rhs = float((ya.detach().double() * w.double()).sum()), float((xa.detach().double() * xa.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-9 * abs(lhs)
 
 
 def test_normal_scaling_transform_module(dev):
@@ -644,5 +659,16 @@ def test_normal_scaling_transform_module(dev):
     assert y.shape == (2, 3, 32, 32) and last_kernel() == "resize_bicubic_kernel"
     with draws.inject([np.array(0.2, dtype=np.float32)]):          # rate 0.75
         assert t(x).shape == (2, 3, 48, 48)
-    with pytest.raises(NotImplementedError):
-        t(x.clone().requires_grad_(True))
+    # gradient through the resize (--no-ProposedLoss__stop_gradient) against torch's CPU autograd of F.interpolate
+    import torch.nn.functional as F
+    for aa, u in ((True, 0.7), (False, 0.2)):
+        tt = transforms.ScalingTransform(kind="normal", antialias=aa)
+        xa = x.clone().requires_grad_(True)
+        with draws.inject([np.array(u, dtype=np.float32)]):
+            ya = tt(xa)
+        gy = torch.rand_like(ya)
+        ya.backward(gy)
+        xr = x.cpu().clone().requires_grad_(True)
+        yr = F.interpolate(xr, scale_factor=0.5 if u > 0.5 else 0.75, mode="bicubic", antialias=aa)
+        yr.backward(gy.cpu())
+        assert rel_err(npy(ya), yr.detach().numpy()) < 1e-5 and rel_err(npy(xa.grad), xr.grad.numpy()) < 1e-5, aa
