@@ -693,11 +693,22 @@ static int conv3_wgrad_ctas(int sm_count) { return sm_count * 4; }
 
 }  // namespace sei
 
+namespace sei {      // csrc/dwconv_tile.cu: shared-memory tile kernel for the 32 -> 3 channel shape
+int conv3_wgrad_tile_slots(int sm_count);
+int conv3_wgrad_tile(const void* g4, const void* x, float* partial, int B, int H, int W, int sm_count, cudaStream_t st);
+}
+static bool conv3_use_tiles(int Cin, int Cout)
+{
+    const char* e = getenv("SEI_CONV3_WGRAD_TILE");      // A/B switch: 0 = the direct kernel of round 1
+    return Cin == 32 && Cout == 3 && !(e && *e == '0');
+}
+
 extern "C" long long sei_conv3x3_small_workspace_bytes(int Cin, int Cout)
 {
     DeviceProps dp;
     if (get_device_props(&dp)) return -1;
-    return (long long)conv3_wgrad_ctas(dp.sm_count) * ((long long)Cout * Cin * 9 + Cout) * (long long)sizeof(float);
+    const int slots = std::max(conv3_wgrad_ctas(dp.sm_count), conv3_wgrad_tile_slots(dp.sm_count));
+    return (long long)slots * ((long long)Cout * Cin * 9 + Cout) * (long long)sizeof(float);
 }
 
 static int conv3_check(int B, int H, int W, int Cin, int Cout)
@@ -782,6 +793,12 @@ extern "C" int sei_conv3x3_small_backward_bf16(const void* gy, const void* x, co
         if (rc) return rc;
     }
     p.partial = static_cast<float*>(workspace);
+    if (conv3_use_tiles(Cin, Cout)) {
+        rc = conv3_wgrad_tile(gy, x, p.partial, B, H, W, dp.sm_count, st);
+        if (rc) return rc;
+        colsum_final_kernel<<<(nW + Cout + 31) / 32, 256, 0, st>>>(p.partial, gw, gb, conv3_wgrad_tile_slots(dp.sm_count), nW + Cout, nW);
+        return finish_launch("colsum_final_kernel");
+    }
     const int GS = 9 * (Cin / 8), NG = std::max(1, 256 / GS), threads = NG * GS;
     const int ctas = conv3_wgrad_ctas(dp.sm_count);
     const size_t smem = (size_t)threads * (Cout * 8 + Cout) * sizeof(float);

@@ -263,6 +263,118 @@ __global__ void __launch_bounds__(kDtThreads, 2) dwconv7_wgrad_tile_kernel(const
     }
 }
 
+// ---------------------------------------------------------------- weight gradient of the 3x3 edge convolutions
+// dW[co][ci][ky][kx] = sum_p g[p][co] * x[p + (ky - 1, kx - 1)][ci],  db[co] = sum_p g[p][co]   (co < 3, ci < 32)
+// for UNet.out_conv (reference src/models/convolutional.py:176; g = dL/dy, 4 bf16 per pixel) and, with the roles of the
+// image and the gradient exchanged, UNet.in_conv (:175).  864 numbers, each a sum over every pixel: 1.8 GFMA per call.
+// Shared-memory tiles like the depthwise kernels above: x tile (32 rows + halo) x (16 + halo, pitch 19) x 32 channels by
+// one TMA copy with zero fill, the 8-byte gradient pixels by ordinary loads.  Warp (slice, ky), half-warp g, lane = channel
+// pair: it slides a 3-pixel register window along the rows 2 i + g of its slice: per pixel one new x word and one
+// broadcast gradient word feed 18 FMAs.  The round-1 kernel (a thread per (ci / 8, tap), every operand through L1) took
+// 680 us per call.
+constexpr int kCwTW = 16, kCwTH = 32, kCwIW = 19, kCwIH = kCwTH + 2, kCwWarps = 9, kCwThreads = 32 * kCwWarps;
+constexpr uint32_t kCwXBytes = kCwIH * kCwIW * 64;
+static_assert(kCwXBytes % 128 == 0, "gradient tile must stay aligned");
+
+struct CwParams {
+    const uint2* g4;              // [B, H, W] pixels of 4 bf16
+    float* partial;               // [3 * gridDim.x][nW + 3]
+    int B, H, W, tiles_x, tiles_y;
+    long long tiles;
+};
+
+__global__ void __launch_bounds__(kCwThreads, 2) conv3_wgrad_tile_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                          const __grid_constant__ CwParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    const uint32_t* sx = reinterpret_cast<const uint32_t*>(base);                 // [IH][IW][16 channel pairs]
+    uint2* sg = reinterpret_cast<uint2*>(base + kCwXBytes);                        // [TH][TW]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ky = warp % 3, slice = warp / 3, g = lane >> 4, cp = lane & 15;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    float acc[3][3][2], gb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int co = 0; co < 3; ++co) acc[kx][co][0] = acc[kx][co][1] = 0.f;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const int tx = (int)(t % p.tiles_x);
+        const long long r = t / p.tiles_x;
+        const int ty = (int)(r % p.tiles_y), b = (int)(r / p.tiles_y);
+        const int x0 = tx * kCwTW, y0 = ty * kCwTH;
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar, kCwXBytes);
+            tma_load_4d(base, &map_x, 0, x0 - 1, y0 - 1, b, &bar);
+        }
+        for (int i = threadIdx.x; i < kCwTH * kCwTW; i += kCwThreads) {
+            const int yy = y0 + i / kCwTW, xx = x0 + i % kCwTW;
+            sg[i] = (yy < p.H && xx < p.W) ? __ldg(p.g4 + ((size_t)b * p.H + yy) * p.W + xx) : make_uint2(0u, 0u);
+        }
+        __syncthreads();
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+#pragma unroll 1
+        for (int pi = slice; pi < kCwTH / 2; pi += 3) {
+            const int row = 2 * pi + g;
+            const uint32_t* xr = sx + (size_t)((row + ky) * kCwIW) * 16 + cp;
+            const uint2* gr = sg + row * kCwTW;
+            float2 w0 = bf2_to_f2(xr[0]), w1 = bf2_to_f2(xr[16]);
+#pragma unroll
+            for (int c = 0; c < kCwTW; ++c) {
+                const float2 w2 = bf2_to_f2(xr[(c + 2) * 16]);
+                const uint2 gq = gr[c];
+                const float2 g01 = bf2_to_f2(gq.x), g2_ = bf2_to_f2(gq.y);
+                const float gv[3] = {g01.x, g01.y, g2_.x};
+#pragma unroll
+                for (int co = 0; co < 3; ++co) {
+                    acc[0][co][0] = fmaf(gv[co], w0.x, acc[0][co][0]); acc[0][co][1] = fmaf(gv[co], w0.y, acc[0][co][1]);
+                    acc[1][co][0] = fmaf(gv[co], w1.x, acc[1][co][0]); acc[1][co][1] = fmaf(gv[co], w1.y, acc[1][co][1]);
+                    acc[2][co][0] = fmaf(gv[co], w2.x, acc[2][co][0]); acc[2][co][1] = fmaf(gv[co], w2.y, acc[2][co][1]);
+                }
+                if (ky == 0) {
+                    gb[0] += gv[0]; gb[1] += gv[1]; gb[2] += gv[2];
+                }
+                w0 = w1;
+                w1 = w2;
+            }
+        }
+        __syncthreads();
+    }
+    // the two half-warps hold the same channel pairs (rows of the other parity)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            acc[kx][co][0] += __shfl_down_sync(0xffffffffu, acc[kx][co][0], 16);
+            acc[kx][co][1] += __shfl_down_sync(0xffffffffu, acc[kx][co][1], 16);
+        }
+#pragma unroll
+    for (int co = 0; co < 3; ++co) gb[co] += __shfl_down_sync(0xffffffffu, gb[co], 16);
+    if (g != 0) return;
+    constexpr int nW = 3 * 32 * 9;
+    float* out = p.partial + ((size_t)blockIdx.x * 3 + slice) * (nW + 3);
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            out[(co * 32 + 2 * cp) * 9 + ky * 3 + kx] = acc[kx][co][0];
+            out[(co * 32 + 2 * cp + 1) * 9 + ky * 3 + kx] = acc[kx][co][1];
+        }
+    if (ky == 0 && cp == 0) {
+#pragma unroll
+        for (int co = 0; co < 3; ++co) out[nW + co] = gb[co];
+    }
+}
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -362,6 +474,24 @@ int dwconv7_tile_wgrad(const void* gy, const void* x, float* partial, int slots,
 {
     return dw_tile_g(C) == 1 ? dw_tile_wgrad<1>(gy, x, partial, slots, B, H, W, C, st)
                              : dw_tile_wgrad<2>(gy, x, partial, slots, B, H, W, C, st);
+}
+
+int conv3_wgrad_tile_slots(int sm_count) { return 3 * 2 * sm_count; }
+
+// partial: [conv3_wgrad_tile_slots()][867] floats; x: bf16 [B, H, W, 32], g4: [B, H, W, 4] bf16 (3 channels used)
+int conv3_wgrad_tile(const void* g4, const void* x, float* partial, int B, int H, int W, int sm_count, cudaStream_t st)
+{
+    CUtensorMap mx;
+    int rc = make_map_bhwc(&mx, x, B, H, W, 32, 32, kCwIW, kCwIH);
+    if (rc) return rc;
+    CwParams p;
+    p.g4 = static_cast<const uint2*>(g4); p.partial = partial; p.B = B; p.H = H; p.W = W;
+    p.tiles_x = (W + kCwTW - 1) / kCwTW; p.tiles_y = (H + kCwTH - 1) / kCwTH;
+    p.tiles = (long long)B * p.tiles_y * p.tiles_x;
+    constexpr size_t smem = kCwXBytes + kCwTH * kCwTW * 8 + 128;
+    SEI_CUDA(allow_smem(conv3_wgrad_tile_kernel, smem));
+    conv3_wgrad_tile_kernel<<<2 * sm_count, kCwThreads, smem, st>>>(mx, p);
+    return finish_launch("conv3_wgrad_tile_kernel");
 }
 
 }  // namespace sei
