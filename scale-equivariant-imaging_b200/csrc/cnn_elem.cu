@@ -84,6 +84,17 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constan
         for (int i = 0; i < NV; ++i) dst[i] = ok ? __ldcs(xr + gl + i * G) : make_uint4(0, 0, 0, 0);
     };
     constexpr bool PF = VPL > 0 && VPL <= 2;       // prefetching 8 vectors per lane would halve the occupancy
+    // a lane keeps the same columns for every row: their gamma / beta live in registers (the first version re-read them
+    // per row, 64 B of L1 traffic per 16 B of data: the kernels ran at 0.4 of the HBM rate)
+    constexpr int NP = PF ? NV : 1;
+    float gam[NP][8], bet[NP][8];
+    if (PF) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            load8f(p.gamma + 8 * (gl + i * G), gam[i]);
+            load8f(p.beta + 8 * (gl + i * G), bet[i]);
+        }
+    }
     if (PF && rb < p.T) fetch(rb, cache);
     for (; rb < p.T; rb += row_step) {
         const long long r = rb + sub;
@@ -141,7 +152,16 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constan
                 for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mu) * rs, ga[j], be[j]);
                 __stcs(yr + v, pack8(f));
             };
-            if (VPL > 0) {
+            if (PF) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    float f[8];
+                    unpack8(cache[i], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mu) * rs, gam[i][j], bet[i][j]);
+                    __stcs(yr + gl + i * G, pack8(f));
+                }
+            } else if (VPL > 0) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) emit(gl + i * G, cache[i]);
             } else {
@@ -183,6 +203,21 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
     };
     // (prefetching the next rows, as the forward kernel does, was measured slower here: 2.7 -> 3.0 ms for C = 32 / 128)
     constexpr bool PF = false;
+    // Register-cached shapes (VPL = 1, 2: C <= 512): gamma stays in registers, and the parameter gradients
+    // dgamma[c] = sum_t gy * xhat, dbeta[c] = sum_t gy of the lane's columns are accumulated here -- the separate
+    // colsum_kernel<0> pass re-read both operands (4.7 ms per step) -- then combined across the lanes / warps that share
+    // columns and written as one partial row per CTA (p.beta doubles as the partial buffer: [gridDim.x][2][C]).
+    constexpr bool FUSE = VPL > 0 && VPL <= 2;
+    constexpr int NP = FUSE ? NV : 1;
+    float gam[NP][8], dgam[NP][8], dbet[NP][8];
+    if (FUSE) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            load8f(p.gamma + 8 * (gl + i * G), gam[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dgam[i][j] = dbet[i][j] = 0.f;
+        }
+    }
     if (PF && VPL > 0 && rb < p.T) fetch(rb, cx, cg);
     for (; rb < p.T; rb += row_step) {
         const long long r = rb + sub;
@@ -197,6 +232,22 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
             fetch(rb, cx, cg);
         }
         float s1 = 0.f, s2 = 0.f;
+        if (FUSE) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                float fx[8], fg[8];
+                unpack8(cx[i], fx);
+                unpack8(cg[i], fg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (fx[j] - mu) * rs, gq = fg[j] * gam[i][j];
+                    s1 += gq;
+                    s2 = fmaf(gq, xh, s2);
+                    dgam[i][j] = fmaf(fg[j], xh, dgam[i][j]);        // (inactive rows were loaded as zeros)
+                    dbet[i][j] += fg[j];
+                }
+            }
+        }
         auto accumulate = [&](int v, const uint4& rx, const uint4& rg) {
             float fx[8], fg[8], ga[8];
             unpack8(rx, fx);
@@ -209,7 +260,8 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
                 s2 = fmaf(g, (fx[j] - mu) * rs, s2);
             }
         };
-        if (VPL > 0) {
+        if (FUSE) {
+        } else if (VPL > 0) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) accumulate(gl + i * G, cx[i], cg[i]);
         } else {
@@ -228,7 +280,17 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
                 for (int j = 0; j < 8; ++j) fx[j] = rs * (fg[j] * ga[j] - m1 - (fx[j] - mu) * rs * m2);
                 __stcs(dr + v, pack8(fx));
             };
-            if (VPL > 0) {
+            if (FUSE) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    float fx[8], fg[8];
+                    unpack8(cx[i], fx);
+                    unpack8(cg[i], fg);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) fx[j] = rs * (fg[j] * gam[i][j] - m1 - (fx[j] - mu) * rs * m2);
+                    __stcs(dr + gl + i * G, pack8(fx));
+                }
+            } else if (VPL > 0) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) emit(gl + i * G, cx[i], cg[i]);
             } else {
@@ -241,6 +303,36 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_c
                 cx[i] = ax[i];
                 cg[i] = ag[i];
             }
+        }
+    }
+    if (FUSE) {
+        __shared__ float red[kLnThreads / 32][1024];        // per warp: [vector][dgamma 8 | dbeta 8], nvec <= 64
+        // lanes of a warp that own the same columns (different rows): xor-shuffle over the row index bits
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                for (int o = G; o < 32; o <<= 1) {
+                    dgam[i][j] += __shfl_xor_sync(0xffffffffu, dgam[i][j], o);
+                    dbet[i][j] += __shfl_xor_sync(0xffffffffu, dbet[i][j], o);
+                }
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    red[warp][(gl + i * G) * 16 + j] = dgam[i][j];
+                    red[warp][(gl + i * G) * 16 + 8 + j] = dbet[i][j];
+                }
+        }
+        __syncthreads();
+        float* out = const_cast<float*>(p.beta) + (size_t)blockIdx.x * 2 * p.C;
+        for (int e = threadIdx.x; e < 2 * p.C; e += kLnThreads) {
+            const int which = e / p.C, c = e - which * p.C;         // 0: dgamma, 1: dbeta
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnThreads / 32; ++w) sum += red[w][(c >> 3) * 16 + which * 8 + (c & 7)];
+            out[e] = sum;
         }
     }
 }
@@ -417,7 +509,8 @@ extern "C" long long sei_ln_cl_backward_workspace_bytes(int C)
     if (get_device_props(&dp) || C < 8 || C % 8) return -1;
     const long long threads = colsum_threads(C, dp.sm_count);
     if (threads == 0) return -1;
-    return colsum_slots(C, threads) * 2 * C * (long long)sizeof(float);
+    // partial rows: one per column-sum slot, or one per CTA of the fused LayerNorm backward (at most 8 per SM)
+    return std::max<long long>(colsum_slots(C, threads), (long long)dp.sm_count * 8) * 2 * C * (long long)sizeof(float);
 }
 
 extern "C" int sei_ln_cl_backward_bf16(const void* gy, const void* x, const float* mean, const float* rstd,
@@ -446,13 +539,20 @@ extern "C" int sei_ln_cl_backward_bf16(const void* gy, const void* x, const floa
     int VPL;
     ln_shape(C, &p.G, &VPL);
     const unsigned grid = ln_grid(T, p.G, dp.sm_count);
-    switch (VPL) {
+    const char* nofuse = getenv("SEI_LN_NO_FUSE");         // A/B switch: separate parameter-gradient pass
+    const bool fused = (VPL == 1 || VPL == 2) && C <= 512 && !(nofuse && *nofuse == '1');
+    if (fused) p.beta = static_cast<const float*>(workspace);      // partial rows [grid][2][C] (the backward needs no beta)
+    switch (fused ? VPL : (VPL == 1 || VPL == 2 ? -VPL : 0)) {
     case 1: ln_bwd_dx_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
     case 2: ln_bwd_dx_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
     default: ln_bwd_dx_kernel<0><<<grid, kLnThreads, 0, st>>>(p); break;
     }
     rc = finish_launch("ln_bwd_dx_kernel");
     if (rc) return rc;
+    if (fused) {
+        colsum_final_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), dgamma, dbeta, grid, 2 * C, C);
+        return finish_launch("colsum_final_kernel");
+    }
     colsum_kernel<0><<<(unsigned)(threads / kLnThreads), kLnThreads, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gy), mean, rstd,
         static_cast<float*>(workspace), T, C);
