@@ -339,8 +339,8 @@ def run_b200(args):
                         "frac": round(achieved / peaks["hbm"], 4), "traffic": None,
                         "peak_source": peaks["src"], "us_per_launch": round(us, 2),
                         "algorithmic_bytes_per_launch": alg_bytes,
-                        "how": f"{reps} back-to-back launches on 128x{CH}x{SIZE}x{SIZE} fp32, 3 rotating inputs (400 MB > L2); "
-                               "traffic: not measured in this run (ncu --set full captures of this kernel are under profiles/)"}
+                        "how": f"{reps} back-to-back launches on 128x{CH}x{SIZE}x{SIZE} fp32, 3 rotating inputs (400 MB > L2)"}
+        roofline_ops["traffic"], roofline_ops["traffic_source"] = ncu_traffic("blur_band_kernel", "r02_ncu_blur_band_traffic.json")
         del big
         roofline = roofline_ops
         if args.network == "cnn":
@@ -372,6 +372,7 @@ def run_b200(args):
                         "step_frac_of_sustained_peak": round(step_tf / peaks["tf_sustained"], 4),
                         "how": f"{reps} back-to-back launches, CUDA events; step_*: tensor-core flops of every GEMM launched in one "
                                "step (counted by sei_b200.ops) / the timed step"}
+            roofline["traffic"], roofline["traffic_source"] = ncu_traffic("gemm_bf16_tn_2cta_kernel", "r02_ncu_gemm_2cta_s4_traffic.json")
             del a_, w_
 
     cpu_baseline = None
@@ -579,6 +580,25 @@ def run_reference(args):
            "e2e": {"value": base["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
+
+
+
+def ncu_traffic(kernel_substr, fname):
+    """DRAM bytes per launch of a kernel from a committed `ncu --set full` capture of the same launch shape
+    (profiles/<fname>, written on the GPU box by benchmarks/ncu_summary.py: dram__bytes_read.sum + dram__bytes_write.sum).
+    Returns (bytes, provenance) or (None, why)."""
+    path = os.path.join(ROOT, "profiles", fname)
+    if not os.path.exists(path):
+        return None, f"no capture at profiles/{fname}"
+    try:
+        d = json.load(open(path))
+        ls = [l for l in d["launches"] if kernel_substr in l["kernel"]]
+        if not ls:
+            return None, f"profiles/{fname} has no launch of {kernel_substr}"
+        b = sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in ls) / len(ls)
+        return b, f"profiles/{fname}: mean of {len(ls)} launch(es), {d['source']}"
+    except Exception as e:  # noqa: BLE001
+        return None, f"profiles/{fname} unreadable ({type(e).__name__})"
 
 
 def main():

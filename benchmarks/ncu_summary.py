@@ -46,6 +46,34 @@ def main():
             f.write(f"  top {top} SASS lines by stall samples:\n")
             for r in sorted(s["rows"], key=lambda r: -int(r[sm]))[:top]:
                 f.write(f"    {100 * int(r[sm]) / tots:5.1f}%  exec {int(r[ie]):>9d}  {r[sc].strip()[:110]}\n")
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of the raw page): the `traffic` of a roofline
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        launches = []
+        if len(rows) > 2:
+            h, units = rows[0], rows[1]
+            try:
+                kn, rd, wr, du = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+                for r in rows[2:]:
+                    if len(r) <= max(rd, wr, du):
+                        continue
+                    fl = lambda v: float(v.replace(",", ""))
+                    launches.append({"kernel": r[kn][:120], "dram_read_bytes": fl(r[rd]) * scale.get(units[rd], 1.0),
+                                     "dram_write_bytes": fl(r[wr]) * scale.get(units[wr], 1.0),
+                                     "duration_us": fl(r[du]) * tscale.get(units[du], 1.0)})
+            except ValueError:
+                pass
+        if launches:
+            f.write("\n==== DRAM traffic per launch (ncu --set full, raw page)\n")
+            for l in launches:
+                f.write(f"  {l['kernel'][:90]}: read {l['dram_read_bytes'] / 1e6:.1f} MB, write {l['dram_write_bytes'] / 1e6:.1f} MB, "
+                        f"{l['duration_us']:.1f} us under ncu\n")
+            import json
+            with open(out.rsplit(".", 1)[0] + "_traffic.json", "w") as jf:
+                json.dump({"source": "ncu --set full --clock-control none, raw page: dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                           "launches": launches}, jf, indent=1)
 
 
 if __name__ == "__main__":
