@@ -510,6 +510,24 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+
+// Tile order of the CTA-pair kernels: n-tiles in groups of kRasterGN; inside a group n runs fastest, then m; then the
+// next group.  The 74 clusters that run together then cover ~9 m-tiles x 8 n-tiles (68 MB of
+// operand strips at K = 8192: they fit the 126 MB L2), the group's B strips stay resident while A streams through once
+// per group.  With plain m-fastest order a wave touched EVERY A strip (134 MB > L2) and 2-3 B strips: ncu measured
+// 9.2 GB of DRAM reads per launch of the deepest layer against 0.67 GB of operands (profiles/r02_ncu_gemm_2cta_s4*).
+constexpr int kRasterGN = 8;
+__device__ __forceinline__ void raster_tile(long long w, int tiles_m, int tiles_n, int& mt, int& nt)
+{
+    const long long per_group = (long long)kRasterGN * tiles_m;
+    const int group = (int)(w / per_group);
+    const int in_group = (int)(w - (long long)group * per_group);
+    const int gn0 = group * kRasterGN;
+    const int gsize = min(kRasterGN, tiles_n - gn0);
+    mt = in_group / gsize;
+    nt = gn0 + in_group - mt * gsize;
+}
+
 template <int STAGES, int EW = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -562,7 +580,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         if (lane == 0) {
             uint32_t it = 0;
             for (long long w = cluster_id; w < total; w += n_clusters) {
-                const int m0 = (int)(w % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(w / tiles_m) * BN + (int)rank * BNH;
+                int mt, nt;
+                raster_tile(w, tiles_m, tiles_n, mt, nt);
+                const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN + (int)rank * BNH;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, use = it / STAGES;
                     if (it >= STAGES) mbar_wait(&empty_bar[s], (use - 1) & 1);
@@ -606,7 +626,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * NSLAB * SLAB_BYTES;
         float* sb = bias_s + (warp - 2) * 64;
         for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
-            const int m0 = (int)(w % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(w / tiles_m) * BN;
+            int mt, nt;
+            raster_tile(w, tiles_m, tiles_n, mt, nt);
+            const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
@@ -684,7 +706,9 @@ gemm_bf16_atb_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             for (long long w = cluster_id; w < total; w += n_clusters) {
                 const int split = (int)(w / tiles_mn);
                 const long long rem = w - split * tiles_mn;
-                const int m0 = (int)(rem % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(rem / tiles_m) * BN + (int)rank * BNH;
+                int mt, nt;
+                raster_tile(rem, tiles_m, tiles_n, mt, nt);
+                const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN + (int)rank * BNH;
                 const int kb0 = split * p.kb_per_split;
                 const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -733,7 +757,9 @@ gemm_bf16_atb_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
             const int split = (int)(w / tiles_mn);
             const long long rem = w - split * tiles_mn;
-            const int m0 = (int)(rem % tiles_m) * 2 * BM + (int)rank * BM, n0 = (int)(rem / tiles_m) * BN;
+            int mt, nt;
+            raster_tile(rem, tiles_m, tiles_n, mt, nt);
+            const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
