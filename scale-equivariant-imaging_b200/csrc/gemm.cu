@@ -45,6 +45,7 @@ struct GemmParams {
     float res_scale;
     int res_mul;
     int gelu_dual;                 // D = gelu(A B^T + bias) and D2 (second tensor map) = gelu'(A B^T + bias)
+    int raster_gn;                 // CTA-pair kernels: n-tiles per group of the tile order (raster_tile)
 };
 
 
@@ -517,13 +518,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
 // per group.  With plain m-fastest order a wave touched EVERY A strip (134 MB > L2) and 2-3 B strips: ncu measured
 // 9.2 GB of DRAM reads per launch of the deepest layer against 0.67 GB of operands (profiles/r02_ncu_gemm_2cta_s4*).
 constexpr int kRasterGN = 8;
-__device__ __forceinline__ void raster_tile(long long w, int tiles_m, int tiles_n, int& mt, int& nt)
+__device__ __forceinline__ void raster_tile(long long w, int tiles_m, int tiles_n, int gn, int& mt, int& nt)
 {
-    const long long per_group = (long long)kRasterGN * tiles_m;
+    const long long per_group = (long long)gn * tiles_m;
     const int group = (int)(w / per_group);
     const int in_group = (int)(w - (long long)group * per_group);
-    const int gn0 = group * kRasterGN;
-    const int gsize = min(kRasterGN, tiles_n - gn0);
+    const int gn0 = group * gn;
+    const int gsize = min(gn, tiles_n - gn0);
     mt = in_group / gsize;
     nt = gn0 + in_group - mt * gsize;
 }
@@ -581,7 +582,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             uint32_t it = 0;
             for (long long w = cluster_id; w < total; w += n_clusters) {
                 int mt, nt;
-                raster_tile(w, tiles_m, tiles_n, mt, nt);
+                raster_tile(w, tiles_m, tiles_n, p.raster_gn, mt, nt);
                 const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN + (int)rank * BNH;
                 for (int kb = 0; kb < nk; ++kb, ++it) {
                     const uint32_t s = it % STAGES, use = it / STAGES;
@@ -627,7 +628,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         float* sb = bias_s + (warp - 2) * 64;
         for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
             int mt, nt;
-            raster_tile(w, tiles_m, tiles_n, mt, nt);
+            raster_tile(w, tiles_m, tiles_n, p.raster_gn, mt, nt);
             const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
@@ -707,7 +708,7 @@ gemm_bf16_atb_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const int split = (int)(w / tiles_mn);
                 const long long rem = w - split * tiles_mn;
                 int mt, nt;
-                raster_tile(rem, tiles_m, tiles_n, mt, nt);
+                raster_tile(rem, tiles_m, tiles_n, p.raster_gn, mt, nt);
                 const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN + (int)rank * BNH;
                 const int kb0 = split * p.kb_per_split;
                 const int nk = min(nk_total, kb0 + p.kb_per_split) - kb0;
@@ -758,7 +759,7 @@ gemm_bf16_atb_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const int split = (int)(w / tiles_mn);
             const long long rem = w - split * tiles_mn;
             int mt, nt;
-            raster_tile(rem, tiles_m, tiles_n, mt, nt);
+            raster_tile(rem, tiles_m, tiles_n, p.raster_gn, mt, nt);
             const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
@@ -1081,6 +1082,14 @@ static int launch_gemm_ew(const CUtensorMap& ma, const CUtensorMap& mb, const CU
     return finish_launch("gemm_bf16_tn_kernel");
 }
 
+// n-tiles per group of the CTA-pair kernels' tile order (SEI_GEMM_RASTER_GN: tuning override; a huge value = m-fastest)
+static int gemm_raster_gn()
+{
+    const char* e = getenv("SEI_GEMM_RASTER_GN");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : kRasterGN;
+}
+
 // epilogue warps per CTA (SEI_GEMM_EW=4 restores the round-1 shape for A/B measurements)
 static int gemm_epilogue_warps()
 {
@@ -1311,7 +1320,7 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
     p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
     p.res = static_cast<const __nv_bfloat16*>(ex.res); p.ld_r = (int)ex.ld_r; p.res_scale = ex.res_scale;
-    p.res_mul = ex.res_mul; p.gelu_dual = ex.d2 ? 1 : 0;
+    p.res_mul = ex.res_mul; p.gelu_dual = ex.d2 ? 1 : 0; p.raster_gn = gemm_raster_gn();
     SEI_REQUIRE(!ex.res || !out_f32, "the fused residual is a bf16-output epilogue");
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
@@ -1414,7 +1423,7 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
-    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f; p.res_mul = 0; p.gelu_dual = 0;
+    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f; p.res_mul = 0; p.gelu_dual = 0; p.raster_gn = gemm_raster_gn();
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);
