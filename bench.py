@@ -197,7 +197,25 @@ def run_b200(args):
     loss_static = torch.zeros((), device=dev)
     # gradient buckets follow the module tree (sei_b200.parallel.completion_groups) so that each can be all-reduced as
     # soon as the backward pass has produced it
-    reducer = parallel.GradAllReducer(params, module=model if args.dp_mode == "overlap" else None)
+    pipelined = args.dp_mode == "pipelined" and world > 1
+    reducer = parallel.GradAllReducer(params, module=model if args.dp_mode == "overlap" else None,
+                                      **({"max_elems": 64 * 2 ** 20} if pipelined else {}))
+    #   pipelined: graph(forward + backward), then per bucket (three for the default network: the two 268 M-parameter
+    #            convolutions of the deepest block end a bucket each) an asynchronous all-reduce followed by that
+    #            bucket's own Adam graph -- the optimizer pass of bucket i runs while bucket i + 1 is on the wire.
+    opt_parts = None
+    if pipelined:
+        opt_parts = [SeiAdam(b, lr=1e-4, betas=(0.9, 0.999)) for b in reducer.buckets if b]
+
+        class _Parts:
+            def zero_grad(self, set_to_none=False):
+                for o in opt_parts:
+                    o.zero_grad(set_to_none=set_to_none)
+
+            def step(self):
+                for o in opt_parts:
+                    o.step()
+        opt = _Parts()
 
     # Data-parallel modes (--dp-mode, only matters for N > 1):
     #   overlap: forward + backward + the per-group gradient all-reduces (launched from inside backward() on NCCL's
@@ -252,7 +270,14 @@ def run_b200(args):
                         opt.step()
             else:
                 g_step = None
-            if world > 1:
+            if pipelined:
+                g_opt = []
+                for o in opt_parts:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side, **mode):
+                        o.step()
+                    g_opt.append(g)
+            elif world > 1:
                 g_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_opt, stream=side, **mode):
                     opt.step()
@@ -270,6 +295,13 @@ def run_b200(args):
             g_step.replay()
         else:
             fwd_bwd(overlap)
+        if pipelined and g_opt is not None:
+            works = [dist.all_reduce(reducer.flat[i], op=dist.ReduceOp.AVG, async_op=True)
+                     for i, b in enumerate(reducer.buckets) if b]
+            for w, g in zip(works, g_opt):
+                w.wait()                      # the compute stream waits for THIS bucket only; the next one is on the wire
+                g.replay()
+            return
         if world > 1 and not overlap:
             reducer()
         if g_opt is not None:
@@ -624,7 +656,7 @@ def main():
     ap.add_argument("--cnn-scales", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--dp-mode", default="serial", choices=["overlap", "serial"],
+    ap.add_argument("--dp-mode", default="serial", choices=["overlap", "serial", "pipelined"],
                     help="N > 1: all-reduce the gradient buckets from inside backward() (one captured graph) or after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=200.0,
