@@ -63,11 +63,16 @@ struct LnParams {
     float eps;
 };
 
-template <int VPL>
+// GT: lanes per row as a compile-time constant (0 = run time).  ncu on the C = 32 / 128 shapes: issue slots 75 %, half of
+// the instructions integer / branch (run-time trip counts of the shuffle reductions, 64-bit index arithmetic) and 31 % of
+// the stall samples on the register copy that ended the one-deep prefetch -- at the power-capped clock of a training
+// step an issue-bound kernel is 1.4 x slower than alone.  With GT the reductions unroll, and the prefetch alternates
+// between two register buffers instead of copying.
+template <int VPL, int GT = 0>
 __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constant__ LnParams p)
 {
     constexpr int NV = VPL > 0 ? VPL : 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = p.G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = GT ? GT : p.G;
     const int gl = lane & (G - 1), sub = lane / G, rpw = 32 / G;
     const int nvec = p.C >> 3;
     const float invC = 1.0f / (float)p.C;
@@ -95,16 +100,52 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constan
             load8f(p.beta + 8 * (gl + i * G), bet[i]);
         }
     }
-    if (PF && rb < p.T) fetch(rb, cache);
+    if (PF) {
+        auto process = [&](long long rbase, const uint4 (&c)[NV]) {
+            const long long r = rbase + sub;
+            float f[NP][8];
+            float sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                unpack8(c[i], f[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sm += f[i][j];
+            }
+            const float mu = group_sum(sm, G) * invC;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q = fmaf(f[i][j] - mu, f[i][j] - mu, q);
+            const float rs = rsqrtf(group_sum(q, G) * invC + p.eps);
+            if (r < p.T) {
+                uint4* yr = reinterpret_cast<uint4*>(p.out + r * p.C);
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[i][j] = fmaf((f[i][j] - mu) * rs, gam[i][j], bet[i][j]);
+                    __stcs(yr + gl + i * G, pack8(f[i]));
+                }
+                if (gl == 0) {
+                    p.mean[r] = mu;
+                    p.rstd[r] = rs;
+                }
+            }
+        };
+        fetch(rb, cache);
+        for (; rb < p.T; rb += 2 * row_step) {
+            fetch(rb + row_step, ahead);             // in flight while `cache` is reduced (rows past the end: zeros)
+            process(rb, cache);
+            fetch(rb + 2 * row_step, cache);
+            process(rb + row_step, ahead);
+        }
+        return;
+    }
     for (; rb < p.T; rb += row_step) {
         const long long r = rb + sub;
         const bool active = r < p.T;
         const uint4* xr = reinterpret_cast<const uint4*>(p.x + (active ? r : 0) * p.C);
-        if (PF) {
-            if (rb + row_step < p.T) fetch(rb + row_step, ahead);
-        } else if (VPL > 0) {
-            fetch(rb, cache);
-        }
+        if (VPL > 0) fetch(rb, cache);
         float s = 0.f;
         if (VPL > 0) {
 #pragma unroll
@@ -152,16 +193,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constan
                 for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mu) * rs, ga[j], be[j]);
                 __stcs(yr + v, pack8(f));
             };
-            if (PF) {
-#pragma unroll
-                for (int i = 0; i < NP; ++i) {
-                    float f[8];
-                    unpack8(cache[i], f);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mu) * rs, gam[i][j], bet[i][j]);
-                    __stcs(yr + gl + i * G, pack8(f));
-                }
-            } else if (VPL > 0) {
+            if (VPL > 0) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) emit(gl + i * G, cache[i]);
             } else {
@@ -172,18 +204,14 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const __grid_constan
                 p.rstd[r] = rs;
             }
         }
-        if (PF) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) cache[i] = ahead[i];
-        }
     }
 }
 
-template <int VPL>
+template <int VPL, int GT = 0>
 __global__ void __launch_bounds__(kLnThreads, 2) ln_bwd_dx_kernel(const __grid_constant__ LnParams p)
 {
     constexpr int NV = VPL > 0 ? VPL : 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = p.G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = GT ? GT : p.G;
     const int gl = lane & (G - 1), sub = lane / G, rpw = 32 / G;
     const int nvec = p.C >> 3;
     const float invC = 1.0f / (float)p.C;
@@ -495,8 +523,15 @@ extern "C" int sei_ln_cl_forward_bf16(const void* x, const float* gamma, const f
     const unsigned grid = ln_grid(T, p.G, dp.sm_count);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (VPL) {
-    case 1: ln_fwd_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 2: ln_fwd_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 1:
+        if (p.G == 4) ln_fwd_kernel<1, 4><<<grid, kLnThreads, 0, st>>>(p);
+        else if (p.G == 16) ln_fwd_kernel<1, 16><<<grid, kLnThreads, 0, st>>>(p);
+        else ln_fwd_kernel<1><<<grid, kLnThreads, 0, st>>>(p);
+        break;
+    case 2:
+        if (p.G == 32) ln_fwd_kernel<2, 32><<<grid, kLnThreads, 0, st>>>(p);
+        else ln_fwd_kernel<2><<<grid, kLnThreads, 0, st>>>(p);
+        break;
     case 8: ln_fwd_kernel<8><<<grid, kLnThreads, 0, st>>>(p); break;
     default: ln_fwd_kernel<0><<<grid, kLnThreads, 0, st>>>(p); break;
     }
@@ -543,8 +578,15 @@ extern "C" int sei_ln_cl_backward_bf16(const void* gy, const void* x, const floa
     const bool fused = (VPL == 1 || VPL == 2) && C <= 512 && !(nofuse && *nofuse == '1');
     if (fused) p.beta = static_cast<const float*>(workspace);      // partial rows [grid][2][C] (the backward needs no beta)
     switch (fused ? VPL : (VPL == 1 || VPL == 2 ? -VPL : 0)) {
-    case 1: ln_bwd_dx_kernel<1><<<grid, kLnThreads, 0, st>>>(p); break;
-    case 2: ln_bwd_dx_kernel<2><<<grid, kLnThreads, 0, st>>>(p); break;
+    case 1:
+        if (p.G == 4) ln_bwd_dx_kernel<1, 4><<<grid, kLnThreads, 0, st>>>(p);
+        else if (p.G == 16) ln_bwd_dx_kernel<1, 16><<<grid, kLnThreads, 0, st>>>(p);
+        else ln_bwd_dx_kernel<1><<<grid, kLnThreads, 0, st>>>(p);
+        break;
+    case 2:
+        if (p.G == 32) ln_bwd_dx_kernel<2, 32><<<grid, kLnThreads, 0, st>>>(p);
+        else ln_bwd_dx_kernel<2><<<grid, kLnThreads, 0, st>>>(p);
+        break;
     default: ln_bwd_dx_kernel<0><<<grid, kLnThreads, 0, st>>>(p); break;
     }
     rc = finish_launch("ln_bwd_dx_kernel");
