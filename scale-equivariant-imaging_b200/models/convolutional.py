@@ -35,7 +35,29 @@ CL = torch.channels_last
 # float32 together with a patched _gemm_tn to check the network's structure against the reference at fp32 accuracy.
 COMPUTE_DTYPE = torch.bfloat16
 COMMUTE_DOWNSAMPLE = True      # Downsample: resample first, then the pointwise convolution on a quarter of the pixels
-_NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"     # A/B switch for measurements
+# Weight gradients of the pointwise convolutions are ADDED straight into an existing contiguous fp32 `param.grad` by the
+# GEMM epilogue (no temporary, no separate accumulation pass over 645 M parameters); the autograd node then returns
+# None for that weight.  That is what `loss.backward()` does anyway, but it is a side effect outside autograd:
+# `torch.autograd.grad(loss, weights)`, tensor hooks and `backward(inputs=...)` do not see such a gradient.  Callers
+# that need those semantics switch the fast path off: `set_inplace_weight_gradients(False)` (or SEI_NO_WGRAD_ACC=1).
+_NO_WGRAD_ACC = __import__("os").environ.get("SEI_NO_WGRAD_ACC", "0") == "1"
+# Recompute gelu / gelu' of a ConvBlock in its backward pass from the C-wide LayerNorm output instead of keeping the two
+# 4C-wide tensors between the passes (SEI_RECOMPUTE_MLP=1, or set_mlp_recompute(True)): one more conv2 GEMM per block and
+# pass (about +9 % step time at batch 32) for 1.07 GB less live memory per block and network pass -- for the
+# configurations that do not fit otherwise (SR x4 beyond batch 2, 512 x 512 at batch 16 uses 116 GiB without it).
+_RECOMPUTE_MLP = __import__("os").environ.get("SEI_RECOMPUTE_MLP", "0") == "1"
+
+
+def set_inplace_weight_gradients(enabled):
+    """see the note above _NO_WGRAD_ACC"""
+    global _NO_WGRAD_ACC
+    _NO_WGRAD_ACC = not enabled
+
+
+def set_mlp_recompute(enabled):
+    """see the note above _RECOMPUTE_MLP"""
+    global _RECOMPUTE_MLP
+    _RECOMPUTE_MLP = bool(enabled)
 # gelu'(h) in the epilogue of conv3's input-gradient GEMM (sei_gemm_bf16_tn_gelu_bwd).  Measured on B200: it removes the
 # 9 ms GELU-backward pass but the four epilogue warps then spend longer on the erf arithmetic than the tensor cores
 # on the tile (CTA-pair GEMMs 76 -> 93 ms, N = 128 GEMMs 6 -> 13 ms per step): off by default.
@@ -269,6 +291,10 @@ class _ConvBlockFn(torch.autograd.Function):
             a = ops.gelu_raw(h)
         out = ops.gemm_bf16_tn_residual(a, w3_bf, b3, xl.view(T, C), res_scale)
         ctx.gelu_epilogue = gelu_epilogue
+        ctx.recompute = _RECOMPUTE_MLP
+        if ctx.recompute:                      # keep only C-wide tensors; (a, h) are rebuilt from t2 in backward()
+            ctx.b2 = None if b2 is None else b2.detach()
+            h = a = t2.new_empty(0)
         ctx.save_for_backward(xl, t1, mean, rstd, t2, h, a, dw32, g32)
         ctx.block, ctx.res_scale, ctx.small = block, float(res_scale), small
         ctx.dtypes = (dw_w.dtype, None if dw_b is None else dw_b.dtype, ln_g.dtype, ln_b.dtype)
@@ -284,6 +310,13 @@ class _ConvBlockFn(torch.autograd.Function):
         g = g.contiguous()
         g2 = g.view(T, C)
         need = ctx.needs_input_grad
+        if ctx.recompute:
+            _, w2_bf = block.conv2._weight_matrix()
+            if ctx.gelu_epilogue:
+                a, h = ops.gemm_bf16_tn_gelu_dual(t2, w2_bf, ctx.b2)
+            else:
+                h = _gemm_tn(t2, w2_bf, ctx.b2, COMPUTE_DTYPE)
+                a = ops.gelu_raw(h)
         gb3 = _colsum(g2) if (ctx.has_bias[1] and need[10]) else None
         gw3 = _wgrad_into(block.conv3.weight, g2, a) if need[9] else None
         if ctx.gelu_epilogue:

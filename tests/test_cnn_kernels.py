@@ -459,3 +459,26 @@ def test_conv3x3_implicit_gemm_matches_torch(dev, B, H, W, kind):
     assert rel_err(xa.grad.float().cpu().numpy(), xr.grad.cpu().numpy()) < 8e-3
     assert rel_err(conv.weight.grad.cpu().numpy(), wq.grad.cpu().numpy()) < 3e-3
     assert rel_err(conv.bias.grad.cpu().numpy(), bq.grad.cpu().numpy()) < 3e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [32, 512])
+def test_convblock_mlp_recompute_is_bit_identical(dev, C, monkeypatch):
+    """recomputing gelu / gelu' in the backward pass (memory option) runs the same kernels on the same inputs: outputs and
+    input gradients are bit-identical to the default path, parameter gradients equal up to fp32 summation order"""
+    import models.convolutional as mc
+    torch.manual_seed(C + 1)
+    blk = mc.ConvBlock(C).to(dev)
+    x = torch.randn(2, C, 16, 24, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(2, C, 16, 24, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    res = []
+    for rec in (False, True):
+        monkeypatch.setattr(mc, "_RECOMPUTE_MLP", rec)
+        blk.zero_grad(set_to_none=True)
+        xa = x.clone().requires_grad_(True)
+        y = blk(xa)
+        y.backward(gy)
+        res.append((y.detach().clone(), xa.grad.clone(), {n: p.grad.detach().clone() for n, p in blk.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for n in res[0][2]:          # (split-K weight gradients add their slices with atomics: equal up to the order of fp32 sums)
+        assert rel_err(res[1][2][n].float().cpu().numpy(), res[0][2][n].float().cpu().numpy()) < 1e-5, n
