@@ -169,6 +169,22 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
 // predicated scalar loads + compares + adds per lane and chunk, three times the instructions of the conversion itself
 // -- and the residual row chunk (128 contiguous bytes per lane) is requested BEFORE the accumulator wait so that the two
 // latencies overlap.
+// The bias values of a warp's column chunks, staged in shared memory when the tile's column offset changes (with m-fastest
+// / grouped tile orders: rarely).  The first round-2 version reloaded the chunk's 64 values from global memory for every
+// chunk, which put one L2 round trip into the latency chain of every 4 KB store.
+template <int NCH>
+__device__ __forceinline__ void gemm_stage_bias(const GemmParams& p, float* sbw, int n0, int sub, int nsub, int lane)
+{
+    __syncwarp();
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int col0 = n0 + 64 * (sub + ci * nsub);
+        sbw[ci * 64 + lane] = col0 + lane < p.N ? __ldg(p.bias + col0 + lane) : 0.f;
+        sbw[ci * 64 + 32 + lane] = col0 + 32 + lane < p.N ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
+    }
+    __syncwarp();
+}
+
 template <int NSLAB>
 __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const CUtensorMap* map_d, const CUtensorMap* map_d2,
                                                       uint32_t taddr, int row0, int col0, int lane, bool add_bias,
@@ -195,11 +211,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
         }
         cp_async_commit();
     }
-    add_bias = add_bias && p.bias != nullptr;
-    if (add_bias) {
-        sb[lane] = col0 + lane < p.N ? __ldg(p.bias + col0 + lane) : 0.f;
-        sb[lane + 32] = col0 + 32 + lane < p.N ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
-    }
+    add_bias = add_bias && sb != nullptr;          // sb: the chunk's 64 bias values, staged by the caller (see gemm_stage_bias)
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(taddr, r0);
     tmem_ld_32x32(taddr + 32u, r1);
@@ -293,8 +305,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
 // short-K tile finishes its MMAs in a few hundred clocks and then waits for 32 - 64 KB of output to leave: with four
 // warps that drain (tcgen05.ld -> convert -> slab -> bulk store, each step waiting on the one before) bounded the
 // expanding pointwise convolutions of the shallow levels at half of the HBM rate.
-template <int BN, int STAGES, bool OUT_F32, bool MN = false, int EW = 4>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+template <int BN, int STAGES, bool OUT_F32, bool MN = false, int EW = 4, int MINB = 1>
+__global__ void __launch_bounds__(64 + 32 * EW, MINB)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_d2,
                     const __grid_constant__ GemmParams p)
@@ -306,7 +318,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float bias_s[EW * 64];
+    constexpr int BCH = BN >= 64 ? (BN / 64 + EW / 4 - 1) / (EW / 4) : 1;     // 64-column chunks per epilogue warp
+    __shared__ __align__(16) float bias_s[EW * BCH * 64];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // SWIZZLE_128B tiles: 1024-byte aligned
@@ -410,21 +423,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t tcount = 0, chunk_count = 0;
         constexpr int NSLAB = EW == 4 ? 2 : 1;     // staging slabs per warp (with eight warps the other warps provide the overlap)
         unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * NSLAB * SLAB_BYTES;
-        float* sb = bias_s + (warp - 2) * 64;
+        float* sbw = bias_s + (warp - 2) * BCH * 64;
+        int bias_n0 = -1;
         for (long long w = blockIdx.x; w < total; w += gridDim.x, ++tcount) {
             const int split = (int)(w / tiles_mn);
             const long long rem = w - split * tiles_mn;
             const int m0 = (int)(rem % tiles_m) * BM, n0 = (int)(rem / tiles_m) * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            const bool tma_path = !OUT_F32 && p.tma_store && BN >= 64;
+            if (tma_path && p.bias && n0 != bias_n0) {       // (before the accumulator wait: the loads overlap the MMAs)
+                gemm_stage_bias<BCH>(p, sbw, n0, sub, NSUB, lane);
+                bias_n0 = n0;
+            }
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            if (!OUT_F32 && p.tma_store && BN >= 64) {
+            if (tma_path) {
+                int ci = 0;
 #pragma unroll 1
-                for (int c = 64 * sub; c < BN; c += 64 * NSUB)
+                for (int c = 64 * sub; c < BN; c += 64 * NSUB, ++ci)
                     gemm_epilogue_chunk64<NSLAB>(p, &map_d, &map_d2, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, split == 0,
-                                                 slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
+                                                 slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES,
+                                                 p.bias ? sbw + ci * 64 : nullptr);
             } else {
 #pragma unroll 1
                 for (int c = 32 * sub; c < BN; c += 32 * NSUB) {
@@ -542,7 +563,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float bias_s[EW * 64];
+    constexpr int BCH = (256 / 64 + EW / 4 - 1) / (EW / 4);      // 64-column chunks per epilogue warp
+    __shared__ __align__(16) float bias_s[EW * BCH * 64];
 
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -625,19 +647,26 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         uint32_t tcount = 0, chunk_count = 0;
         constexpr int NSLAB = EW == 4 ? 2 : 1;
         unsigned char* slabs = tiles + (size_t)STAGES * STAGE_BYTES + (size_t)(warp - 2) * NSLAB * SLAB_BYTES;
-        float* sb = bias_s + (warp - 2) * 64;
+        float* sbw = bias_s + (warp - 2) * BCH * 64;
+        int bias_n0 = -1;
         for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
             int mt, nt;
             raster_tile(w, tiles_m, tiles_n, p.raster_gn, mt, nt);
             const int m0 = mt * 2 * BM + (int)rank * BM, n0 = nt * BN;
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
+            if (p.bias && n0 != bias_n0) {
+                gemm_stage_bias<BCH>(p, sbw, n0, sub, NSUB, lane);
+                bias_n0 = n0;
+            }
             mbar_wait(&tmem_full_bar[acc], acc_use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            int ci = 0;
 #pragma unroll 1
-            for (int c = 64 * sub; c < BN; c += 64 * NSUB)
+            for (int c = 64 * sub; c < BN; c += 64 * NSUB, ++ci)
                 gemm_epilogue_chunk64<NSLAB>(p, &map_d, &map_d2, taddr + (uint32_t)c, m0 + q * 32, n0 + c, lane, true,
-                                             slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES, sb);
+                                             slabs + (size_t)(chunk_count++ % NSLAB) * SLAB_BYTES,
+                                             p.bias ? sbw + ci * 64 : nullptr);
             tc_fence_before();
             mbar_arrive_leader(&tmem_empty_bar[acc]);       // this thread is done reading the accumulator stage
         }
@@ -1090,6 +1119,21 @@ static int gemm_raster_gn()
     return v > 0 ? v : kRasterGN;
 }
 
+// Short-K, wide-output products (the expanding pointwise convolutions of the two shallowest levels: K <= 128): two
+// CTAs per SM with a two-stage ring and four epilogue warps each -- two producers, two MMA issuers and two independent
+// accumulator pipelines per SM instead of one (SEI_GEMM_SHORTK=0: the one-CTA shape)
+static int launch_gemm_short_k(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& md2,
+                               const GemmParams& p, int sm_count, cudaStream_t st)
+{
+    constexpr int BN = 128, STAGES = 2, EW = 4;
+    constexpr size_t smem = (size_t)STAGES * (kGemmBM + BN) * kGemmBK * 2 + 1024 + (size_t)EW * 2 * 32 * 128;
+    const long long tiles = (long long)((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
+    const unsigned grid = (unsigned)std::min<long long>(tiles, 2ll * sm_count);
+    SEI_CUDA(allow_smem(gemm_bf16_tn_kernel<BN, STAGES, false, false, EW, 2>, smem));
+    gemm_bf16_tn_kernel<BN, STAGES, false, false, EW, 2><<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, md, md2, p);
+    return finish_launch("gemm_bf16_tn_kernel");
+}
+
 // epilogue warps per CTA (SEI_GEMM_EW=4 restores the round-1 shape for A/B measurements)
 static int gemm_epilogue_warps()
 {
@@ -1367,6 +1411,9 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
         }
         return finish_launch("gemm_bf16_tn_2cta_kernel");
     }
+    const char* sk = getenv("SEI_GEMM_SHORTK");
+    if (bn == 128 && nk <= 2 && !out_f32 && p.tma_store && !(sk && *sk == '0'))
+        return launch_gemm_short_k(ma, mb, md, md2, p, dp.sm_count, st);
     if (gemm_epilogue_warps() == 8) {        // eight epilogue warps; one operand stage fewer where the slabs need the room
         switch (bn) {
         case 32: return launch_gemm_ew<32, 8, 8>(ma, mb, md, md2, p, out_f32 != 0, dp.sm_count, st);
