@@ -205,6 +205,13 @@ int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, const float
                               long long M, int N, int K, long long lda, long long ldb, long long ldd, long long ld_r,
                               void* stream);
 
+/* D (bf16) = A B^T + bias[n] * row_scale[m % period]: Downsample's pointwise convolution (reference
+ * src/models/convolutional.py:136-150) applied AFTER the ideal resampler (the two commute); the constant image bias[n]
+ * turns into bias[n] * R(1)[pixel], a per-row factor added in the GEMM epilogue.  row_scale: fp32 [period] (device). */
+int sei_gemm_bf16_tn_rowscaled_bias(const void* A, const void* B, void* D, const float* bias, const float* row_scale,
+                                    int period, long long M, int N, int K, long long lda, long long ldb, long long ldd,
+                                    void* stream);
+
 /* Aout (bf16) = gelu(A B^T + bias) and Dout (bf16) = gelu'(A B^T + bias), both written from the GEMM epilogue:
  * ConvBlock.conv2 followed by ConvBlock.gelu (reference src/models/convolutional.py:40-41, 46-47) without the
  * pre-activation ever reaching memory.  The pre-activation is rounded to bf16 before the GELU (the value an unfused

@@ -46,6 +46,8 @@ struct GemmParams {
     int res_mul;
     int gelu_dual;                 // D = gelu(A B^T + bias) and D2 (second tensor map) = gelu'(A B^T + bias)
     int raster_gn;                 // CTA-pair kernels: n-tiles per group of the tile order (raster_tile)
+    const float* row_scale;        // optional [row_period]: the bias of row r is bias[n] * row_scale[r % row_period]
+    int row_period;
 };
 
 
@@ -101,9 +103,10 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmParams& p, const uint
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (p.bias && add_bias) {
+        const float rsc = p.row_scale ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            if (col0 + j < p.N) v[j] = fmaf(rsc, __ldg(p.bias + col0 + j), v[j]);
     }
     if (!OUT_F32 && p.res) {
         const __nv_bfloat16* rp = p.res + (size_t)row * p.ld_r + col0;
@@ -212,6 +215,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
         cp_async_commit();
     }
     add_bias = add_bias && sb != nullptr;          // sb: the chunk's 64 bias values, staged by the caller (see gemm_stage_bias)
+    // bias behind a resampler (Downsample with the resampler applied first): the constant image bias[n] became
+    // bias[n] * R(1)[pixel], a per-row factor
+    const float rsc = (add_bias && p.row_scale) ? __ldg(p.row_scale + (min(row, p.M - 1) % p.row_period)) : 1.0f;
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(taddr, r0);
     tmem_ld_32x32(taddr + 32u, r1);
@@ -237,8 +243,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const GemmParams& p, const
         }
         if (add_bias) {
             const float4 b0 = *reinterpret_cast<const float4*>(sb + 8 * j), b1 = *reinterpret_cast<const float4*>(sb + 8 * j + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            v[0] = fmaf(rsc, b0.x, v[0]); v[1] = fmaf(rsc, b0.y, v[1]); v[2] = fmaf(rsc, b0.z, v[2]); v[3] = fmaf(rsc, b0.w, v[3]);
+            v[4] = fmaf(rsc, b1.x, v[4]); v[5] = fmaf(rsc, b1.y, v[5]); v[6] = fmaf(rsc, b1.z, v[6]); v[7] = fmaf(rsc, b1.w, v[7]);
         }
         if (has_res) {
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
@@ -1273,6 +1279,8 @@ struct GemmEpilogueExtra {
     float res_scale = 1.0f;
     int res_mul = 0;
     void* d2 = nullptr;                // gelu_dual: second output gelu'(.) (same shape and pitch as D)
+    const float* row_scale = nullptr;  // per-row factor of the bias (period row_period)
+    int row_period = 1;
 };
 
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
@@ -1296,6 +1304,19 @@ extern "C" int sei_gemm_bf16_tn_residual(const void* A, const void* B, void* D, 
     SEI_REQUIRE(N % 8 == 0, "the fused residual needs N %% 8 == 0 (N=%d)", N);
     GemmEpilogueExtra ex;
     ex.res = R; ex.ld_r = ld_r; ex.res_scale = res_scale;
+    return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
+}
+
+// D (bf16) = A B^T + bias[n] * row_scale[m % period]: the pointwise convolution of Downsample (reference
+// src/models/convolutional.py:136-150) when the ideal resampler is applied BEFORE it -- the constant image bias[n]
+// becomes bias[n] * R(1)[pixel]; added in the GEMM epilogue instead of an in-place pass over the output.
+extern "C" int sei_gemm_bf16_tn_rowscaled_bias(const void* A, const void* B, void* D, const float* bias, const float* row_scale,
+                                               int period, long long M, int N, int K, long long lda, long long ldb,
+                                               long long ldd, void* stream)
+{
+    SEI_REQUIRE(bias && row_scale && period > 0, "bias, row_scale and a positive period are required");
+    GemmEpilogueExtra ex;
+    ex.row_scale = row_scale; ex.row_period = period;
     return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
 }
 
@@ -1365,6 +1386,7 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
     p.res = static_cast<const __nv_bfloat16*>(ex.res); p.ld_r = (int)ex.ld_r; p.res_scale = ex.res_scale;
     p.res_mul = ex.res_mul; p.gelu_dual = ex.d2 ? 1 : 0; p.raster_gn = gemm_raster_gn();
+    p.row_scale = ex.row_scale; p.row_period = ex.row_period;
     SEI_REQUIRE(!ex.res || !out_f32, "the fused residual is a bf16-output epilogue");
     // bf16 output through shared memory + bulk tensor stores when the row pitch allows a tensor map
     const char* nts = getenv("SEI_GEMM_NO_TMA_STORE");
@@ -1470,7 +1492,7 @@ static int gemm_bf16_atb_impl(const void* A, const void* B, float* D, long long 
     if (rc) return rc;
     GemmParams p;
     p.D = D; p.bias = nullptr; p.M = M; p.N = N; p.K = (int)K; p.ldd = N; p.tma_store = 0; p.accumulate = accumulate;
-    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f; p.res_mul = 0; p.gelu_dual = 0; p.raster_gn = gemm_raster_gn();
+    p.gelu_h = nullptr; p.ld_h = 0; p.res = nullptr; p.ld_r = 0; p.res_scale = 0.f; p.res_mul = 0; p.gelu_dual = 0; p.raster_gn = gemm_raster_gn(); p.row_scale = nullptr; p.row_period = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nk = (int)((K + kGemmBK - 1) / kGemmBK);
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn);

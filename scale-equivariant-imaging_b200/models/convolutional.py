@@ -161,13 +161,16 @@ class _GemmTN(torch.autograd.Function):
     """out[T, N] = x[T, K] @ w[N, K]^T + bias[N]; all three passes on sei_gemm_bf16_tn."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, wt_getter, param=None, res=None):
+    def forward(ctx, x, weight, bias, w_bf16, wt_getter, param=None, res=None, row_scale=None):
         ctx.save_for_backward(x, w_bf16)
         ctx.has_bias = bias is not None
         ctx.wt_getter = wt_getter
         ctx.param = param                      # nn.Parameter whose .grad may receive the weight gradient in place
+        ctx.row_scale = row_scale if bias is not None else None
         if res is not None:                    # out = x w^T + bias + res, the addition in the GEMM epilogue
             return ops.gemm_bf16_tn_residual(x, w_bf16, bias, res, 1.0)
+        if ctx.row_scale is not None:          # out = x w^T + bias[n] * row_scale[m % period] (bias behind a resampler)
+            return ops.gemm_bf16_tn_rowscaled_bias(x, w_bf16, bias, row_scale)
         return _gemm_tn(x, w_bf16, bias, COMPUTE_DTYPE)
 
     @staticmethod
@@ -195,8 +198,9 @@ class _GemmTN(torch.autograd.Function):
                 gw = _gemm_tn(_pad_k(gy.t()), _pad_k(x.t()), None, torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             # one pass, fp32 accumulation, fixed order (csrc/cnn_elem.cu); library reduction for odd channel counts
-            gb = _colsum(gy)
-        return gx, gw, gb, None, None, None, (gy if len(ctx.needs_input_grad) > 6 and ctx.needs_input_grad[6] else None)
+            gb = _colsum(gy) if ctx.row_scale is None else ops.bias_pattern_grad(gy, ctx.row_scale)
+        return (gx, gw, gb, None, None, None, (gy if len(ctx.needs_input_grad) > 6 and ctx.needs_input_grad[6] else None),
+                None)
 
 
 class _GeluGemmTN(torch.autograd.Function):
@@ -441,6 +445,19 @@ class _GemmConv2d(Conv2d):
         out = _GeluGemmTN.apply(h2, w2, self.bias, w_bf16, self._weight_matrix_t, self.weight)
         return out.view(B, H, W, -1).permute(0, 3, 1, 2)
 
+    def forward_rowscaled_bias(self, x, row_scale):
+        """1x1 convolution whose bias is multiplied by row_scale[pixel] (Downsample behind its resampler); None when the
+        shape needs the unfused path"""
+        B, C, H, W = x.shape
+        if not (self.kernel_size == (1, 1) and self.bias is not None and x.is_cuda and C % 8 == 0 and self.out_channels % 8 == 0
+                and COMPUTE_DTYPE == torch.bfloat16 and ops.padded_width(self.out_channels, "colsum") == self.out_channels):
+            return None
+        xl = x.to(dtype=COMPUTE_DTYPE, memory_format=CL).permute(0, 2, 3, 1)
+        w2, w_bf16 = self._weight_matrix()
+        out = _GemmTN.apply(xl.reshape(B * H * W, C), w2, self.bias, w_bf16, self._weight_matrix_t,
+                            self.weight if w_bf16.shape == w2.shape else None, None, row_scale.reshape(-1))
+        return out.view(B, H, W, -1).permute(0, 3, 1, 2)
+
     def forward(self, x, use_bias=True, residual=None):
         """residual: a tensor of the output's shape added to it -- in the GEMM epilogue when the shapes allow"""
         B, C, H, W = x.shape
@@ -600,9 +617,16 @@ class Downsample(Module):
             # resampler bytes and GEMM flops than conv -> resample).  The bias is a constant image per channel; the
             # resampler maps it to bias[c] * R(1), added afterwards.
             H, W = x.shape[-2], x.shape[-1]
-            out = self.conv.forward_nobias(self.ideal_downsample(x))
+            xr = self.ideal_downsample(x)
             if self.conv.bias is not None:
+                # the scaled bias rides in the GEMM epilogue (an in-place pass on a view of the GEMM output made autograd
+                # copy the whole tensor on the way back: 2.2 ms of device-to-device copies per step)
                 pat = resample.constant_response("down", H, W, self.rate, x.device)                 # (Ho, Wo) fp32
+                out = self.conv.forward_rowscaled_bias(xr, pat)
+                if out is not None:
+                    return out
+            out = self.conv.forward_nobias(xr)
+            if self.conv.bias is not None:
                 rows = out.permute(0, 2, 3, 1).reshape(-1, out.shape[1])                            # view of the GEMM output
                 out = _op_bias_pattern(out, rows, pat, self.conv.bias)
             return out

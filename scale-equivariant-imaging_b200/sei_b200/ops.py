@@ -403,6 +403,22 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     return d
 
 
+def gemm_bf16_tn_rowscaled_bias(a, b, bias, row_scale):
+    """D[M,N] (bf16) = a @ b^T + bias[n] * row_scale[m % len(row_scale)] (sei_gemm_bf16_tn_rowscaled_bias)"""
+    _check_2d_bf16("gemm_bf16_tn_rowscaled_bias", a=a, b=b)
+    M, K = a.shape
+    N, K2 = b.shape
+    if K != K2:
+        raise SeiError("gemm_bf16_tn_rowscaled_bias: inner dimensions differ")
+    bias, row_scale = _t(bias, "bias"), _t(row_scale, "row_scale").reshape(-1)
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_tn_rowscaled_bias(_ptr(a), _ptr(b), _ptr(d), _ptr(bias), _ptr(row_scale),
+                                                          row_scale.numel(), M, N, K, a.stride(0), b.stride(0), N, _stream(a)))
+    return d
+
+
 def gemm_bf16_tn_residual(a, b, bias, res, res_scale=1.0):
     """D[M,N] (bf16) = a[M,K] @ b[N,K]^T + bias[N] + res_scale * res[M,N]: a pointwise convolution added to a tensor of its
     output's shape in the GEMM epilogue (sei_gemm_bf16_tn_residual)"""
@@ -836,6 +852,18 @@ class _BiasPattern(torch.autograd.Function):
         with torch.cuda.device(gy.device):
             check(lib.sei_bias_pattern_grad_bf16(_ptr(gy), _ptr(pat), _ptr(gb), _ptr(ws), T, Cc, pat.numel(), _stream(gy)))
         return gy, None, gb.to(ctx.bias_dtype)
+
+
+def bias_pattern_grad(gy_rows, pat):
+    """fp32 [C]: sum_t pat[t % period] * gy[t, c] -- the bias gradient behind a resampler (sei_bias_pattern_grad_bf16)"""
+    T, Cc = gy_rows.shape
+    lib = _lib.load()
+    pat = _t(pat, "pat").reshape(-1)
+    gb = torch.empty(Cc, dtype=torch.float32, device=gy_rows.device)
+    ws = torch.empty(int(lib.sei_ln_cl_backward_workspace_bytes(Cc)), dtype=torch.uint8, device=gy_rows.device)
+    with torch.cuda.device(gy_rows.device):
+        check(lib.sei_bias_pattern_grad_bf16(_ptr(gy_rows), _ptr(pat), _ptr(gb), _ptr(ws), T, Cc, pat.numel(), _stream(gy_rows)))
+    return gb
 
 
 def bias_pattern_add(rows, pat, bias):

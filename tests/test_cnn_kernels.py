@@ -482,3 +482,17 @@ def test_convblock_mlp_recompute_is_bit_identical(dev, C, monkeypatch):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for n in res[0][2]:          # (split-K weight gradients add their slices with atomics: equal up to the order of fp32 sums)
         assert rel_err(res[1][2][n].float().cpu().numpy(), res[0][2][n].float().cpu().numpy()) < 1e-5, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,period", [(1024, 128, 32, 256), (4096, 512, 128, 64), (300, 40, 72, 25), (2048, 2048, 512, 16)])
+def test_gemm_rowscaled_bias(dev, M, N, K, period):
+    """D = A B^T + bias[n] * row_scale[m % period] (Downsample's convolution behind its resampler) vs fp32"""
+    from sei_b200 import ops
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bias, rs = torch.randn(N, device=dev), torch.rand(period, device=dev) + 0.5
+    d = ops.gemm_bf16_tn_rowscaled_bias(a, b, bias, rs)
+    ref = a.float() @ b.float().t() + rs.repeat(-(-M // period))[:M, None] * bias[None, :]
+    assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
