@@ -212,6 +212,13 @@ int sei_gemm_bf16_tn_rowscaled_bias(const void* A, const void* B, void* D, const
                                     int period, long long M, int N, int K, long long lda, long long ldb, long long ldd,
                                     void* stream);
 
+/* D (bf16) = A Bkn (optionally * Mult element-wise): B given as [K, N] row-major and read IN PLACE as an MN-major UMMA
+ * operand by the CTA-pair kernel.  The input gradient of a pointwise convolution (autograd of nn.Conv2d(kernel_size=1),
+ * reference src/models/convolutional.py:40-42,106,143): gx = gy W with W the (C_out x C_in) weight itself, so no
+ * transposed copy of the weights exists.  M >= 256, N >= 256, N % 8 == 0; Mult: bf16 [M, N] (row pitch ld_m) or NULL. */
+int sei_gemm_bf16_nn(const void* A, const void* Bkn, const void* Mult, void* D, long long M, int N, int K, long long lda,
+                     long long ldb, long long ldd, long long ld_m, void* stream);
+
 /* Aout (bf16) = gelu(A B^T + bias) and Dout (bf16) = gelu'(A B^T + bias), both written from the GEMM epilogue:
  * ConvBlock.conv2 followed by ConvBlock.gelu (reference src/models/convolutional.py:40-41, 46-47) without the
  * pre-activation ever reaching memory.  The pre-activation is rounded to bf16 before the GELU (the value an unfused

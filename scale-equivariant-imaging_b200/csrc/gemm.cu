@@ -556,7 +556,10 @@ __device__ __forceinline__ void raster_tile(long long w, int tiles_m, int tiles_
     nt = gn0 + in_group - mt * gsize;
 }
 
-template <int STAGES, int EW = 4>
+// B_MN: the B operand is given as [K, N] row-major (N contiguous: the UMMA MN-major layout, TMA boxes of 64 n x BK k-rows,
+// two per CTA) instead of [N, K] -- D = A B.  The input-gradient GEMMs read the weight matrix in place that way; round 1
+// kept a transposed bf16 copy of every weight (1.3 GB, rewritten by the optimizer every step: 1.8 ms of transposes).
+template <int STAGES, int EW = 4, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_d2,
@@ -618,14 +621,20 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                     unsigned char* a_dst = tiles + (size_t)s * STAGE_BYTES;
                     tma_load_2d_2sm(a_dst, &map_a, kb * BK, m0, &full_bar[s]);
-                    tma_load_2d_2sm(a_dst + A_BYTES, &map_b, kb * BK, n0, &full_bar[s]);
+                    if (B_MN) {
+#pragma unroll
+                        for (int nb = 0; nb < BNH / 64; ++nb)
+                            tma_load_2d_2sm(a_dst + A_BYTES + nb * (BK * 128), &map_b, n0 + 64 * nb, kb * BK, &full_bar[s]);
+                    } else {
+                        tma_load_2d_2sm(a_dst + A_BYTES, &map_b, kb * BK, n0, &full_bar[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, false);
+            constexpr uint32_t idesc = B_MN ? umma_idesc_bf16_kmn(2 * BM, BN) : umma_idesc_bf16(2 * BM, BN, false);
             uint32_t it = 0, tcount = 0;
             for (long long w = cluster_id; w < total; w += n_clusters, ++tcount) {
                 const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
@@ -637,10 +646,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     mbar_wait(&full_bar[s], (it / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                    const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + A_BYTES);
+                    const uint64_t da = umma_smem_desc_sw128(a_addr);
+                    const uint64_t db = B_MN ? umma_smem_desc_mn_sw128(a_addr + A_BYTES, BK * 128) : umma_smem_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 16; ++k)     // B_MN: 16 k-rows = 2048 B further = +128 in the (addr >> 4) field
+                        umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(B_MN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
                     umma_commit_2sm(&empty_bar[s]);              // frees this stage in both CTAs
                 }
                 umma_commit_2sm(&tmem_full_bar[acc]);            // accumulator complete: both epilogues
@@ -842,12 +852,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
-// instruction descriptor: A K-major, B MN-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_kmn(int M, int N)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 struct BgemmTcParams {
     int M, K, N;                 // logical sizes
     int mb, kb;                  // 128-row blocks of A per CTA (1 or 2), 64-column k-blocks
@@ -1281,6 +1285,7 @@ struct GemmEpilogueExtra {
     void* d2 = nullptr;                // gelu_dual: second output gelu'(.) (same shape and pitch as D)
     const float* row_scale = nullptr;  // per-row factor of the bias (period row_period)
     int row_period = 1;
+    bool b_kn = false;                 // B is [K, N] row-major (read in place as an MN-major operand): D = A B
 };
 
 static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float* bias, long long M, int N, int K,
@@ -1318,6 +1323,22 @@ extern "C" int sei_gemm_bf16_tn_rowscaled_bias(const void* A, const void* B, voi
     GemmEpilogueExtra ex;
     ex.row_scale = row_scale; ex.row_period = period;
     return gemm_bf16_tn_impl(A, B, D, bias, M, N, K, lda, ldb, ldd, 0, 0, ex, stream);
+}
+
+// D (bf16) = A Bkn (* Mult): B given as [K, N] row-major and read in place (MN-major UMMA operand) by the CTA-pair kernel:
+// the input gradient of a pointwise convolution, gx = gy W with W = the (C_out x C_in) weight itself -- no transposed
+// copy of the weights.  Mult (optional, bf16 [M, N], row pitch ld_m): element-wise multiplier in the epilogue (the stored
+// gelu').  Needs M >= 256, N >= 256.
+extern "C" int sei_gemm_bf16_nn(const void* A, const void* Bkn, const void* Mult, void* D, long long M, int N, int K,
+                                long long lda, long long ldb, long long ldd, long long ld_m, void* stream)
+{
+    GemmEpilogueExtra ex;
+    ex.b_kn = true;
+    if (Mult) {
+        SEI_REQUIRE(aligned16(Mult) && ld_m % 8 == 0 && ld_m >= N, "Mult must be 16-byte aligned with a row pitch >= N that is a multiple of 8");
+        ex.res = Mult; ex.ld_r = ld_m; ex.res_mul = 1;
+    }
+    return gemm_bf16_tn_impl(A, Bkn, D, nullptr, M, N, K, lda, ldb, ldd, 0, 256, ex, stream);
 }
 
 // Aout (bf16) = gelu(A B^T + bias), Dout (bf16) = gelu'(A B^T + bias): ConvBlock.conv2 and ConvBlock.gelu (reference
@@ -1365,7 +1386,9 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     const long long ld_h = ex.ld_h;
     SEI_REQUIRE(A && B && D, "null pointer argument");
     SEI_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31), "bad shape M=%lld N=%d K=%d", M, N, K);
-    SEI_REQUIRE(lda >= K && ldb >= K && ldd >= N, "leading dimensions smaller than the rows");
+    SEI_REQUIRE(lda >= K && ldb >= (ex.b_kn ? N : K) && ldd >= N, "leading dimensions smaller than the rows");
+    SEI_REQUIRE(!ex.b_kn || (!out_f32 && M >= 256 && N >= 256 && N % 8 == 0 && ldd % 8 == 0),
+                "the [K, N] form of B is taken by the CTA-pair kernel only (bf16 output, M >= 256, N >= 256, N %% 8 == 0)");
     SEI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA row pitch); pad K");
     SEI_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), "A, B, D must be 16-byte aligned");
     DeviceProps dp;
@@ -1379,8 +1402,10 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     CUtensorMap ma, mb;
     rc = make_map_bf16(&ma, A, M, K, lda, kGemmBM);
     if (rc) return rc;
-    rc = make_map_bf16(&mb, B, N, K, ldb, bn);
-    if (rc) return rc;
+    if (!ex.b_kn) {
+        rc = make_map_bf16(&mb, B, N, K, ldb, bn);
+        if (rc) return rc;
+    }
     GemmParams p;
     p.D = D; p.bias = bias; p.M = (int)M; p.N = N; p.K = K; p.ldd = (int)ldd; p.accumulate = 0;
     p.gelu_h = static_cast<const __nv_bfloat16*>(gelu_h); p.ld_h = (int)ld_h;
@@ -1417,11 +1442,15 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
     if (bn == 256 && p.tma_store && p.splits == 1 && M >= 256 && N >= 256 && dp.sm_count >= 2 && !(no2 && *no2 == '1')) {
         constexpr int ST2 = 5;
         CUtensorMap mb2;
-        rc = make_map_bf16(&mb2, B, N, K, ldb, 128);
+        rc = ex.b_kn ? make_map_bf16_mn(&mb2, B, K, N, ldb) : make_map_bf16(&mb2, B, N, K, ldb, 128);
         if (rc) return rc;
         const long long ctiles = ((M + 255) / 256) * (long long)((N + 255) / 256);
         const unsigned grid = 2u * (unsigned)std::min<long long>(ctiles, dp.sm_count / 2);
-        if (gemm_epilogue_warps() == 8) {
+        if (ex.b_kn) {
+            constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 8 * 32 * 128;
+            SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 8, true>, smem2));
+            gemm_bf16_tn_2cta_kernel<ST2, 8, true><<<grid, 64 + 32 * 8, smem2, st>>>(ma, mb2, md, md2, p);
+        } else if (gemm_epilogue_warps() == 8) {
             constexpr size_t smem2 = (size_t)ST2 * (kGemmBM + 128) * kGemmBK * 2 + 1024 + 8 * 32 * 128;
             static_assert(smem2 + 4096 <= 227 * 1024, "CTA-pair kernel: ring + slabs + barriers exceed the shared memory of an SM");
             SEI_CUDA(allow_smem(gemm_bf16_tn_2cta_kernel<ST2, 8>, smem2));
@@ -1433,6 +1462,7 @@ static int gemm_bf16_tn_impl(const void* A, const void* B, void* D, const float*
         }
         return finish_launch("gemm_bf16_tn_2cta_kernel");
     }
+    SEI_REQUIRE(!ex.b_kn, "the [K, N] form of B needs the CTA-pair kernel (disabled by SEI_GEMM_NO_2CTA or a split)");
     const char* sk = getenv("SEI_GEMM_SHORTK");
     if (bn == 128 && nk <= 2 && !out_f32 && p.tma_store && !(sk && *sk == '0'))
         return launch_gemm_short_k(ma, mb, md, md2, p, dp.sm_count, st);

@@ -113,6 +113,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool mn_maj
 }
 
 
+// instruction descriptor: A K-major, B MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_kmn(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -87,6 +87,23 @@ def _gemm_atb(a, b, out=None):
     return ops.gemm_bf16_atb(a, b, out=out)
 
 
+# input gradients read the weight matrix in place (sei_gemm_bf16_nn) where the CTA-pair kernel takes the shape; SEI_DGRAD_NN=0:
+# the transposed bf16 copies of round 1 (kept for the small layers either way)
+_DGRAD_NN = __import__("os").environ.get("SEI_DGRAD_NN", "1") == "1"
+
+
+def _dgrad(gy, w_bf16, wt_getter, mult=None):
+    """gx = gy @ W (* mult): W = w_bf16 [C_out, C_in] read in place by the CTA-pair kernel when the shape allows, else through
+    the transposed copy (wt_getter)"""
+    gy = _pad_k(gy)
+    if (_DGRAD_NN and COMPUTE_DTYPE == torch.bfloat16 and gy.is_cuda and w_bf16.shape[0] == gy.shape[1]
+            and ops.gemm_nn_supported(gy.shape[0], w_bf16.shape[1])):
+        return ops.gemm_bf16_nn(gy, w_bf16, mult)
+    if mult is not None:
+        return ops.gemm_bf16_tn_mul(gy, wt_getter(), mult)
+    return _gemm_tn(gy, wt_getter(), None, COMPUTE_DTYPE)
+
+
 def _require_device_rows(t, what):
     if not t.is_cuda or t.dtype != torch.bfloat16:
         raise SeiError(f"{what}: got a {t.dtype} tensor on {t.device}; the restoration CNN runs on CUDA (sm_100a) in bf16 "
@@ -179,7 +196,7 @@ class _GemmTN(torch.autograd.Function):
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = _gemm_tn(_pad_k(gy), ctx.wt_getter(), None, COMPUTE_DTYPE)          # dgrad: gy[T,N] @ w[N,K]
+            gx = _dgrad(gy, w_bf16, ctx.wt_getter)                                    # dgrad: gy[T,N] @ w[N,K]
         if ctx.needs_input_grad[1]:
             if gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0:
                 g = None if (ctx.param is None or _NO_WGRAD_ACC) else ctx.param.grad
@@ -324,14 +341,14 @@ class _ConvBlockFn(torch.autograd.Function):
         gb3 = _colsum(g2) if (ctx.has_bias[1] and need[10]) else None
         gw3 = _wgrad_into(block.conv3.weight, g2, a) if need[9] else None
         if ctx.gelu_epilogue:
-            gh = ops.gemm_bf16_tn_mul(g2, block.conv3._weight_matrix_t(), h)            # (g W3) * gelu'(h): [T, 4C]
+            gh = _dgrad(g2, block.conv3._weight_matrix()[1], block.conv3._weight_matrix_t, mult=h)     # (g W3) * gelu'(h)
             gb2 = _colsum(gh) if (ctx.has_bias[0] and need[8]) else None
         else:
-            ga = _gemm_tn(g2, block.conv3._weight_matrix_t(), None, COMPUTE_DTYPE)      # [T, 4C]
+            ga = _dgrad(g2, block.conv3._weight_matrix()[1], block.conv3._weight_matrix_t)            # [T, 4C]
             gh, gb2 = ops.gelu_bwd_colsum(h, ga)
             del ga
         gw2 = _wgrad_into(block.conv2.weight, gh, t2) if need[7] else None
-        gt2 = _gemm_tn(gh, block.conv2._weight_matrix_t(), None, COMPUTE_DTYPE)         # [T, C]
+        gt2 = _dgrad(gh, block.conv2._weight_matrix()[1], block.conv2._weight_matrix_t)         # [T, C]
         del gh
         gt1, dgam, dbet = ops.ln_backward_raw(gt2, t1.view(T, C), mean, rstd, g32, ctx.small)
         del gt2

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sei_gemm_bf16_tn_gelu_dual": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _vp]),
     "sei_gemm_bf16_tn_mul": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_gemm_bf16_tn_rowscaled_bias": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _ll, _ll, _ll, _vp]),
+    "sei_gemm_bf16_nn": (C.c_int, [_vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_gemm_bf16_tn_residual": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f, _ll, _i, _i, _ll, _ll, _ll, _ll, _vp]),
     "sei_ln_cl_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "sei_ln_cl_backward_workspace_bytes": (C.c_longlong, [_i]),

@@ -403,6 +403,29 @@ def gemm_bf16_tn(a, b, bias=None, out_dtype=torch.bfloat16, tile_n=0):
     return d
 
 
+def gemm_nn_supported(M, N):
+    """shapes sei_gemm_bf16_nn takes (the CTA-pair kernel)"""
+    return M >= 256 and N >= 256 and N % 8 == 0
+
+
+def gemm_bf16_nn(a, bkn, mult=None):
+    """D[M,N] (bf16) = a[M,K] @ bkn[K,N] (* mult[M,N]) with bkn read in place (MN-major operand of the CTA-pair kernel,
+    sei_gemm_bf16_nn): the input gradient of a pointwise convolution straight from its weight matrix"""
+    _check_2d_bf16("gemm_bf16_nn", a=a, bkn=bkn)
+    M, K = a.shape
+    K2, N = bkn.shape
+    if K != K2 or (mult is not None and tuple(mult.shape) != (M, N)):
+        raise SeiError("gemm_bf16_nn: shape mismatch")
+    if mult is not None:
+        _check_2d_bf16("gemm_bf16_nn", mult=mult)
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _FLOPS[0] += 2.0 * M * N * K
+    with torch.cuda.device(a.device):
+        check(_lib.load().sei_gemm_bf16_nn(_ptr(a), _ptr(bkn), _ptr(mult), _ptr(d), M, N, K, a.stride(0), bkn.stride(0), N,
+                                           0 if mult is None else mult.stride(0), _stream(a)))
+    return d
+
+
 def gemm_bf16_tn_rowscaled_bias(a, b, bias, row_scale):
     """D[M,N] (bf16) = a @ b^T + bias[n] * row_scale[m % len(row_scale)] (sei_gemm_bf16_tn_rowscaled_bias)"""
     _check_2d_bf16("gemm_bf16_tn_rowscaled_bias", a=a, b=b)

@@ -496,3 +496,22 @@ def test_gemm_rowscaled_bias(dev, M, N, K, period):
     d = ops.gemm_bf16_tn_rowscaled_bias(a, b, bias, rs)
     ref = a.float() @ b.float().t() + rs.repeat(-(-M // period))[:M, None] * bias[None, :]
     assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (300, 264, 72), (4100, 2048, 520), (8192, 512, 2048)])
+def test_gemm_nn_reads_the_weight_in_place(dev, M, N, K):
+    """D = A B with B [K, N] row-major read in place as an MN-major operand of the CTA-pair kernel (the input gradient of a
+    pointwise convolution without a transposed weight copy), plain and with the multiplier epilogue, vs fp32"""
+    from sei_b200 import ops, last_kernel
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()
+    mult = torch.randn(M, N, device=dev).bfloat16()
+    ref = a.float() @ b.float()
+    d = ops.gemm_bf16_nn(a, b)
+    assert last_kernel() == "gemm_bf16_tn_2cta_kernel"
+    assert rel_err(d.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
+    assert torch.equal(d, ops.gemm_bf16_tn(a, b.t().contiguous()))          # same products, same accumulation order
+    dm = ops.gemm_bf16_nn(a, b, mult)
+    assert rel_err(dm.float().cpu().numpy(), (ref * mult.float()).cpu().numpy()) < 6e-3
