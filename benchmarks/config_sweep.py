@@ -23,6 +23,7 @@ CONFIGS = [
     ("cfg2 deblur Gaussian_R2 proposed 256 b32", "deblurring", "Gaussian_R2", None, "proposed", "Scaling_Transforms", 256, 32),
     ("cfg3 SR x2 proposed 256 b8/GPU", "sr", None, 2, "proposed", "Scaling_Transforms", 256, 8),
     ("cfg4 SR x4 proposed 256 b2", "sr", None, 4, "proposed", "Scaling_Transforms", 256, 2),
+    ("cfg4 SR x4 proposed 256 b8", "sr", None, 4, "proposed", "Scaling_Transforms", 256, 8),
     ("cfg4 deblur Box_R3 proposed 256 b32", "deblurring", "Box_R3", None, "proposed", "Scaling_Transforms", 256, 32),
     ("cfg5 supervised 512 b16", "deblurring", "Gaussian_R2", None, "supervised", "Scaling_Transforms", 512, 16),
     ("cfg5 css 512 b16", "deblurring", "Gaussian_R2", None, "css", "Scaling_Transforms", 512, 16),
