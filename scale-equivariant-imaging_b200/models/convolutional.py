@@ -3,17 +3,23 @@ tcgen05 tensor cores.
 
 Same module tree and parameter names as the reference's ConvolutionalModel, so its state dicts load
 unchanged.  What differs is where the arithmetic runs:
-  * every 1x1 convolution (ConvBlock.conv2 / conv3, Downsample.conv, Upsample.seq[2]) and, through an
-    unfold, the two 3x3 in/out convolutions are ONE kernel, sei_gemm_bf16_tn (bf16 operands, fp32
-    accumulation in TMEM), on channels-last activations: pixels x C_in  @  (C_out x C_in)^T.  dgrad and
-    wgrad call the same kernel with the operand roles permuted;
-  * activations travel through the network in bf16, channels-last; parameters stay fp32 masters and are
-    cast once per optimizer step;
+  * every 1x1 convolution (ConvBlock.conv2 / conv3, Downsample.conv, Upsample.seq[2]) is the tcgen05 GEMM
+    (sei_gemm_bf16_tn and its fused-epilogue forms: bf16 operands, fp32 accumulation in TMEM) on channels-last
+    activations: pixels x C_in  @  (C_out x C_in)^T.  The input gradient of the deep layers reads the weight matrix in
+    place (sei_gemm_bf16_nn), the weight gradient reads both operands in place (sei_gemm_bf16_atb) and is added straight
+    into the parameter's gradient buffer;
+  * the two 3x3 edge convolutions (UNet.in_conv / out_conv) are implicit GEMMs on tcgen05 (sei_conv3x3_igemm_bf16:
+    nine TMA windows with zero fill as the K-chunks of the A operand, no unfolded copy);
+  * a ConvBlock is ONE autograd node (_ConvBlockFn): residual in conv3's epilogue, gelu / gelu' from conv2's epilogue at
+    the deep levels, the GELU backward as a multiplier epilogue of conv3's input gradient, the incoming gradient added in
+    the store of the depthwise input-gradient kernel; UNet's inner-residual and skip additions ride in GEMM epilogues too;
+  * activations travel through the network in bf16, channels-last; parameters stay fp32 masters whose bf16 copies are
+    rewritten by the optimizer kernel in the pass that updates them;
   * the FFT "ideal" resamplers (including the reference's quirks: fftshift applied to the half-spectrum axis,
     ifftshift results discarded) are applied as the explicit linear operators they are, by two batched
     tensor-core products per call (models/resample.py, csrc/bgemm.cu) -- no cuFFT, no layout copies;
-  * depthwise 7x7, channel LayerNorm, GELU and the output 3x3 convolution are hand-written kernels as well
-    (csrc/cnn_elem.cu).
+  * depthwise 7x7 (TMA-staged halo tiles, csrc/dwconv_tile.cu), channel LayerNorm, GELU and the reductions behind the bias /
+    gamma / beta gradients are hand-written kernels as well (csrc/cnn_elem.cu).
 
 There is no library fallback: a CPU tensor, a dtype other than bf16 activations or a missing libsei_b200.so raises
 SeiError.  Channel counts the vectorised kernels do not take (3-channel layers of the SR / no-in-out-conv variants) are
