@@ -270,3 +270,43 @@ def test_adam_host_logic():
     other = torch.optim.SGD([w], lr=0.1)
     other.step()                                      # a foreign optimizer touched w: the maintained flag is dropped
     assert optim.shadow_epoch(w) is not None
+
+
+def test_igemm_weight_chunks_reproduce_the_convolution():
+    """the chunk form the implicit-GEMM kernel reads ([tap * blocks + block][n][8], zero padded): contracting it with the
+    shifted, zero-padded windows (what the nine TMA copies deliver) is F.conv2d(padding=1)"""
+    import torch.nn.functional as F
+    from sei_b200 import ops
+    torch.manual_seed(0)
+    for cin, cinp, cout, nout in ((3, 8, 32, 32), (32, 32, 3, 16)):
+        w = torch.randn(cout, cin, 3, 3)
+        x = torch.randn(2, cin, 9, 11)
+        wg = ops.igemm_weight_chunks(w, cinp, nout).float()                  # bf16-rounded weights
+        cch = cinp // 8
+        assert wg.shape == (((9 * cch + 1) // 2) * 2, nout, 8)
+        xp = F.pad(F.pad(x, (0, 0, 0, 0, 0, cinp - cin)), (1, 1, 1, 1))      # channel padding, then the 'same' halo
+        out = torch.zeros(2, nout, 9, 11)
+        for tap in range(9):
+            ky, kx = divmod(tap, 3)
+            win = xp[:, :, ky:ky + 9, kx:kx + 11]                            # the window of this tap
+            for blk in range(cch):
+                out += torch.einsum("bchw,nc->bnhw", win[:, 8 * blk:8 * blk + 8], wg[tap * cch + blk])
+        ref = F.conv2d(x, w.bfloat16().float(), padding=1)
+        assert torch.allclose(out[:, :cout], ref, atol=1e-4) and float(out[:, cout:].abs().max() if nout > cout else 0) == 0.0
+        assert float(wg[9 * cch:].abs().max() if wg.shape[0] > 9 * cch else 0) == 0.0
+
+
+def test_convblock_is_one_completion_group():
+    """a ConvBlock runs as one autograd node, so the data-parallel reducer must treat it as one bucket however large it is
+    (its children are never called as modules: hooks on them would never fire)"""
+    import models.convolutional as mc
+    from sei_b200 import parallel
+    net = mc.ConvolutionalModel(in_channels=3, upsampling_rate=1, residual=True, inner_residual=True, num_conv_blocks=1,
+                                hidden_channels=8, inout_convs=True, scales=3)
+    groups = parallel.completion_groups(net, max_elems=64)                   # smaller than any block
+    blocks = [m for m in net.modules() if isinstance(m, mc.ConvBlock)]
+    assert all(any(g is b for g in groups) for b in blocks)
+    inner = {id(m) for b in blocks for m in b.modules() if m is not b}
+    assert not any(id(g) in inner for g in groups)
+    seen = [id(p) for g in groups for p in g.parameters()]
+    assert len(seen) == len(set(seen)) == len(list(net.parameters()))         # a partition of the parameters
